@@ -1,0 +1,136 @@
+/* kzp_b200 — C ABI of the B200-native Groth16/BN254 prover (libkzp_b200.so).
+ *
+ * Plain pointers and sizes only; no C++ or torch types. Two layers:
+ *
+ *  (1) The prover object. Same life cycle and error behaviour as the reference's C++ boundary class
+ *      FullProver (rust-rapidsnark/rapidsnark/src/fullprover.hpp:54-64, fullprover.cpp:80-125,204-250):
+ *      construct from a zkey path (never fails hard: the state says why it is unusable), prove from a
+ *      .wtns path, get a malloc'd compact proof JSON plus prover_time in ms. The reference binds that
+ *      class through bindgen (rust-rapidsnark/build.rs:183-206, src/lib.rs:41-106); the same mangled C++
+ *      symbols are ALSO exported by this library (include/fullprover_b200.hpp), so either binding works.
+ *      INTEGRATION.md shows both.
+ *
+ *  (2) Component entry points used by the parity tests and the micro-benchmarks: Fr NTT
+ *      (FFT<Fr>::fft/ifft, fft.cpp:192-246), G1/G2 MSM (Curve::multiMulByScalar, curve.hpp:209-215 ->
+ *      multiexp.cpp:183-245), raw field and group operations (fr.hpp:206-281, curve.cpp), all with host
+ *      buffers in the reference's own byte layouts.
+ *
+ * Every function returns 0 on success unless stated otherwise; on failure kzp_last_error() (thread-local)
+ * describes the problem. Nothing here falls back to the CPU: without a CUDA device every compute entry
+ * point fails with KZP_ERR_CUDA.
+ */
+#ifndef KZP_B200_H
+#define KZP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------------- */
+#define KZP_OK 0
+#define KZP_ERR_CUDA 1     /* no device, launch failure, out of memory */
+#define KZP_ERR_FORMAT 2   /* malformed zkey/wtns, wrong curve, bad arguments */
+#define KZP_ERR_IO 3       /* open/fstat/mmap failure */
+#define KZP_ERR_STATE 4    /* prover not ready / call order */
+
+/* FullProverState (fullprover.hpp:11-16) */
+#define KZP_STATE_OK 0
+#define KZP_STATE_ZKEY_FILE_LOAD_ERROR 1
+#define KZP_STATE_UNSUPPORTED_ZKEY_CURVE 2
+/* ProverResponseType (fullprover.hpp:5-9) */
+#define KZP_RESPONSE_SUCCESS 0
+#define KZP_RESPONSE_ERROR 1
+/* ProverError (fullprover.hpp:18-24) */
+#define KZP_PROVER_ERROR_NONE 0
+#define KZP_PROVER_ERROR_NOT_READY 1
+#define KZP_PROVER_ERROR_INVALID_INPUT 2
+#define KZP_PROVER_ERROR_WITNESS_GENERATION_INVALID_CURVE 3
+
+const char* kzp_last_error(void);
+int         kzp_device_count(void); /* number of CUDA devices visible, 0 if none / no driver */
+const char* kzp_version(void);
+void        kzp_free(void* p);      /* frees buffers returned by this library (malloc family) */
+
+/* ---- (1) prover --------------------------------------------------------------------------------- */
+typedef struct kzp_prover kzp_prover;
+
+/* FullProver::FullProver(const char*) — fullprover.cpp:80-101. Always returns a handle (NULL only when
+ * out of host memory); *state_out receives a KZP_STATE_* value. device < 0 selects $KZP_DEVICE or 0. */
+kzp_prover* kzp_prover_new(const char* zkey_path, int device, int* state_out);
+/* MSM base ranges of shard `rank` of `world` only; used one process per GPU. */
+kzp_prover* kzp_prover_new_sharded(const char* zkey_path, int device, int rank, int world, int* state_out);
+void        kzp_prover_free(kzp_prover* p); /* FullProver::~FullProver */
+
+/* FullProver::prove(const char* wtnsPath) — fullprover.cpp:114-125,204-250.
+ * Returns KZP_RESPONSE_*; *json_out is malloc'd (kzp_free) on success, NULL otherwise; *error_out is a
+ * KZP_PROVER_ERROR_*; *prover_time_ms covers witness upload + GPU work + proof JSON, like the reference's
+ * metrics.prover_time (file mapping excluded). r32/s32: optional fixed blinding scalars (32-byte LE,
+ * canonical); pass NULL for fresh randomness (groth16.cpp:296-316). */
+int kzp_prover_prove(kzp_prover* p, const char* wtns_path, const uint8_t* r32, const uint8_t* s32,
+                     char** json_out, int* error_out, int* prover_time_ms);
+/* Additive entry: witness values already in memory, n x 32-byte LE canonical. */
+int kzp_prover_prove_mem(kzp_prover* p, const uint8_t* witness, uint64_t n, const uint8_t* r32,
+                         const uint8_t* s32, char** json_out, int* error_out, int* prover_time_ms);
+
+/* Split life cycle, used by bench.py and by the sharded (one process per GPU) mode. */
+int kzp_prover_upload_witness(kzp_prover* p, const uint8_t* witness, uint64_t n);
+int kzp_prover_upload_witness_file(kzp_prover* p, const char* wtns_path);
+int kzp_prover_run_gpu(kzp_prover* p);                         /* all kernels, result = this shard's partials */
+#define KZP_PARTIALS_BYTES 768                                 /* A,B1,C,H as XYZZ (4x128) + B2 XYZZ (256) */
+int kzp_prover_get_partials(kzp_prover* p, uint8_t* out768);
+/* sum `count` shards' partials (count*768 bytes), blind and print */
+int kzp_prover_assemble(kzp_prover* p, const uint8_t* partials, int count, const uint8_t* r32,
+                        const uint8_t* s32, char** json_out);
+
+/* introspection */
+int kzp_prover_info(kzp_prover* p, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size,
+                    uint64_t* n_coefs, int* device);
+/* last proof: floats {h2d, spmv, ntt, msm_h, msm_a, msm_b1, msm_b2, msm_c, gpu, assemble_host, total_host,
+ * kernel_launches}; returns the number of values written (<= cap) */
+int kzp_prover_timings(kzp_prover* p, float* out, int cap);
+/* parity artefacts of the last proof */
+int kzp_prover_get_h(kzp_prover* p, uint8_t* out, uint64_t out_bytes);       /* domain x 32, canonical */
+int kzp_prover_keep_ab(kzp_prover* p, int on);
+int kzp_prover_get_ab(kzp_prover* p, uint8_t* out, uint64_t out_bytes);      /* 2 x domain x 32, Montgomery */
+int kzp_prover_get_msm_results(kzp_prover* p, uint8_t* out384);              /* A,B1,B2,C,H affine canonical */
+
+/* ---- (2) components ------------------------------------------------------------------------------ */
+/* FFT<Fr>::fft / ifft contract: n = 2^k Montgomery elements, natural order in and out, in place. */
+int kzp_fr_ntt(uint8_t* data, uint64_t n, int inverse, int device);
+/* The prover's H chain on one vector: ifft, multiply by w_2n^i, fft (groth16.cpp:172-203). */
+int kzp_fr_coset_chain(uint8_t* data, uint64_t n, int device);
+/* times `iters` coset chains on a device-resident vector of size 2^log_n; *ms_per_chain averaged */
+int kzp_fr_ntt_bench(uint32_t log_n, int iters, int device, float* ms_per_chain);
+
+typedef struct kzp_msm kzp_msm;
+/* group: 0 = G1 (64-byte bases), 1 = G2 (128-byte bases); bases affine Montgomery, (0,0) = infinity */
+kzp_msm* kzp_msm_new(int group, const uint8_t* bases, uint64_t n, int device);
+void     kzp_msm_free(kzp_msm* m);
+/* scalars: n x 32-byte LE integers; out: affine canonical LE (64 / 128 bytes), zeros for infinity */
+int kzp_msm_run(kzp_msm* m, const uint8_t* scalars, uint8_t* out);
+/* device-resident timing: uploads scalars once, runs `iters` MSMs, average ms; entries = non-zero digits */
+int kzp_msm_bench(kzp_msm* m, const uint8_t* scalars, int iters, float* ms_per_msm, uint64_t* entries);
+
+/* field: 0 Fr, 1 Fq, 2 Fq2 (64-byte elements); op: 0 mul 1 add 2 sub 3 neg 4 toMontgomery 5 fromMontgomery
+ * 6 square 7 inverse. Host buffers, `count` elements; b may be NULL for unary ops. */
+int kzp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t count,
+                 int device);
+/* group: 0 G1, 1 G2; op: 0 xyzz += affine, 1 xyzz += xyzz, 2 double. p/out XYZZ (128/256 B per point). */
+int kzp_point_op(int group, int op, const uint8_t* p, const uint8_t* q, uint8_t* out, uint64_t count,
+                 int device);
+/* integer-pipe roofline probe: independent 32x32+64 multiply-adds on every SM */
+int kzp_imad_peak(int iters, int device, float* ms, uint64_t* multiply_adds);
+
+/* host-only helpers (no GPU needed): decimal printing and file parsing, for the CPU test suite */
+int kzp_host_parse_zkey(const char* path, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size,
+                        uint64_t* n_coefs, int* state_out);
+int kzp_host_fq_decimal(const uint8_t* mont32, char* out, size_t cap);
+int kzp_host_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KZP_B200_H */

@@ -1,0 +1,356 @@
+"""keyless-zk-proofs_b200 — B200-native Groth16/BN254 prover behind rust-rapidsnark's FullProver boundary.
+
+This package is only the Python-side mirror of the reference's binding (rust-rapidsnark/src/lib.rs:41-106):
+a ctypes view of ``libkzp_b200.so`` (include/kzp_b200.h). All computation happens in the CUDA library; there
+is no CPU fallback and nothing here imports ``oracle/``. Import through ``keyless_zk_proofs_b200`` (the
+underscore alias at the repo root) or ``importlib.import_module("keyless-zk-proofs_b200")``.
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+import os
+from typing import Optional, Sequence, Tuple
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkzp_b200.so")
+
+PARTIALS_BYTES = 768
+
+
+class ProverInitError(Exception):
+    """Mirror of rust-rapidsnark's ProverInitError (src/lib.rs:17-22)."""
+
+
+class ZKeyFileLoadError(ProverInitError):
+    pass
+
+
+class UnsupportedZKeyCurve(ProverInitError):
+    pass
+
+
+class ProverError(Exception):
+    """Mirror of rust-rapidsnark's ProverError (src/lib.rs:24-33)."""
+
+
+class ProverNotReady(ProverError):
+    pass
+
+
+class InvalidInput(ProverError):
+    pass
+
+
+class WitnessGenerationInvalidCurve(ProverError):
+    pass
+
+
+class KzpError(RuntimeError):
+    """Component-level failure (status code + kzp_last_error())."""
+
+
+class Field(enum.IntEnum):
+    FR = 0
+    FQ = 1
+    FQ2 = 2
+
+
+class FieldOp(enum.IntEnum):
+    MUL = 0
+    ADD = 1
+    SUB = 2
+    NEG = 3
+    TO_MONTGOMERY = 4
+    FROM_MONTGOMERY = 5
+    SQUARE = 6
+    INVERSE = 7
+
+
+_lib = None
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    from importlib import util
+
+    spec = util.spec_from_file_location("_kzp_build", os.path.join(_HERE, "build.py"))
+    mod = util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force, verbose=verbose)
+
+
+def lib() -> ctypes.CDLL:
+    """Loads the CUDA library. Raises if it has not been built — there is no other implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libkzp_b200.so is missing: run `python keyless-zk-proofs_b200/build.py` (needs nvcc). "
+            "This package has no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    u8p, vp, i32p = c.c_char_p, c.c_void_p, c.POINTER(c.c_int)
+    sig = {
+        "kzp_last_error": (c.c_char_p, []),
+        "kzp_version": (c.c_char_p, []),
+        "kzp_device_count": (c.c_int, []),
+        "kzp_free": (None, [vp]),
+        "kzp_prover_new": (vp, [c.c_char_p, c.c_int, i32p]),
+        "kzp_prover_new_sharded": (vp, [c.c_char_p, c.c_int, c.c_int, c.c_int, i32p]),
+        "kzp_prover_free": (None, [vp]),
+        "kzp_prover_prove": (c.c_int, [vp, c.c_char_p, u8p, u8p, c.POINTER(vp), i32p, i32p]),
+        "kzp_prover_prove_mem": (c.c_int, [vp, u8p, c.c_uint64, u8p, u8p, c.POINTER(vp), i32p, i32p]),
+        "kzp_prover_upload_witness": (c.c_int, [vp, u8p, c.c_uint64]),
+        "kzp_prover_upload_witness_file": (c.c_int, [vp, c.c_char_p]),
+        "kzp_prover_run_gpu": (c.c_int, [vp]),
+        "kzp_prover_get_partials": (c.c_int, [vp, u8p]),
+        "kzp_prover_assemble": (c.c_int, [vp, u8p, c.c_int, u8p, u8p, c.POINTER(vp)]),
+        "kzp_prover_info": (c.c_int, [vp, c.POINTER(c.c_uint32), c.POINTER(c.c_uint32), c.POINTER(c.c_uint32),
+                                      c.POINTER(c.c_uint64), i32p]),
+        "kzp_prover_timings": (c.c_int, [vp, c.POINTER(c.c_float), c.c_int]),
+        "kzp_prover_get_h": (c.c_int, [vp, u8p, c.c_uint64]),
+        "kzp_prover_keep_ab": (c.c_int, [vp, c.c_int]),
+        "kzp_prover_get_ab": (c.c_int, [vp, u8p, c.c_uint64]),
+        "kzp_prover_get_msm_results": (c.c_int, [vp, u8p]),
+        "kzp_fr_ntt": (c.c_int, [u8p, c.c_uint64, c.c_int, c.c_int]),
+        "kzp_fr_coset_chain": (c.c_int, [u8p, c.c_uint64, c.c_int]),
+        "kzp_fr_ntt_bench": (c.c_int, [c.c_uint32, c.c_int, c.c_int, c.POINTER(c.c_float)]),
+        "kzp_msm_new": (vp, [c.c_int, u8p, c.c_uint64, c.c_int]),
+        "kzp_msm_free": (None, [vp]),
+        "kzp_msm_run": (c.c_int, [vp, u8p, u8p]),
+        "kzp_msm_bench": (c.c_int, [vp, u8p, c.c_int, c.POINTER(c.c_float), c.POINTER(c.c_uint64)]),
+        "kzp_field_op": (c.c_int, [c.c_int, c.c_int, u8p, u8p, u8p, c.c_uint64, c.c_int]),
+        "kzp_point_op": (c.c_int, [c.c_int, c.c_int, u8p, u8p, u8p, c.c_uint64, c.c_int]),
+        "kzp_imad_peak": (c.c_int, [c.c_int, c.c_int, c.POINTER(c.c_float), c.POINTER(c.c_uint64)]),
+        "kzp_host_parse_zkey": (c.c_int, [c.c_char_p, c.POINTER(c.c_uint32), c.POINTER(c.c_uint32),
+                                          c.POINTER(c.c_uint32), c.POINTER(c.c_uint64), i32p]),
+        "kzp_host_fq_decimal": (c.c_int, [u8p, c.c_char_p, c.c_size_t]),
+        "kzp_host_field_op": (c.c_int, [c.c_int, c.c_int, u8p, u8p, u8p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here means the library and the header disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = None  # filled lazily by exported_symbols()
+
+
+def last_error() -> str:
+    return (lib().kzp_last_error() or b"").decode()
+
+
+def device_count() -> int:
+    return lib().kzp_device_count()
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise KzpError("kzp status %d: %s" % (rc, last_error()))
+
+
+def _take_string(ptr: ctypes.c_void_p) -> str:
+    s = ctypes.string_at(ptr).decode()
+    lib().kzp_free(ptr)
+    return s
+
+
+TIMING_KEYS = ("h2d_ms", "spmv_ms", "ntt_ms", "msm_h_ms", "msm_a_ms", "msm_b1_ms", "msm_b2_ms", "msm_c_ms",
+               "gpu_ms", "assemble_host_ms", "total_host_ms", "kernel_launches")
+
+
+class FullProver:
+    """Python mirror of ``rust_rapidsnark::FullProver`` (rust-rapidsnark/src/lib.rs:41-106).
+
+    ``FullProver(zkey_path)`` raises ZKeyFileLoadError / UnsupportedZKeyCurve exactly where the Rust
+    ``FullProver::new`` returns those errors; ``prove(wtns_path)`` returns ``(proof_json, metrics)`` where
+    ``metrics["prover_time"]`` is in milliseconds, and raises the ProverError variants of the Rust binding.
+    """
+
+    def __init__(self, zkey_path: str, device: int = -1, shard: Optional[Tuple[int, int]] = None):
+        L = lib()
+        st = ctypes.c_int(0)
+        if shard is None:
+            self._h = L.kzp_prover_new(os.fsencode(zkey_path), device, ctypes.byref(st))
+        else:
+            self._h = L.kzp_prover_new_sharded(os.fsencode(zkey_path), device, shard[0], shard[1], ctypes.byref(st))
+        self.state = st.value
+        if self.state != 0:
+            msg = last_error()
+            h, self._h = self._h, None
+            L.kzp_prover_free(h)
+            if self.state == 1:
+                raise ZKeyFileLoadError(msg)
+            raise UnsupportedZKeyCurve(msg)
+        nv, npub, dom = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        nc, dev = ctypes.c_uint64(), ctypes.c_int()
+        _check(L.kzp_prover_info(self._h, ctypes.byref(nv), ctypes.byref(npub), ctypes.byref(dom), ctypes.byref(nc),
+                                 ctypes.byref(dev)))
+        self.n_vars, self.n_public, self.domain_size = nv.value, npub.value, dom.value
+        self.n_coefs, self.device = nc.value, dev.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().kzp_prover_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @staticmethod
+    def _raise_prover_error(err: int):
+        msg = last_error()
+        if err == 1:
+            raise ProverNotReady(msg)
+        if err == 3:
+            raise WitnessGenerationInvalidCurve(msg)
+        raise InvalidInput(msg)
+
+    def prove(self, wtns_path: str, r: Optional[bytes] = None, s: Optional[bytes] = None):
+        out, err, ms = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int()
+        rc = lib().kzp_prover_prove(self._h, os.fsencode(wtns_path), r, s, ctypes.byref(out), ctypes.byref(err),
+                                    ctypes.byref(ms))
+        if rc != 0:
+            self._raise_prover_error(err.value)
+        return _take_string(out), {"prover_time": ms.value}
+
+    def prove_mem(self, witness: bytes, r: Optional[bytes] = None, s: Optional[bytes] = None):
+        out, err, ms = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int()
+        rc = lib().kzp_prover_prove_mem(self._h, witness, len(witness) // 32, r, s, ctypes.byref(out),
+                                        ctypes.byref(err), ctypes.byref(ms))
+        if rc != 0:
+            self._raise_prover_error(err.value)
+        return _take_string(out), {"prover_time": ms.value}
+
+    # ---- split life cycle (bench, sharded mode)
+    def upload_witness(self, witness: bytes):
+        _check(lib().kzp_prover_upload_witness(self._h, witness, len(witness) // 32))
+
+    def upload_witness_file(self, path: str):
+        _check(lib().kzp_prover_upload_witness_file(self._h, os.fsencode(path)))
+
+    def run_gpu(self):
+        _check(lib().kzp_prover_run_gpu(self._h))
+
+    def partials(self) -> bytes:
+        buf = ctypes.create_string_buffer(PARTIALS_BYTES)
+        _check(lib().kzp_prover_get_partials(self._h, buf))
+        return buf.raw
+
+    def assemble(self, partials: Sequence[bytes], r: Optional[bytes] = None, s: Optional[bytes] = None) -> str:
+        blob = b"".join(partials)
+        out = ctypes.c_void_p()
+        _check(lib().kzp_prover_assemble(self._h, blob, len(partials), r, s, ctypes.byref(out)))
+        return _take_string(out)
+
+    # ---- parity artefacts / diagnostics
+    def timings(self) -> dict:
+        arr = (ctypes.c_float * 12)()
+        n = lib().kzp_prover_timings(self._h, arr, 12)
+        return {k: float(arr[i]) for i, k in enumerate(TIMING_KEYS[:n])}
+
+    def h_coefficients(self) -> bytes:
+        buf = ctypes.create_string_buffer(self.domain_size * 32)
+        _check(lib().kzp_prover_get_h(self._h, buf, len(buf)))
+        return buf.raw
+
+    def keep_ab(self, on: bool = True):
+        _check(lib().kzp_prover_keep_ab(self._h, 1 if on else 0))
+
+    def ab(self) -> bytes:
+        buf = ctypes.create_string_buffer(self.domain_size * 64)
+        _check(lib().kzp_prover_get_ab(self._h, buf, len(buf)))
+        return buf.raw
+
+    def msm_results(self) -> bytes:
+        buf = ctypes.create_string_buffer(384)
+        _check(lib().kzp_prover_get_msm_results(self._h, buf))
+        return buf.raw
+
+
+# ---- component wrappers ------------------------------------------------------------------------------------
+def fr_ntt(data: bytes, inverse: bool = False, device: int = -1) -> bytes:
+    """FFT<Fr>::fft / ifft (fft.cpp:192-246): Montgomery elements, natural order in and out."""
+    buf = ctypes.create_string_buffer(data, len(data))
+    _check(lib().kzp_fr_ntt(buf, len(data) // 32, 1 if inverse else 0, device))
+    return buf.raw
+
+
+def fr_coset_chain(data: bytes, device: int = -1) -> bytes:
+    buf = ctypes.create_string_buffer(data, len(data))
+    _check(lib().kzp_fr_coset_chain(buf, len(data) // 32, device))
+    return buf.raw
+
+
+def fr_ntt_bench(log_n: int, iters: int = 10, device: int = -1) -> float:
+    ms = ctypes.c_float()
+    _check(lib().kzp_fr_ntt_bench(log_n, iters, device, ctypes.byref(ms)))
+    return ms.value
+
+
+class Msm:
+    """Curve::multiMulByScalar (curve.hpp:209-215) with the bases resident on the GPU."""
+
+    def __init__(self, group: int, bases: bytes, device: int = -1):
+        self.group = group
+        self.point_bytes = 64 if group == 0 else 128
+        self.n = len(bases) // self.point_bytes
+        self._h = lib().kzp_msm_new(group, bases, self.n, device)
+        if not self._h:
+            raise KzpError("kzp_msm_new failed: " + last_error())
+
+    def run(self, scalars: bytes) -> bytes:
+        assert len(scalars) == self.n * 32
+        out = ctypes.create_string_buffer(self.point_bytes)
+        _check(lib().kzp_msm_run(self._h, scalars, out))
+        return out.raw
+
+    def bench(self, scalars: bytes, iters: int = 5):
+        ms, ent = ctypes.c_float(), ctypes.c_uint64()
+        _check(lib().kzp_msm_bench(self._h, scalars, iters, ctypes.byref(ms), ctypes.byref(ent)))
+        return ms.value, ent.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().kzp_msm_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def field_op(field: int, op: int, a: bytes, b: Optional[bytes] = None, device: int = -1) -> bytes:
+    esz = 64 if field == 2 else 32
+    out = ctypes.create_string_buffer(len(a))
+    _check(lib().kzp_field_op(int(field), int(op), a, b, out, len(a) // esz, device))
+    return out.raw
+
+
+def point_op(group: int, op: int, p: bytes, q: Optional[bytes] = None, device: int = -1) -> bytes:
+    psz = 128 if group == 0 else 256
+    out = ctypes.create_string_buffer(len(p))
+    _check(lib().kzp_point_op(group, op, p, q, out, len(p) // psz, device))
+    return out.raw
+
+
+def imad_peak(iters: int = 4096, device: int = -1):
+    """Returns (multiply-adds per second, ms) of the dependent-free IMAD.WIDE probe."""
+    ms, n = ctypes.c_float(), ctypes.c_uint64()
+    _check(lib().kzp_imad_peak(iters, device, ctypes.byref(ms), ctypes.byref(n)))
+    return n.value / (ms.value * 1e-3), ms.value

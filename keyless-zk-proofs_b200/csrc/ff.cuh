@@ -1,0 +1,465 @@
+// BN254 prime-field arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form with R = 2^256.
+//
+// Byte layout of an element is identical to the reference's FrRawElement / FqRawElement
+// (4 x u64 little-endian limbs, rust-rapidsnark/rapidsnark/src/fr_element.hpp:6-13), so zkey
+// sections and witness values are consumed without conversion. Semantics follow the reference
+// raw API (fr_raw_generic.cpp:11-39,68-80,107-148,192-232): every result is canonical (< p).
+//
+// Device path: the Montgomery product is a word-serial (CIOS) loop whose multiply-accumulates are
+// written as mad.lo.cc / madc.hi.cc carry chains over an even-aligned and an odd-aligned
+// accumulator, so ptxas can pair each lo/hi couple into one IMAD.WIDE.U32 with carry; 16 wide
+// multiplies for a*b_i, 16 for m*p and one IMAD for m per limb of b (136 per product).
+// Host path (same templates, used by the host-side proof assembly and by tests): portable
+// 64-bit C++.
+#pragma once
+
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define KZP_HD __host__ __device__ __forceinline__
+#define KZP_D __device__ __forceinline__
+#else
+#define KZP_HD inline
+#define KZP_D inline
+#endif
+
+namespace kzp
+{
+
+// ------------------------------------------------------------------ parameters
+// Constants: fr_raw_generic.cpp:5-7 / fq_raw_generic.cpp:6-8 (q, R^2, -p^-1), re-split in 32-bit limbs.
+struct FrParams
+{
+    static constexpr uint32_t P0 = 0xf0000001u, P1 = 0x43e1f593u, P2 = 0x79b97091u, P3 = 0x2833e848u,
+                              P4 = 0x8181585du, P5 = 0xb85045b6u, P6 = 0xe131a029u, P7 = 0x30644e72u;
+    static constexpr uint32_t NP0 = 0xefffffffu; // -p^-1 mod 2^32
+    static constexpr uint32_t R1[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                                       0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    static constexpr uint32_t R2[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                                       0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+};
+
+struct FqParams
+{
+    static constexpr uint32_t P0 = 0xd87cfd47u, P1 = 0x3c208c16u, P2 = 0x6871ca8du, P3 = 0x97816a91u,
+                              P4 = 0x8181585du, P5 = 0xb85045b6u, P6 = 0xe131a029u, P7 = 0x30644e72u;
+    static constexpr uint32_t NP0 = 0xe4866389u;
+    static constexpr uint32_t R1[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                                       0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    static constexpr uint32_t R2[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                                       0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+};
+
+template <class P>
+KZP_HD uint32_t modulus_limb(int i)
+{
+    switch (i)
+    {
+    case 0: return P::P0;
+    case 1: return P::P1;
+    case 2: return P::P2;
+    case 3: return P::P3;
+    case 4: return P::P4;
+    case 5: return P::P5;
+    case 6: return P::P6;
+    default: return P::P7;
+    }
+}
+
+// ------------------------------------------------------------------ element
+template <class P>
+struct alignas(16) Fp
+{
+    uint32_t v[8];
+
+    typedef P Params;
+
+    static KZP_HD Fp zero()
+    {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            r.v[i] = 0;
+        return r;
+    }
+
+    // Montgomery representation of 1 (R mod p)
+    static KZP_HD Fp one()
+    {
+        Fp r;
+        r.v[0] = P::R1[0]; r.v[1] = P::R1[1]; r.v[2] = P::R1[2]; r.v[3] = P::R1[3];
+        r.v[4] = P::R1[4]; r.v[5] = P::R1[5]; r.v[6] = P::R1[6]; r.v[7] = P::R1[7];
+        return r;
+    }
+
+    static KZP_HD Fp r2()
+    {
+        Fp r;
+        r.v[0] = P::R2[0]; r.v[1] = P::R2[1]; r.v[2] = P::R2[2]; r.v[3] = P::R2[3];
+        r.v[4] = P::R2[4]; r.v[5] = P::R2[5]; r.v[6] = P::R2[6]; r.v[7] = P::R2[7];
+        return r;
+    }
+
+    static KZP_HD bool is_zero(const Fp& a)
+    {
+        uint32_t t = a.v[0] | a.v[1] | a.v[2] | a.v[3] | a.v[4] | a.v[5] | a.v[6] | a.v[7];
+        return t == 0;
+    }
+
+    static KZP_HD bool eq(const Fp& a, const Fp& b)
+    {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            t |= a.v[i] ^ b.v[i];
+        return t == 0;
+    }
+
+    // a >= p ?
+    static KZP_HD bool geq_p(const Fp& a)
+    {
+#pragma unroll
+        for (int i = 7; i >= 0; i--)
+        {
+            uint32_t pi = modulus_limb<P>(i);
+            if (a.v[i] > pi)
+                return true;
+            if (a.v[i] < pi)
+                return false;
+        }
+        return true;
+    }
+
+    // ---------------------------------------------------------------- add / sub / neg
+    // r = a + b mod p (Fr_rawAdd: fr_raw_generic.cpp:11-22). Inputs canonical -> no 2^256 overflow.
+    static KZP_HD void add(Fp& r, const Fp& a, const Fp& b)
+    {
+#if defined(__CUDA_ARCH__)
+        uint32_t s0, s1, s2, s3, s4, s5, s6, s7, t0, t1, t2, t3, t4, t5, t6, t7, bw;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
+              "r"(a.v[6]), "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]),
+              "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7),
+              "=r"(bw)
+            : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7), "r"(P::P0),
+              "r"(P::P1), "r"(P::P2), "r"(P::P3), "r"(P::P4), "r"(P::P5), "r"(P::P6), "r"(P::P7));
+        bool keep = (bw != 0); // borrow -> sum < p -> keep the plain sum
+        r.v[0] = keep ? s0 : t0; r.v[1] = keep ? s1 : t1; r.v[2] = keep ? s2 : t2;
+        r.v[3] = keep ? s3 : t3; r.v[4] = keep ? s4 : t4; r.v[5] = keep ? s5 : t5;
+        r.v[6] = keep ? s6 : t6; r.v[7] = keep ? s7 : t7;
+#else
+        uint32_t s[8], t[8];
+        uint64_t c = 0;
+        for (int i = 0; i < 8; i++)
+        {
+            c += (uint64_t)a.v[i] + b.v[i];
+            s[i] = (uint32_t)c;
+            c >>= 32;
+        }
+        int64_t bw = 0;
+        for (int i = 0; i < 8; i++)
+        {
+            bw += (int64_t)s[i] - (int64_t)modulus_limb<P>(i);
+            t[i] = (uint32_t)bw;
+            bw >>= 32;
+        }
+        for (int i = 0; i < 8; i++)
+            r.v[i] = bw ? s[i] : t[i];
+#endif
+    }
+
+    // r = a - b mod p (Fr_rawSub: fr_raw_generic.cpp:24-32)
+    static KZP_HD void sub(Fp& r, const Fp& a, const Fp& b)
+    {
+#if defined(__CUDA_ARCH__)
+        uint32_t s0, s1, s2, s3, s4, s5, s6, s7, bw;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7),
+              "=r"(bw)
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
+              "r"(a.v[6]), "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]),
+              "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+        // bw = 0xffffffff when a < b: add p back
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;"
+            : "+r"(s0), "+r"(s1), "+r"(s2), "+r"(s3), "+r"(s4), "+r"(s5), "+r"(s6), "+r"(s7)
+            : "r"(P::P0 & bw), "r"(P::P1 & bw), "r"(P::P2 & bw), "r"(P::P3 & bw), "r"(P::P4 & bw),
+              "r"(P::P5 & bw), "r"(P::P6 & bw), "r"(P::P7 & bw));
+        r.v[0] = s0; r.v[1] = s1; r.v[2] = s2; r.v[3] = s3;
+        r.v[4] = s4; r.v[5] = s5; r.v[6] = s6; r.v[7] = s7;
+#else
+        uint32_t s[8];
+        int64_t  bw = 0;
+        for (int i = 0; i < 8; i++)
+        {
+            bw += (int64_t)a.v[i] - (int64_t)b.v[i];
+            s[i] = (uint32_t)bw;
+            bw >>= 32;
+        }
+        uint32_t mask = bw ? 0xffffffffu : 0u;
+        uint64_t c    = 0;
+        for (int i = 0; i < 8; i++)
+        {
+            c += (uint64_t)s[i] + (modulus_limb<P>(i) & mask);
+            r.v[i] = (uint32_t)c;
+            c >>= 32;
+        }
+#endif
+    }
+
+    // r = -a mod p, with -0 = 0 (Fr_rawNeg: fr_raw_generic.cpp:34-39)
+    static KZP_HD void neg(Fp& r, const Fp& a)
+    {
+        if (is_zero(a))
+        {
+            r = a;
+            return;
+        }
+        Fp z = zero();
+        sub(r, z, a);
+    }
+
+    static KZP_HD void dbl(Fp& r, const Fp& a) { add(r, a, a); }
+
+    // ---------------------------------------------------------------- Montgomery product
+#if defined(__CUDA_ARCH__)
+    // x0 += pend (carry into limb 1); y[k], k=0..7 (limb offsets 1..8) += {m1,m3,m5,m7} * b
+    static KZP_D void chain_odd_pend(uint32_t& x0, uint32_t pend, uint32_t (&y)[8], uint32_t m1,
+                                     uint32_t m3, uint32_t m5, uint32_t m7, uint32_t b)
+    {
+        asm("add.cc.u32 %0, %0, %9;\n\t"
+            "madc.lo.cc.u32 %1, %10, %14, %1;\n\t"
+            "madc.hi.cc.u32 %2, %10, %14, %2;\n\t"
+            "madc.lo.cc.u32 %3, %11, %14, %3;\n\t"
+            "madc.hi.cc.u32 %4, %11, %14, %4;\n\t"
+            "madc.lo.cc.u32 %5, %12, %14, %5;\n\t"
+            "madc.hi.cc.u32 %6, %12, %14, %6;\n\t"
+            "madc.lo.cc.u32 %7, %13, %14, %7;\n\t"
+            "madc.hi.u32 %8, %13, %14, %8;"
+            : "+r"(x0), "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]),
+              "+r"(y[6]), "+r"(y[7])
+            : "r"(pend), "r"(m1), "r"(m3), "r"(m5), "r"(m7), "r"(b));
+    }
+
+    // y[k] += {m1,m3,m5,m7} * b (no carry-in)
+    static KZP_D void chain_odd(uint32_t (&y)[8], uint32_t m1, uint32_t m3, uint32_t m5,
+                                uint32_t m7, uint32_t b)
+    {
+        asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+            "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+            "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+            "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+            "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+            "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+            "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+            "madc.hi.u32 %7, %11, %12, %7;"
+            : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]),
+              "+r"(y[7])
+            : "r"(m1), "r"(m3), "r"(m5), "r"(m7), "r"(b));
+    }
+
+    // x[k], k=0..7 (limb offsets 0..7) += {m0,m2,m4,m6} * b ; carry out of limb 7 goes to ytop (limb 8)
+    static KZP_D void chain_even(uint32_t (&x)[8], uint32_t& ytop, uint32_t m0, uint32_t m2,
+                                 uint32_t m4, uint32_t m6, uint32_t b)
+    {
+        asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+            "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32 %8, %8, 0;"
+            : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]),
+              "+r"(x[7]), "+r"(ytop)
+            : "r"(m0), "r"(m2), "r"(m4), "r"(m6), "r"(b));
+    }
+#endif
+
+    // r = a * b * R^-1 mod p, canonical (Fr_rawMMul: fr_raw_generic.cpp:107-148)
+    static KZP_HD void mul(Fp& r, const Fp& a, const Fp& b)
+    {
+#if defined(__CUDA_ARCH__)
+        // T = X + (Y << 32) + pend, X at limb offsets 0..7, Y at 1..8; T < 2^288 throughout.
+        uint32_t x[8], y[8], pend = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            x[i] = 0;
+            y[i] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            uint32_t bi = b.v[i];
+            chain_odd_pend(x[0], pend, y, a.v[1], a.v[3], a.v[5], a.v[7], bi);
+            chain_even(x, y[7], a.v[0], a.v[2], a.v[4], a.v[6], bi);
+            uint32_t m = x[0] * P::NP0;
+            chain_even(x, y[7], P::P0, P::P2, P::P4, P::P6, m);
+            chain_odd(y, P::P1, P::P3, P::P5, P::P7, m);
+            // divide by 2^32: x[0] == 0 now; x[1] lands on limb 0 (kept pending), the odd-aligned
+            // array becomes the even-aligned one and vice versa.
+            pend = x[1];
+            uint32_t t0 = y[0], t1 = y[1], t2 = y[2], t3 = y[3], t4 = y[4], t5 = y[5], t6 = y[6],
+                     t7 = y[7];
+            y[0] = x[2]; y[1] = x[3]; y[2] = x[4]; y[3] = x[5]; y[4] = x[6]; y[5] = x[7];
+            y[6] = 0; y[7] = 0;
+            x[0] = t0; x[1] = t1; x[2] = t2; x[3] = t3; x[4] = t4; x[5] = t5; x[6] = t6; x[7] = t7;
+        }
+        // merge: T = pend + X + (Y << 32)  (T < 2p < 2^255, so limb 8 is zero)
+        uint32_t s0, s1, s2, s3, s4, s5, s6, s7;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+            : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]),
+              "r"(x[7]), "r"(pend), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]),
+              "r"(y[5]), "r"(y[6]));
+        uint32_t t0, t1, t2, t3, t4, t5, t6, t7, bw;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7),
+              "=r"(bw)
+            : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7), "r"(P::P0),
+              "r"(P::P1), "r"(P::P2), "r"(P::P3), "r"(P::P4), "r"(P::P5), "r"(P::P6), "r"(P::P7));
+        bool keep = (bw != 0);
+        r.v[0] = keep ? s0 : t0; r.v[1] = keep ? s1 : t1; r.v[2] = keep ? s2 : t2;
+        r.v[3] = keep ? s3 : t3; r.v[4] = keep ? s4 : t4; r.v[5] = keep ? s5 : t5;
+        r.v[6] = keep ? s6 : t6; r.v[7] = keep ? s7 : t7;
+#else
+        // portable CIOS
+        uint32_t t[10];
+        for (int i = 0; i < 10; i++)
+            t[i] = 0;
+        for (int i = 0; i < 8; i++)
+        {
+            uint64_t c = 0;
+            for (int j = 0; j < 8; j++)
+            {
+                c += (uint64_t)a.v[j] * b.v[i] + t[j];
+                t[j] = (uint32_t)c;
+                c >>= 32;
+            }
+            c += t[8];
+            t[8] = (uint32_t)c;
+            t[9] = (uint32_t)(c >> 32);
+            uint32_t m = t[0] * P::NP0;
+            c          = ((uint64_t)m * modulus_limb<P>(0) + t[0]) >> 32;
+            for (int j = 1; j < 8; j++)
+            {
+                c += (uint64_t)m * modulus_limb<P>(j) + t[j];
+                t[j - 1] = (uint32_t)c;
+                c >>= 32;
+            }
+            c += t[8];
+            t[7] = (uint32_t)c;
+            t[8] = t[9] + (uint32_t)(c >> 32);
+        }
+        Fp s;
+        for (int i = 0; i < 8; i++)
+            s.v[i] = t[i];
+        if (t[8] || geq_p(s))
+        {
+            int64_t bw = 0;
+            for (int i = 0; i < 8; i++)
+            {
+                bw += (int64_t)s.v[i] - (int64_t)modulus_limb<P>(i);
+                s.v[i] = (uint32_t)bw;
+                bw >>= 32;
+            }
+        }
+        r = s;
+#endif
+    }
+
+    static KZP_HD void sqr(Fp& r, const Fp& a) { mul(r, a, a); }
+
+    // canonical integer -> Montgomery (Fr_rawToMontgomery: fr_raw_generic.cpp:192-196)
+    static KZP_HD void to_mont(Fp& r, const Fp& a)
+    {
+        Fp k = r2();
+        mul(r, a, k);
+    }
+
+    // Montgomery -> canonical integer (Fr_rawFromMontgomery: fr_raw_generic.cpp:198-232)
+    static KZP_HD void from_mont(Fp& r, const Fp& a)
+    {
+        Fp k = zero();
+        k.v[0] = 1;
+        mul(r, a, k);
+    }
+
+    // r = a^e (e given as 8 x 32-bit limbs, plain integer); Montgomery in/out.
+    static KZP_HD void pow(Fp& r, const Fp& a, const uint32_t (&e)[8])
+    {
+        Fp acc = one();
+        for (int i = 255; i >= 0; i--)
+        {
+            sqr(acc, acc);
+            if ((e[i >> 5] >> (i & 31)) & 1)
+                mul(acc, acc, a);
+        }
+        r = acc;
+    }
+
+    // r = a^-1 via Fermat (a^(p-2)); inverse of 0 is 0. Montgomery in/out.
+    static KZP_HD void inv(Fp& r, const Fp& a)
+    {
+        uint32_t e[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            e[i] = modulus_limb<P>(i);
+        e[0] -= 2; // p is odd and p0 >= 2 for both fields: no borrow
+        pow(r, a, e);
+    }
+};
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+} // namespace kzp

@@ -1,0 +1,394 @@
+// sm_100a kernels for the Groth16/BN254 hot path: SpMV, Fr NTT stages, pointwise H, and the Pippenger MSM
+// pipeline (signed digits -> counting sort -> chunked bucket accumulation -> bucket reduction).
+// All integer work on the IMAD/IADD3 pipes; no tensor cores (not a dense contraction).
+//
+// Reference functions these kernels replace (rust-rapidsnark/rapidsnark/src):
+//   spmv_abc        groth16.cpp:125-167      ntt_*        fft.cpp:192-246
+//   h_pointwise     groth16.cpp:266-275      msm_run      multiexp.cpp:183-245 (+ curve.cpp group law)
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "device.hpp"
+#include "hostff.hpp"
+
+namespace kzp
+{
+
+static inline unsigned int div_up(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }
+
+// =====================================================================================================
+// SpMV + pointwise
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+    k_spmv_abc(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ wire,
+               const Fr* __restrict__ coef, const Fr* __restrict__ w, Fr* __restrict__ a,
+               Fr* __restrict__ b, Fr* __restrict__ c, uint32_t n_rows)
+{
+    uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows)
+        return;
+    uint32_t e0 = row_ptr[2 * row], e1 = row_ptr[2 * row + 1], e2 = row_ptr[2 * row + 2];
+    Fr       sa = Fr::zero(), sb = Fr::zero(), t;
+    for (uint32_t e = e0; e < e1; e++)
+    {
+        Fr ws = w[wire[e]];
+        if (Fr::is_zero(ws))
+            continue;
+        Fr::mul(t, ws, coef[e]);
+        Fr::add(sa, sa, t);
+    }
+    for (uint32_t e = e1; e < e2; e++)
+    {
+        Fr ws = w[wire[e]];
+        if (Fr::is_zero(ws))
+            continue;
+        Fr::mul(t, ws, coef[e]);
+        Fr::add(sb, sb, t);
+    }
+    a[row] = sa;
+    b[row] = sb;
+    Fr::mul(t, sa, sb);
+    c[row] = t;
+}
+
+void spmv_abc(const CoefCsr& m, const Fr* w, Fr* a, Fr* b, Fr* c, cudaStream_t st)
+{
+    k_spmv_abc<<<div_up(m.n_rows, 256), 256, 0, st>>>(m.row_ptr, m.wire, m.coef, w, a, b, c, m.n_rows);
+    KZP_CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+    k_h_pointwise(const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c,
+                  Fr* __restrict__ h, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    Fr t;
+    Fr::mul(t, a[i], b[i]);
+    Fr::sub(t, t, c[i]);
+    Fr::from_mont(t, t);
+    h[i] = t;
+}
+
+void h_pointwise(const Fr* a, const Fr* b, const Fr* c, Fr* h, uint64_t n, cudaStream_t st)
+{
+    k_h_pointwise<<<div_up(n, 256), 256, 0, st>>>(a, b, c, h, n);
+    KZP_CUDA_CHECK(cudaGetLastError());
+}
+
+// =====================================================================================================
+// NTT (radix-2 stages in global memory; tiled shared-memory version lives in ntt_tiled.cuh)
+// =====================================================================================================
+// One decimation-in-frequency stage: (u, v) -> (u + v, (u - v) * w). half = 2^log_h.
+__global__ void __launch_bounds__(256)
+    k_ntt_dif_stage(Fr* __restrict__ x, const Fr* __restrict__ tw, uint32_t log_n, uint32_t log_h,
+                    const Fr* __restrict__ post)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (1ull << (log_n - 1)))
+        return;
+    uint64_t h  = 1ull << log_h;
+    uint64_t j  = t & (h - 1);
+    uint64_t i0 = ((t >> log_h) << (log_h + 1)) + j;
+    uint64_t i1 = i0 + h;
+    Fr       u = x[i0], v = x[i1], s, d;
+    Fr::add(s, u, v);
+    Fr::sub(d, u, v);
+    Fr wj = tw[j << (log_n - 1 - log_h)];
+    Fr::mul(d, d, wj);
+    if (post)
+    {
+        Fr::mul(s, s, post[i0]);
+        Fr::mul(d, d, post[i1]);
+    }
+    x[i0] = s;
+    x[i1] = d;
+}
+
+// One decimation-in-time stage: (u, v) -> (u + w v, u - w v).
+__global__ void __launch_bounds__(256)
+    k_ntt_dit_stage(Fr* __restrict__ x, const Fr* __restrict__ tw, uint32_t log_n, uint32_t log_h)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (1ull << (log_n - 1)))
+        return;
+    uint64_t h  = 1ull << log_h;
+    uint64_t j  = t & (h - 1);
+    uint64_t i0 = ((t >> log_h) << (log_h + 1)) + j;
+    uint64_t i1 = i0 + h;
+    Fr       u = x[i0], v = x[i1], s, d;
+    Fr wj = tw[j << (log_n - 1 - log_h)];
+    Fr::mul(v, v, wj);
+    Fr::add(s, u, v);
+    Fr::sub(d, u, v);
+    x[i0] = s;
+    x[i1] = d;
+}
+
+__global__ void __launch_bounds__(256) k_fr_scale(Fr* __restrict__ x, uint64_t n, Fr k, const Fr* __restrict__ kv)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    Fr t = x[i];
+    if (kv)
+        Fr::mul(t, t, kv[i]);
+    else
+        Fr::mul(t, t, k);
+    x[i] = t;
+}
+
+__global__ void __launch_bounds__(256) k_bitrev_permute(Fr* __restrict__ x, uint32_t log_n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1ull << log_n))
+        return;
+    uint64_t r = log_n ? (__brevll(i) >> (64 - log_n)) : 0;
+    if (i < r)
+    {
+        Fr t = x[i];
+        x[i] = x[r];
+        x[r] = t;
+    }
+}
+
+void ntt_bitrev_permute(Fr* x, uint32_t log_n, cudaStream_t st)
+{
+    k_bitrev_permute<<<div_up(1ull << log_n, 256), 256, 0, st>>>(x, log_n);
+    KZP_CUDA_CHECK(cudaGetLastError());
+}
+
+void fr_scale(Fr* x, uint64_t n, const Fr& k, cudaStream_t st)
+{
+    k_fr_scale<<<div_up(n, 256), 256, 0, st>>>(x, n, k, nullptr);
+    KZP_CUDA_CHECK(cudaGetLastError());
+}
+
+void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st)
+{
+    uint32_t log_n = d.log_n;
+    if (log_n == 0)
+    {
+        if (post)
+        {
+            k_fr_scale<<<1, 256, 0, st>>>(x, 1, Fr::zero(), post);
+            KZP_CUDA_CHECK(cudaGetLastError());
+        }
+        return;
+    }
+    unsigned int grid = div_up(1ull << (log_n - 1), 256);
+    for (int lh = (int)log_n - 1; lh >= 0; lh--)
+    {
+        k_ntt_dif_stage<<<grid, 256, 0, st>>>(x, d.tw_inv, log_n, (uint32_t)lh, lh == 0 ? post : nullptr);
+        KZP_CUDA_CHECK(cudaGetLastError());
+    }
+}
+
+void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st)
+{
+    uint32_t log_n = d.log_n;
+    if (log_n == 0)
+        return;
+    unsigned int grid = div_up(1ull << (log_n - 1), 256);
+    for (uint32_t lh = 0; lh < log_n; lh++)
+    {
+        k_ntt_dit_stage<<<grid, 256, 0, st>>>(x, d.tw_fwd, log_n, lh);
+        KZP_CUDA_CHECK(cudaGetLastError());
+    }
+}
+
+// ---- twiddle tables (host generated once per domain; fft.cpp:40-136 computes the same roots:
+//      w = nqr^((r-1)/2^s) with nqr = 5 the smallest non-residue)
+static HFr hfr_from_u64(uint64_t v)
+{
+    HFr t = HFr::zero();
+    t.v[0] = v;
+    HFr::to_mont(t, t);
+    return t;
+}
+
+static HFr hfr_root_of_unity(uint32_t log_n)
+{
+    // exponent (r - 1) >> log_n
+    uint64_t e[4];
+    for (int i = 0; i < 4; i++)
+        e[i] = HFr::p(i);
+    e[0] -= 1;
+    for (uint32_t s = 0; s < log_n; s++)
+    {
+        for (int i = 0; i < 4; i++)
+            e[i] = (e[i] >> 1) | (i < 3 ? (e[i + 1] << 63) : 0);
+    }
+    HFr g   = hfr_from_u64(5);
+    HFr acc = HFr::one();
+    for (int i = 255; i >= 0; i--)
+    {
+        HFr::sqr(acc, acc);
+        if ((e[i >> 6] >> (i & 63)) & 1)
+            HFr::mul(acc, acc, g);
+    }
+    return acc;
+}
+
+void ntt_domain_create(NttDomain& d, uint32_t log_n)
+{
+    if (log_n > 27) // Fr has 2-adicity 28 and the coset needs a 2^(log_n+1)-th root (fft.cpp:72-84)
+        throw CudaError("domain size too big for the curve");
+    d.log_n    = log_n;
+    uint64_t n = 1ull << log_n;
+    HFr      w = hfr_root_of_unity(log_n);
+    HFr      winv;
+    HFr::inv(winv, w);
+    HFr w2n  = hfr_root_of_unity(log_n + 1);
+    HFr ninv = hfr_from_u64(n);
+    HFr::inv(ninv, ninv);
+    memcpy(&d.n_inv, &ninv, 32);
+
+    uint64_t         half = n > 1 ? n / 2 : 1;
+    std::vector<HFr> fwd(half), inv(half), cos(n);
+    fwd[0] = HFr::one();
+    inv[0] = HFr::one();
+    for (uint64_t i = 1; i < half; i++)
+    {
+        HFr::mul(fwd[i], fwd[i - 1], w);
+        HFr::mul(inv[i], inv[i - 1], winv);
+    }
+    // coset_br[p] = w2n^bitrev(p) / n
+    std::vector<HFr> pw(n);
+    pw[0] = ninv;
+    for (uint64_t i = 1; i < n; i++)
+        HFr::mul(pw[i], pw[i - 1], w2n);
+    for (uint64_t p = 0; p < n; p++)
+    {
+        uint64_t r = 0;
+        for (uint32_t k = 0; k < log_n; k++)
+            r |= ((p >> k) & 1) << (log_n - 1 - k);
+        cos[p] = pw[r];
+    }
+    KZP_CUDA_CHECK(cudaMalloc(&d.tw_fwd, half * 32));
+    KZP_CUDA_CHECK(cudaMalloc(&d.tw_inv, half * 32));
+    KZP_CUDA_CHECK(cudaMalloc(&d.coset_br, n * 32));
+    KZP_CUDA_CHECK(cudaMemcpy(d.tw_fwd, fwd.data(), half * 32, cudaMemcpyHostToDevice));
+    KZP_CUDA_CHECK(cudaMemcpy(d.tw_inv, inv.data(), half * 32, cudaMemcpyHostToDevice));
+    KZP_CUDA_CHECK(cudaMemcpy(d.coset_br, cos.data(), n * 32, cudaMemcpyHostToDevice));
+}
+
+void ntt_domain_destroy(NttDomain& d)
+{
+    cudaFree(d.tw_fwd);
+    cudaFree(d.tw_inv);
+    cudaFree(d.coset_br);
+    d.tw_fwd = d.tw_inv = d.coset_br = nullptr;
+}
+
+// =====================================================================================================
+// diagnostics
+// =====================================================================================================
+template <class F>
+__global__ void __launch_bounds__(128)
+    k_field_op(int op, const F* __restrict__ a, const F* __restrict__ b, F* __restrict__ out, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    F x = a[i], y, r;
+    if (b)
+        y = b[i];
+    else
+        y = x;
+    switch (op)
+    {
+    case 0: F::mul(r, x, y); break;
+    case 1: F::add(r, x, y); break;
+    case 2: F::sub(r, x, y); break;
+    case 3: F::neg(r, x); break;
+    case 6: F::sqr(r, x); break;
+    case 7: F::inv(r, x); break;
+    default: r = x;
+    }
+    out[i] = r;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+    k_field_mont(int op, const F* __restrict__ a, F* __restrict__ out, uint64_t n)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    F x = a[i], r;
+    if (op == 4)
+        F::to_mont(r, x);
+    else
+        F::from_mont(r, x);
+    out[i] = r;
+}
+
+void point_op(int group, int op, const void* p, const void* q, void* out, uint64_t count, cudaStream_t st)
+{
+    if (group == 0)
+        point_op_g1(op, p, q, out, count, st);
+    else
+        point_op_g2(op, p, q, out, count, st);
+}
+
+void field_op(int field, int op, const void* a, const void* b, void* out, uint64_t count, cudaStream_t st)
+{
+    unsigned int grid = div_up(count, 128);
+    if (count == 0)
+        return;
+    if (op == 4 || op == 5)
+    {
+        if (field == 0)
+            k_field_mont<Fr><<<grid, 128, 0, st>>>(op, (const Fr*)a, (Fr*)out, count);
+        else if (field == 1)
+            k_field_mont<Fq><<<grid, 128, 0, st>>>(op, (const Fq*)a, (Fq*)out, count);
+        else
+            throw CudaError("to/fromMontgomery is defined on prime fields only");
+    }
+    else if (field == 0)
+        k_field_op<Fr><<<grid, 128, 0, st>>>(op, (const Fr*)a, (const Fr*)b, (Fr*)out, count);
+    else if (field == 1)
+        k_field_op<Fq><<<grid, 128, 0, st>>>(op, (const Fq*)a, (const Fq*)b, (Fq*)out, count);
+    else
+        k_field_op<Fq2><<<grid, 128, 0, st>>>(op, (const Fq2*)a, (const Fq2*)b, (Fq2*)out, count);
+    KZP_CUDA_CHECK(cudaGetLastError());
+}
+
+// Independent IMAD.WIDE chains, 8 accumulators per thread: the integer-pipe roofline denominator.
+__global__ void __launch_bounds__(256) k_imad_probe(uint32_t* sink, int iters)
+{
+    uint32_t a = threadIdx.x * 2654435761u + 1u, b = blockIdx.x * 40503u + 3u;
+    unsigned long long acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        acc[k] = a + k;
+    for (int it = 0; it < iters; it++)
+    {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b));
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        s ^= acc[k];
+    if (s == 0x1234567ull)
+        sink[0] = (uint32_t)s;
+}
+
+uint64_t imad_probe(uint32_t* sink, int iters, cudaStream_t st)
+{
+    int dev = 0, sms = 0;
+    KZP_CUDA_CHECK(cudaGetDevice(&dev));
+    KZP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    unsigned int grid = (unsigned int)sms * 8;
+    k_imad_probe<<<grid, 256, 0, st>>>(sink, iters);
+    KZP_CUDA_CHECK(cudaGetLastError());
+    return (uint64_t)grid * 256 * 8 * (uint64_t)iters;
+}
+
+} // namespace kzp

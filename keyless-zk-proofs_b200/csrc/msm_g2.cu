@@ -1,0 +1,19 @@
+// G2 instantiation of the MSM pipeline (see msm.cuh).
+#include "msm.cuh"
+
+namespace kzp
+{
+
+template struct MsmBases<G2Xyzz>;
+template void msm_bases_create<G2Xyzz>(MsmBases<G2Xyzz>&, const uint8_t*, uint64_t, uint64_t, uint32_t, cudaStream_t);
+template void msm_bases_destroy<G2Xyzz>(MsmBases<G2Xyzz>&);
+template void msm_scratch_create<G2Xyzz>(MsmScratch<G2Xyzz>&, uint32_t);
+template void msm_scratch_destroy<G2Xyzz>(MsmScratch<G2Xyzz>&);
+template void msm_run<G2Xyzz>(const MsmBases<G2Xyzz>&, MsmScratch<G2Xyzz>&, const uint32_t*, cudaStream_t);
+
+void point_op_g2(int op, const void* p, const void* q, void* out, uint64_t count, cudaStream_t st)
+{
+    point_op_t<G2Xyzz>(op, p, q, out, count, st);
+}
+
+} // namespace kzp

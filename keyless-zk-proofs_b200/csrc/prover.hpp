@@ -1,0 +1,84 @@
+// Groth16 prover resident on one GPU: proving key uploaded once, one proof per prove() call.
+// Replaces Groth16::Prover<Engine> + FullProverImpl of the reference
+// (rust-rapidsnark/rapidsnark/src/groth16.hpp:44-106, fullprover.cpp:136-250).
+#pragma once
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace kzp
+{
+
+// stage timings of the last proof, milliseconds (CUDA events on the launching streams, except *_host)
+struct ProveTimings
+{
+    float h2d_ms      = 0; // witness host -> device
+    float spmv_ms     = 0;
+    float ntt_ms      = 0; // 3 x (iNTT + coset + NTT) + pointwise
+    float msm_h_ms    = 0;
+    float msm_a_ms    = 0;
+    float msm_b1_ms   = 0;
+    float msm_b2_ms   = 0;
+    float msm_c_ms    = 0;
+    float gpu_ms      = 0; // first kernel to last kernel (both streams)
+    float assemble_host_ms = 0;
+    float total_host_ms    = 0; // wall clock of prove_*()
+    uint32_t kernel_launches = 0;
+};
+
+// The five MSM results of the last proof before blinding, affine canonical
+// little-endian: A(64) B1(64) B2(128) C(64) H(64)
+struct MsmArtefacts
+{
+    uint8_t bytes[384];
+};
+
+// Jacobian-free partial results of one shard (XYZZ, Montgomery): A, B1, C, H (128 B each) then B2 (256 B)
+struct ShardPartials
+{
+    uint8_t bytes[4 * 128 + 256];
+};
+
+class DeviceProverImpl;
+
+class DeviceProver
+{
+    std::unique_ptr<DeviceProverImpl> impl_;
+
+public:
+    // Throws kzp::LoadError / kzp::FormatError / kzp::CudaError.
+    // shard_rank/shard_world: this instance holds only base range [rank*n/world, (rank+1)*n/world) of every
+    // MSM section; world == 1 is the ordinary single-GPU prover.
+    DeviceProver(const std::string& zkey_path, int device, int shard_rank = 0, int shard_world = 1);
+    ~DeviceProver();
+
+    uint32_t n_vars() const;
+    uint32_t n_public() const;
+    uint32_t domain_size() const;
+    uint64_t n_coefs() const;
+    int      device() const;
+
+    // Upload a witness (n values x 32 B canonical LE) from host memory; n must be >= n_vars.
+    void upload_witness(const uint8_t* values, uint64_t n);
+    // Run the GPU part on the resident witness; leaves partial MSM results on the host.
+    void run_gpu();
+    const ShardPartials& partials() const;
+    // Sum `count` shard partials, blind with (r,s) (32 B canonical LE each; nullptr = sample like
+    // groth16.cpp:296-316) and print the proof JSON (groth16.cpp:379-410 + nlohmann dump()).
+    std::string assemble(const ShardPartials* parts, int count, const uint8_t* r32, const uint8_t* s32);
+
+    // convenience: upload + run + assemble for world == 1
+    std::string prove(const uint8_t* values, uint64_t n, const uint8_t* r32, const uint8_t* s32);
+
+    const ProveTimings& timings() const;
+    const MsmArtefacts& msm_artefacts() const; // filled by assemble()
+    // H coefficients of the last proof (domain_size x 32 B canonical, natural order) -> host buffer
+    void copy_h(uint8_t* out) const;
+    // when enabled, a and b after the SpMV are kept (device copy) and can be fetched with copy_ab
+    void set_keep_ab(bool on);
+    void copy_ab(uint8_t* out) const; // 2 * domain_size * 32 B, Montgomery
+};
+
+} // namespace kzp
