@@ -970,35 +970,39 @@ class _Lcg:
 
 
 def synth_circuit(n_constraints: int, n_vars: int, seed: int, n_public: int = 1) -> Tuple[R1CS, List[int]]:
-    """Keyless-shaped synthetic R1CS with a satisfying witness: most wires are
-    bits produced by AND gates, some are bytes composed from bits, a few are full-width field products;
-    surplus constraints are booleanity checks b*(b-1)=0 (C-less rows). Wire 0 = 1, wire 1 = public."""
-    assert n_public == 1 and n_vars >= 16 and n_constraints >= n_vars
+    """Keyless-shaped synthetic R1CS with a satisfying witness: ~80 % of the wires
+    are bits (XOR / AND gates), ~15 % bytes composed from 8 bits, ~5 % full-width field products; surplus
+    constraints are booleanity checks b*(b-1)=0 (C-less rows). Wire 0 = 1, wire 1 = public.
+    Bit-for-bit the same generator as circuit_synth() in oracle/kzp_port.c (same PRNG call order)."""
+    assert n_public == 1 and n_vars >= 16 and n_constraints >= n_vars - 9
     rng = _Lcg(seed)
     w = [0] * n_vars
-    kind = [0] * n_vars  # 0 bit, 1 byte, 2 field
     w[0] = 1
     rows: List[Tuple[dict, dict, dict]] = []
-    n_inputs = 8
-    first_free = 2
-    for i in range(first_free, first_free + n_inputs):
-        w[i] = rng.below(2)
-    # wire 1 (public) := in2 AND in3 handled as a normal gate below
-    next_wire = first_free + n_inputs
-    bits = list(range(first_free, first_free + n_inputs))
+    bits: List[int] = []
     fields: List[int] = []
+    for i in range(2, 10):
+        w[i] = rng.below(2)
+        bits.append(i)
 
     def and_gate(out):
         i = bits[rng.below(len(bits))]
         j = bits[rng.below(len(bits))]
-        w[out] = w[i] * w[j] % R_MOD
+        w[out] = w[i] & w[j]
         rows.append(({i: 1}, {j: 1}, {out: 1}))
 
     and_gate(1)
-    while next_wire < n_vars:
-        out = next_wire
+    for out in range(10, n_vars):
         t = rng.below(100)
-        if t < 80 or len(bits) < 8:
+        if t < 50 or len(bits) < 8:
+            i = bits[rng.below(len(bits))]
+            j = bits[rng.below(len(bits))]
+            w[out] = w[i] ^ w[j]
+            c = {i: 2} if i == j else {i: 1, j: 1}
+            c[out] = R_MOD - 1
+            rows.append(({i: 2}, {j: 1}, c))  # 2ij = i + j - out
+            bits.append(out)
+        elif t < 80:
             and_gate(out)
             bits.append(out)
         elif t < 95:
@@ -1006,15 +1010,13 @@ def synth_circuit(n_constraints: int, n_vars: int, seed: int, n_public: int = 1)
             val = 0
             for k in range(8):
                 i = bits[rng.below(len(bits))]
-                a[i] = (a.get(i, 0) + (1 << k)) % R_MOD
+                a[i] = a.get(i, 0) + (1 << k)
                 val += w[i] << k
-            w[out] = val % R_MOD
-            kind[out] = 1
+            w[out] = val
             rows.append((a, {0: 1}, {out: 1}))
         else:
             if len(fields) < 2:
                 x = rng.fr()
-                # seed value: (x * 1) = out
                 w[out] = x
                 rows.append(({0: x}, {0: 1}, {out: 1}))
             else:
@@ -1023,9 +1025,7 @@ def synth_circuit(n_constraints: int, n_vars: int, seed: int, n_public: int = 1)
                 k = bits[rng.below(len(bits))]
                 w[out] = (w[i] + w[k]) * (w[j] + 3) % R_MOD
                 rows.append(({i: 1, k: 1}, {j: 1, 0: 3}, {out: 1}))
-            kind[out] = 2
             fields.append(out)
-        next_wire += 1
     while len(rows) < n_constraints:
         i = bits[rng.below(len(bits))]
         rows.append(({i: 1}, {i: 1, 0: R_MOD - 1}, {}))
