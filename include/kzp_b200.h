@@ -91,6 +91,9 @@ int kzp_prover_info(kzp_prover* p, uint32_t* n_vars, uint32_t* n_public, uint32_
 /* last proof: floats {h2d, spmv, ntt, msm_h, msm_a, msm_b1, msm_b2, msm_c, gpu, assemble_host, total_host,
  * kernel_launches}; returns the number of values written (<= cap) */
 int kzp_prover_timings(kzp_prover* p, float* out, int cap);
+/* bucket-accumulation kernel (the dominant kernel) of MSM `which` (0 A, 1 B1, 2 B2, 3 C, 4 H) in the last proof:
+ * its duration from CUDA events on its stream and the number of (point, bucket) entries it summed */
+int kzp_prover_msm_profile(kzp_prover* p, int which, float* accumulate_ms, uint64_t* entries);
 /* parity artefacts of the last proof */
 int kzp_prover_get_h(kzp_prover* p, uint8_t* out, uint64_t out_bytes);       /* domain x 32, canonical */
 int kzp_prover_keep_ab(kzp_prover* p, int on);
@@ -127,6 +130,10 @@ int kzp_imad_peak(int iters, int device, float* ms, uint64_t* multiply_adds);
 /* host-only helpers (no GPU needed): decimal printing and file parsing, for the CPU test suite */
 int kzp_host_parse_zkey(const char* path, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size,
                         uint64_t* n_coefs, int* state_out);
+/* proof assembly without a GPU: sums `count` 768-byte shard partials, blinds and prints (host arithmetic only;
+ * this is the step rank 0 performs after the all-gather in sharded mode). msm_out384 may be NULL. */
+int kzp_host_assemble(const char* zkey_path, const uint8_t* partials, int count, const uint8_t* r32,
+                      const uint8_t* s32, char** json_out, uint8_t* msm_out384);
 int kzp_host_fq_decimal(const uint8_t* mont32, char* out, size_t cap);
 int kzp_host_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out);
 

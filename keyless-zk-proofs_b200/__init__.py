@@ -110,6 +110,7 @@ def lib() -> ctypes.CDLL:
         "kzp_prover_info": (c.c_int, [vp, c.POINTER(c.c_uint32), c.POINTER(c.c_uint32), c.POINTER(c.c_uint32),
                                       c.POINTER(c.c_uint64), i32p]),
         "kzp_prover_timings": (c.c_int, [vp, c.POINTER(c.c_float), c.c_int]),
+        "kzp_prover_msm_profile": (c.c_int, [vp, c.c_int, c.POINTER(c.c_float), c.POINTER(c.c_uint64)]),
         "kzp_prover_get_h": (c.c_int, [vp, u8p, c.c_uint64]),
         "kzp_prover_keep_ab": (c.c_int, [vp, c.c_int]),
         "kzp_prover_get_ab": (c.c_int, [vp, u8p, c.c_uint64]),
@@ -126,6 +127,7 @@ def lib() -> ctypes.CDLL:
         "kzp_imad_peak": (c.c_int, [c.c_int, c.c_int, c.POINTER(c.c_float), c.POINTER(c.c_uint64)]),
         "kzp_host_parse_zkey": (c.c_int, [c.c_char_p, c.POINTER(c.c_uint32), c.POINTER(c.c_uint32),
                                           c.POINTER(c.c_uint32), c.POINTER(c.c_uint64), i32p]),
+        "kzp_host_assemble": (c.c_int, [c.c_char_p, u8p, c.c_int, u8p, u8p, c.POINTER(vp), u8p]),
         "kzp_host_fq_decimal": (c.c_int, [u8p, c.c_char_p, c.c_size_t]),
         "kzp_host_field_op": (c.c_int, [c.c_int, c.c_int, u8p, u8p, u8p]),
     }
@@ -262,6 +264,12 @@ class FullProver:
         n = lib().kzp_prover_timings(self._h, arr, 12)
         return {k: float(arr[i]) for i, k in enumerate(TIMING_KEYS[:n])}
 
+    def msm_profile(self, which: int):
+        """(accumulate kernel ms, sorted entries) of MSM 0=A 1=B1 2=B2 3=C 4=H in the last proof."""
+        ms, ent = ctypes.c_float(), ctypes.c_uint64()
+        _check(lib().kzp_prover_msm_profile(self._h, which, ctypes.byref(ms), ctypes.byref(ent)))
+        return ms.value, ent.value
+
     def h_coefficients(self) -> bytes:
         buf = ctypes.create_string_buffer(self.domain_size * 32)
         _check(lib().kzp_prover_get_h(self._h, buf, len(buf)))
@@ -347,6 +355,16 @@ def point_op(group: int, op: int, p: bytes, q: Optional[bytes] = None, device: i
     out = ctypes.create_string_buffer(len(p))
     _check(lib().kzp_point_op(group, op, p, q, out, len(p) // psz, device))
     return out.raw
+
+
+def host_assemble(zkey_path: str, partials: Sequence[bytes], r: Optional[bytes] = None, s: Optional[bytes] = None):
+    """Rank-0 step of the sharded mode, host only: sum the shards' partial MSM results, blind, print.
+    Returns (proof_json, msm_results_384_bytes)."""
+    out = ctypes.c_void_p()
+    art = ctypes.create_string_buffer(384)
+    _check(lib().kzp_host_assemble(os.fsencode(zkey_path), b"".join(partials), len(partials), r, s,
+                                   ctypes.byref(out), art))
+    return _take_string(out), art.raw
 
 
 def imad_peak(iters: int = 4096, device: int = -1):

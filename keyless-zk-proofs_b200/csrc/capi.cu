@@ -323,6 +323,12 @@ int kzp_prover_timings(kzp_prover* p, float* out, int cap)
     return n;
 }
 
+int kzp_prover_msm_profile(kzp_prover* p, int which, float* accumulate_ms, uint64_t* entries)
+{
+    KZP_REQUIRE_READY(p);
+    return guarded([&] { p->prover->msm_profile(which, accumulate_ms, entries); });
+}
+
 int kzp_prover_get_h(kzp_prover* p, uint8_t* out, uint64_t out_bytes)
 {
     KZP_REQUIRE_READY(p);
@@ -724,6 +730,35 @@ int kzp_host_parse_zkey(const char* path, uint32_t* n_vars, uint32_t* n_public, 
     if (state_out)
         *state_out = state;
     return rc;
+}
+
+int kzp_host_assemble(const char* zkey_path, const uint8_t* partials, int count, const uint8_t* r32,
+                      const uint8_t* s32, char** json_out, uint8_t* msm_out384)
+{
+    if (!partials || count < 1 || !json_out)
+    {
+        g_last_error = "bad arguments";
+        return KZP_ERR_FORMAT;
+    }
+    return guarded([&] {
+        MappedFile file(zkey_path ? zkey_path : "");
+        BinView    bin(file.data(), file.size(), "zkey", 1);
+        ZkeyHeader zh = parse_zkey(bin);
+        HostVk     vk;
+        memcpy(vk.alpha1, zh.alpha1, 64);
+        memcpy(vk.beta1, zh.beta1, 64);
+        memcpy(vk.delta1, zh.delta1, 64);
+        memcpy(vk.beta2, zh.beta2, 128);
+        memcpy(vk.delta2, zh.delta2, 128);
+        std::vector<ShardPartials> ps(count);
+        for (int k = 0; k < count; k++)
+            memcpy(ps[k].bytes, partials + (size_t)k * KZP_PARTIALS_BYTES, KZP_PARTIALS_BYTES);
+        MsmArtefacts art;
+        std::string  j = assemble_proof(vk, ps.data(), count, r32, s32, &art);
+        if (msm_out384)
+            memcpy(msm_out384, art.bytes, 384);
+        *json_out = dup_string(j);
+    });
 }
 
 int kzp_host_fq_decimal(const uint8_t* mont32, char* out, size_t cap)

@@ -98,6 +98,7 @@ struct MsmScratch
     XY*       buckets     = nullptr; // kMsmBuckets + 1
     XY*       partial     = nullptr; // 2 * (kMsmBuckets / 256)
     XY*       result      = nullptr; // 1 (device)
+    cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr; // bracket the bucket-accumulation kernel of the last run
 };
 
 // bases_host: n_total affine Montgomery points exactly as in the zkey (64 B G1 / 128 B G2), (0,0) = infinity.
@@ -115,6 +116,10 @@ void msm_scratch_destroy(MsmScratch<XY>& s);
 // Leaves the XYZZ result in s.result (device).
 template <class XY>
 void msm_run(const MsmBases<XY>& b, MsmScratch<XY>& s, const uint32_t* scalars, cudaStream_t st);
+
+// duration of the last bucket-accumulation launch (ms, CUDA events on its stream) and its number of sorted entries
+template <class XY>
+void msm_last_accumulate(const MsmScratch<XY>& s, float* ms, uint64_t* entries);
 
 extern template struct MsmBases<G1Xyzz>;
 extern template struct MsmBases<G2Xyzz>;

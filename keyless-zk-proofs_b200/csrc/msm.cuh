@@ -585,6 +585,8 @@ void msm_scratch_create(MsmScratch<XY>& s, uint32_t n_active)
     KZP_CUDA_CHECK(cudaMalloc(&s.buckets, (kMsmBuckets + 1) * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.partial, 2 * (kMsmBuckets / 256) * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.result, sizeof(XY)));
+    KZP_CUDA_CHECK(cudaEventCreate(&s.ev_acc0));
+    KZP_CUDA_CHECK(cudaEventCreate(&s.ev_acc1));
 }
 
 template <class XY>
@@ -598,6 +600,10 @@ void msm_scratch_destroy(MsmScratch<XY>& s)
     cudaFree(s.buckets);
     cudaFree(s.partial);
     cudaFree(s.result);
+    if (s.ev_acc0)
+        cudaEventDestroy(s.ev_acc0);
+    if (s.ev_acc1)
+        cudaEventDestroy(s.ev_acc1);
     s = MsmScratch<XY>();
 }
 
@@ -620,8 +626,10 @@ void msm_run(const MsmBases<XY>& b, MsmScratch<XY>& s, const uint32_t* scalars, 
         k_msm_scatter<<<msm_div_up(b.n, 256), 256, 0, st>>>(scalars, b.scalar_idx, b.n, s.cursor, s.sorted);
         KZP_CUDA_CHECK(cudaGetLastError());
         uint64_t threads = ((uint64_t)b.n * kMsmWindows + kMsmChunk - 1) / kMsmChunk;
+        KZP_CUDA_CHECK(cudaEventRecord(s.ev_acc0, st));
         k_msm_accumulate<XY><<<msm_div_up(threads, 128), 128, 0, st>>>(s.offsets, s.sorted, b.table, s.records);
         KZP_CUDA_CHECK(cudaGetLastError());
+        KZP_CUDA_CHECK(cudaEventRecord(s.ev_acc1, st));
     }
     k_msm_bucket_finalize<XY><<<kMsmBuckets, 256, 256 * sizeof(XY), st>>>(s.offsets, s.records, s.buckets);
     KZP_CUDA_CHECK(cudaGetLastError());
@@ -629,6 +637,23 @@ void msm_run(const MsmBases<XY>& b, MsmScratch<XY>& s, const uint32_t* scalars, 
     KZP_CUDA_CHECK(cudaGetLastError());
     k_msm_reduce2<XY><<<1, 128, 3 * (kMsmBuckets / 256) * sizeof(XY), st>>>(s.partial, s.result);
     KZP_CUDA_CHECK(cudaGetLastError());
+}
+
+template <class XY>
+void msm_last_accumulate(const MsmScratch<XY>& s, float* ms, uint64_t* entries)
+{
+    float t = 0;
+    if (s.ev_acc0 && cudaEventElapsedTime(&t, s.ev_acc0, s.ev_acc1) != cudaSuccess)
+    {
+        cudaGetLastError();
+        t = 0;
+    }
+    uint32_t total = 0;
+    KZP_CUDA_CHECK(cudaMemcpy(&total, s.offsets + kMsmBuckets + 1, 4, cudaMemcpyDeviceToHost));
+    if (ms)
+        *ms = t;
+    if (entries)
+        *entries = total;
 }
 
 template <class XY>

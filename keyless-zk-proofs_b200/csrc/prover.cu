@@ -87,6 +87,160 @@ void append_decimal(std::string& s, const F& mont)
 
 } // namespace
 
+// Sums the shards' partial MSM results, blinds with (r, s) and prints the proof. Host-only arithmetic (a few
+// thousand field multiplications); mirrors groth16.cpp:296-357 + Proof::toJson (:379-410).
+std::string assemble_proof(const HostVk& vk, const ShardPartials* ps, int count, const uint8_t* r32,
+                           const uint8_t* s32, MsmArtefacts* art_out)
+{
+    HG1Affine alpha1, beta1, delta1;
+    HG2Affine beta2, delta2;
+    memcpy(&alpha1, vk.alpha1, 64);
+    memcpy(&beta1, vk.beta1, 64);
+    memcpy(&delta1, vk.delta1, 64);
+    memcpy(&beta2, vk.beta2, 128);
+    memcpy(&delta2, vk.delta2, 128);
+    MsmArtefacts art_local;
+    MsmArtefacts& art = art_out ? *art_out : art_local;
+    HG1 A, B1, C, H;
+    HG2 B2;
+    HG1::set_inf(A);
+    HG1::set_inf(B1);
+    HG1::set_inf(C);
+    HG1::set_inf(H);
+    HG2::set_inf(B2);
+    for (int k = 0; k < count; k++)
+    {
+        HG1 t;
+        HG2 t2;
+        memcpy(&t, ps[k].bytes + 0, 128);
+        HG1::add(A, t);
+        memcpy(&t, ps[k].bytes + 128, 128);
+        HG1::add(B1, t);
+        memcpy(&t, ps[k].bytes + 256, 128);
+        HG1::add(C, t);
+        memcpy(&t, ps[k].bytes + 384, 128);
+        HG1::add(H, t);
+        memcpy(&t2, ps[k].bytes + 512, 256);
+        HG2::add(B2, t2);
+    }
+    // parity artefacts (affine, canonical)
+    {
+        auto put1 = [&](uint8_t* out, const HG1& p) {
+            HG1Affine a;
+            HG1::to_affine(a, p);
+            HFq t;
+            HFq::from_mont(t, a.x);
+            memcpy(out, &t, 32);
+            HFq::from_mont(t, a.y);
+            memcpy(out + 32, &t, 32);
+        };
+        put1(art.bytes + 0, A);
+        put1(art.bytes + 64, B1);
+        HG2Affine b2;
+        HG2::to_affine(b2, B2);
+        HFq t;
+        HFq::from_mont(t, b2.x.a);
+        memcpy(art.bytes + 128, &t, 32);
+        HFq::from_mont(t, b2.x.b);
+        memcpy(art.bytes + 160, &t, 32);
+        HFq::from_mont(t, b2.y.a);
+        memcpy(art.bytes + 192, &t, 32);
+        HFq::from_mont(t, b2.y.b);
+        memcpy(art.bytes + 224, &t, 32);
+        put1(art.bytes + 256, C);
+        put1(art.bytes + 320, H);
+    }
+
+    uint8_t r[32], s[32];
+    if (r32 && s32)
+    {
+        memcpy(r, r32, 32);
+        memcpy(s, s32, 32);
+    }
+    else
+    {
+        sample_blinding(r);
+        sample_blinding(s);
+    }
+    // rs = r*s mod r_modulus, canonical (groth16.cpp:346-347)
+    uint8_t rs[32];
+    {
+        HFr fr, fs, t;
+        memcpy(&fr, r, 32);
+        memcpy(&fs, s, 32);
+        while (HFr::geq_p(fr))
+            HFr::sub_p(fr);
+        while (HFr::geq_p(fs))
+            HFr::sub_p(fs);
+        HFr::to_mont(fr, fr);
+        HFr::mul(t, fr, fs); // (r R)(s) R^-1 = r s
+        memcpy(rs, &t, 32);
+    }
+    HG1 d1, al, be1, p1;
+    HG2 d2, be2, p2;
+    HG1::from_affine(d1, delta1);
+    HG1::from_affine(al, alpha1);
+    HG1::from_affine(be1, beta1);
+    HG2::from_affine(d2, delta2);
+    HG2::from_affine(be2, beta2);
+
+    // pi_a = A + alpha1 + r*delta1            (groth16.cpp:328-330)
+    HG1 pi_a = A;
+    HG1::add(pi_a, al);
+    scalar_mul(p1, d1, r);
+    HG1::add(pi_a, p1);
+    // pi_b = B2 + beta2 + s*delta2            (:332-334)
+    HG2 pi_b = B2;
+    HG2::add(pi_b, be2);
+    scalar_mul(p2, d2, s);
+    HG2::add(pi_b, p2);
+    // pib1 = B1 + beta1 + s*delta1            (:336-338)
+    HG1 pib1 = B1;
+    HG1::add(pib1, be1);
+    scalar_mul(p1, d1, s);
+    HG1::add(pib1, p1);
+    // pi_c = C + H + s*pi_a + r*pib1 - rs*delta1   (:340-352)
+    HG1 pi_c = C;
+    HG1::add(pi_c, H);
+    scalar_mul(p1, pi_a, s);
+    HG1::add(pi_c, p1);
+    scalar_mul(p1, pib1, r);
+    HG1::add(pi_c, p1);
+    scalar_mul(p1, d1, rs);
+    HG1 np1;
+    HG1::neg(np1, p1);
+    HG1::add(pi_c, np1);
+
+    HG1Affine a_aff, c_aff;
+    HG2Affine b_aff;
+    HG1::to_affine(a_aff, pi_a);
+    HG2::to_affine(b_aff, pi_b);
+    HG1::to_affine(c_aff, pi_c);
+
+    // compact JSON, keys in sorted order, exactly what nlohmann::json::dump() prints for
+    // Proof::toJson (groth16.cpp:379-410, fullprover.cpp:246)
+    std::string j;
+    j.reserve(900);
+    j += "{\"pi_a\":[";
+    append_decimal(j, a_aff.x);
+    j += ',';
+    append_decimal(j, a_aff.y);
+    j += ",\"1\"],\"pi_b\":[[";
+    append_decimal(j, b_aff.x.a);
+    j += ',';
+    append_decimal(j, b_aff.x.b);
+    j += "],[";
+    append_decimal(j, b_aff.y.a);
+    j += ',';
+    append_decimal(j, b_aff.y.b);
+    j += "],[\"1\",\"0\"]],\"pi_c\":[";
+    append_decimal(j, c_aff.x);
+    j += ',';
+    append_decimal(j, c_aff.y);
+    j += ",\"1\"],\"protocol\":\"groth16\"}";
+    return j;
+}
+
 class DeviceProverImpl
 {
 public:
@@ -100,7 +254,7 @@ public:
     uint64_t n_coefs    = 0;
 
     cudaStream_t st_h = nullptr, st_w = nullptr, st_copy = nullptr;
-    cudaEvent_t  ev[16];
+    cudaEvent_t  ev[16] = {};
 
     CoefCsr   csr;
     NttDomain ntt;
@@ -115,8 +269,7 @@ public:
     MsmScratch<G1Xyzz> sc_a, sc_b1, sc_c, sc_h;
     MsmScratch<G2Xyzz> sc_b2;
 
-    HG1Affine alpha1, beta1, delta1;
-    HG2Affine beta2, delta2;
+    HostVk vk;
 
     ShardPartials parts;
     MsmArtefacts  art;
@@ -206,11 +359,11 @@ public:
         for (auto& e : ev)
             KZP_CUDA_CHECK(cudaEventCreate(&e));
 
-        memcpy(&alpha1, zh.alpha1, 64);
-        memcpy(&beta1, zh.beta1, 64);
-        memcpy(&delta1, zh.delta1, 64);
-        memcpy(&beta2, zh.beta2, 128);
-        memcpy(&delta2, zh.delta2, 128);
+        memcpy(vk.alpha1, zh.alpha1, 64);
+        memcpy(vk.beta1, zh.beta1, 64);
+        memcpy(vk.delta1, zh.delta1, 64);
+        memcpy(vk.beta2, zh.beta2, 128);
+        memcpy(vk.delta2, zh.delta2, 128);
 
         build_csr(zh);
         ntt_domain_create(ntt, log_domain);
@@ -355,144 +508,8 @@ public:
 
     std::string assemble(const ShardPartials* ps, int count, const uint8_t* r32, const uint8_t* s32)
     {
-        double t0 = now_ms();
-        HG1    A, B1, C, H;
-        HG2    B2;
-        HG1::set_inf(A);
-        HG1::set_inf(B1);
-        HG1::set_inf(C);
-        HG1::set_inf(H);
-        HG2::set_inf(B2);
-        for (int k = 0; k < count; k++)
-        {
-            HG1 t;
-            HG2 t2;
-            memcpy(&t, ps[k].bytes + 0, 128);
-            HG1::add(A, t);
-            memcpy(&t, ps[k].bytes + 128, 128);
-            HG1::add(B1, t);
-            memcpy(&t, ps[k].bytes + 256, 128);
-            HG1::add(C, t);
-            memcpy(&t, ps[k].bytes + 384, 128);
-            HG1::add(H, t);
-            memcpy(&t2, ps[k].bytes + 512, 256);
-            HG2::add(B2, t2);
-        }
-        // parity artefacts (affine, canonical)
-        {
-            auto put1 = [&](uint8_t* out, const HG1& p) {
-                HG1Affine a;
-                HG1::to_affine(a, p);
-                HFq t;
-                HFq::from_mont(t, a.x);
-                memcpy(out, &t, 32);
-                HFq::from_mont(t, a.y);
-                memcpy(out + 32, &t, 32);
-            };
-            put1(art.bytes + 0, A);
-            put1(art.bytes + 64, B1);
-            HG2Affine b2;
-            HG2::to_affine(b2, B2);
-            HFq t;
-            HFq::from_mont(t, b2.x.a);
-            memcpy(art.bytes + 128, &t, 32);
-            HFq::from_mont(t, b2.x.b);
-            memcpy(art.bytes + 160, &t, 32);
-            HFq::from_mont(t, b2.y.a);
-            memcpy(art.bytes + 192, &t, 32);
-            HFq::from_mont(t, b2.y.b);
-            memcpy(art.bytes + 224, &t, 32);
-            put1(art.bytes + 256, C);
-            put1(art.bytes + 320, H);
-        }
-
-        uint8_t r[32], s[32];
-        if (r32 && s32)
-        {
-            memcpy(r, r32, 32);
-            memcpy(s, s32, 32);
-        }
-        else
-        {
-            sample_blinding(r);
-            sample_blinding(s);
-        }
-        // rs = r*s mod r_modulus, canonical (groth16.cpp:346-347)
-        uint8_t rs[32];
-        {
-            HFr fr, fs, t;
-            memcpy(&fr, r, 32);
-            memcpy(&fs, s, 32);
-            while (HFr::geq_p(fr))
-                HFr::sub_p(fr);
-            while (HFr::geq_p(fs))
-                HFr::sub_p(fs);
-            HFr::to_mont(fr, fr);
-            HFr::mul(t, fr, fs); // (r R)(s) R^-1 = r s
-            memcpy(rs, &t, 32);
-        }
-        HG1 d1, al, be1, p1;
-        HG2 d2, be2, p2;
-        HG1::from_affine(d1, delta1);
-        HG1::from_affine(al, alpha1);
-        HG1::from_affine(be1, beta1);
-        HG2::from_affine(d2, delta2);
-        HG2::from_affine(be2, beta2);
-
-        // pi_a = A + alpha1 + r*delta1            (groth16.cpp:328-330)
-        HG1 pi_a = A;
-        HG1::add(pi_a, al);
-        scalar_mul(p1, d1, r);
-        HG1::add(pi_a, p1);
-        // pi_b = B2 + beta2 + s*delta2            (:332-334)
-        HG2 pi_b = B2;
-        HG2::add(pi_b, be2);
-        scalar_mul(p2, d2, s);
-        HG2::add(pi_b, p2);
-        // pib1 = B1 + beta1 + s*delta1            (:336-338)
-        HG1 pib1 = B1;
-        HG1::add(pib1, be1);
-        scalar_mul(p1, d1, s);
-        HG1::add(pib1, p1);
-        // pi_c = C + H + s*pi_a + r*pib1 - rs*delta1   (:340-352)
-        HG1 pi_c = C;
-        HG1::add(pi_c, H);
-        scalar_mul(p1, pi_a, s);
-        HG1::add(pi_c, p1);
-        scalar_mul(p1, pib1, r);
-        HG1::add(pi_c, p1);
-        scalar_mul(p1, d1, rs);
-        HG1 np1;
-        HG1::neg(np1, p1);
-        HG1::add(pi_c, np1);
-
-        HG1Affine a_aff, c_aff;
-        HG2Affine b_aff;
-        HG1::to_affine(a_aff, pi_a);
-        HG2::to_affine(b_aff, pi_b);
-        HG1::to_affine(c_aff, pi_c);
-
-        // compact JSON, keys in sorted order, exactly what nlohmann::json::dump() prints for
-        // Proof::toJson (groth16.cpp:379-410, fullprover.cpp:246)
-        std::string j;
-        j.reserve(900);
-        j += "{\"pi_a\":[";
-        append_decimal(j, a_aff.x);
-        j += ',';
-        append_decimal(j, a_aff.y);
-        j += ",\"1\"],\"pi_b\":[[";
-        append_decimal(j, b_aff.x.a);
-        j += ',';
-        append_decimal(j, b_aff.x.b);
-        j += "],[";
-        append_decimal(j, b_aff.y.a);
-        j += ',';
-        append_decimal(j, b_aff.y.b);
-        j += "],[\"1\",\"0\"]],\"pi_c\":[";
-        append_decimal(j, c_aff.x);
-        j += ',';
-        append_decimal(j, c_aff.y);
-        j += ",\"1\"],\"protocol\":\"groth16\"}";
+        double      t0 = now_ms();
+        std::string j  = assemble_proof(vk, ps, count, r32, s32, &art);
         tm.assemble_host_ms = (float)(now_ms() - t0);
         return j;
     }
@@ -527,6 +544,19 @@ std::string DeviceProver::prove(const uint8_t* values, uint64_t n, const uint8_t
     return j;
 }
 const ProveTimings& DeviceProver::timings() const { return impl_->tm; }
+void DeviceProver::msm_profile(int which, float* ms, uint64_t* entries) const
+{
+    impl_->set_device();
+    switch (which)
+    {
+    case 0: msm_last_accumulate(impl_->sc_a, ms, entries); break;
+    case 1: msm_last_accumulate(impl_->sc_b1, ms, entries); break;
+    case 2: msm_last_accumulate(impl_->sc_b2, ms, entries); break;
+    case 3: msm_last_accumulate(impl_->sc_c, ms, entries); break;
+    case 4: msm_last_accumulate(impl_->sc_h, ms, entries); break;
+    default: throw FormatError("msm index out of range");
+    }
+}
 const MsmArtefacts& DeviceProver::msm_artefacts() const { return impl_->art; }
 void DeviceProver::copy_h(uint8_t* out) const
 {

@@ -41,6 +41,18 @@ struct ShardPartials
     uint8_t bytes[4 * 128 + 256];
 };
 
+// the five points of the proving key the proof assembly needs (zkey section 2; affine Montgomery bytes)
+struct HostVk
+{
+    uint8_t alpha1[64], beta1[64], delta1[64];
+    uint8_t beta2[128], delta2[128];
+};
+
+// Host-only: sum `count` shards' partials, blind with (r,s) (nullptr = sample like groth16.cpp:296-316),
+// print the proof JSON. art_out (optional) receives the five unblinded MSM results.
+std::string assemble_proof(const HostVk& vk, const ShardPartials* parts, int count, const uint8_t* r32,
+                           const uint8_t* s32, MsmArtefacts* art_out);
+
 class DeviceProverImpl;
 
 class DeviceProver
@@ -73,6 +85,8 @@ public:
     std::string prove(const uint8_t* values, uint64_t n, const uint8_t* r32, const uint8_t* s32);
 
     const ProveTimings& timings() const;
+    // bucket-accumulation kernel of MSM `which` (0 A, 1 B1, 2 B2, 3 C, 4 H) in the last proof: duration and entries
+    void msm_profile(int which, float* accumulate_ms, uint64_t* entries) const;
     const MsmArtefacts& msm_artefacts() const; // filled by assemble()
     // H coefficients of the last proof (domain_size x 32 B canonical, natural order) -> host buffer
     void copy_h(uint8_t* out) const;

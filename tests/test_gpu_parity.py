@@ -1,0 +1,499 @@
+"""GPU parity tests (run with -m gpu on a B200). Every call goes through the C ABI of libkzp_b200.so; the oracle
+(oracle/bn254.py, oracle/kzp_port.c) and the reference itself (oracle/_ref) are used only as checkers.
+Bar: bit-exact (integer arithmetic only on this path)."""
+import json
+import os
+import random
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _fr_bytes(o, vals, mont=False):
+    return b"".join(o.le32(o.to_mont(v, o.R_MOD) if mont else v) for v in vals)
+
+
+def _ints(o, blob):
+    return [o.from_le(blob[i:i + 32]) for i in range(0, len(blob), 32)]
+
+
+# ---------------------------------------------------------------- field arithmetic (RS/fr_raw_generic.cpp)
+@pytest.mark.parametrize("field", [0, 1])
+def test_field_ops(gpu, kzp, oracle, field):
+    o = oracle
+    mod = o.R_MOD if field == 0 else o.Q_MOD
+    rnd = random.Random(100 + field)
+    n = 4096
+    a = [rnd.randrange(mod) for _ in range(n)]
+    b = [rnd.randrange(mod) for _ in range(n)]
+    edge = [0, 1, 2, mod - 1, mod - 2, (1 << 32) - 1, 1 << 32, (1 << 64) - 1, 1 << 128, (1 << 253), o.MONT_R % mod]
+    for i, e in enumerate(edge):
+        a[i] = e
+        b[i] = edge[(i * 7 + 3) % len(edge)]
+    b[20] = a[20]
+    b[21] = mod - a[21]
+    A, B = b"".join(map(o.le32, a)), b"".join(map(o.le32, b))
+    want = {0: [o.mont_mul(x, y, mod) for x, y in zip(a, b)], 1: [(x + y) % mod for x, y in zip(a, b)],
+            2: [(x - y) % mod for x, y in zip(a, b)], 3: [(-x) % mod for x in a],
+            4: [o.to_mont(x, mod) for x in a], 5: [o.from_mont(x, mod) for x in a],
+            6: [o.mont_mul(x, x, mod) for x in a]}
+    for op, w in want.items():
+        got = _ints(o, kzp.field_op(field, op, A, B))
+        assert got == w, "field %d op %d" % (field, op)
+    got = _ints(o, kzp.field_op(field, 7, A[:32 * 64], None))
+    for x, g in zip(a[:64], got):
+        assert g == (o.to_mont(pow(o.from_mont(x, mod), -1, mod), mod) if x else 0)
+
+
+def test_field_kats_on_device(gpu, kzp, oracle):
+    """The reference's limb-level KATs (RS/test_prover.cpp, canonical inputs) on the device code."""
+    opcode = {"mul": 0, "add": 1, "sub": 2, "square": 6}
+    n = 0
+    for rec in json.load(open(os.path.join(GOLDEN, "field_kats.json"))):
+        mod = oracle.R_MOD if rec["field"] == "Fr" else oracle.Q_MOD
+        a, b = int(rec["a"], 16), int(rec.get("b", "0x0"), 16)
+        if a >= mod or b >= mod:
+            continue
+        got = kzp.field_op(0 if rec["field"] == "Fr" else 1, opcode[rec["op"]], oracle.le32(a), oracle.le32(b))
+        assert oracle.from_le(got) == int(rec["expected"], 16), rec
+        n += 1
+    assert n >= 20
+
+
+def test_fq2_ops(gpu, kzp, oracle):
+    o = oracle
+    rnd = random.Random(5)
+    n = 1024
+    a = [(rnd.randrange(o.Q_MOD), rnd.randrange(o.Q_MOD)) for _ in range(n)]
+    b = [(rnd.randrange(o.Q_MOD), rnd.randrange(o.Q_MOD)) for _ in range(n)]
+    a[0], b[0] = (2, 2), (3, 3)  # f2_simpleMul, RS/alt_bn128_test.cpp:12-29
+    a[1] = (0, 0)
+    b[2] = (0, 5)
+    enc = lambda xs: b"".join(o.le32(o.to_mont(x[0], o.Q_MOD)) + o.le32(o.to_mont(x[1], o.Q_MOD)) for x in xs)
+    dec = lambda blob: [(o.from_mont(o.from_le(blob[i:i + 32]), o.Q_MOD), o.from_mont(o.from_le(blob[i + 32:i + 64]), o.Q_MOD))
+                        for i in range(0, len(blob), 64)]
+    A, B = enc(a), enc(b)
+    assert dec(kzp.field_op(2, 0, A, B)) == [o.f2_mul(x, y) for x, y in zip(a, b)]
+    assert dec(kzp.field_op(2, 0, A, B))[0] == (0, 12)
+    assert dec(kzp.field_op(2, 1, A, B)) == [o.f2_add(x, y) for x, y in zip(a, b)]
+    assert dec(kzp.field_op(2, 2, A, B)) == [o.f2_sub(x, y) for x, y in zip(a, b)]
+    assert dec(kzp.field_op(2, 3, A, None)) == [o.f2_neg(x) for x in a]
+    assert dec(kzp.field_op(2, 6, A, None)) == [o.f2_sqr(x) for x in a]
+    got = dec(kzp.field_op(2, 7, A[:64 * 32], None))
+    assert got == [o.f2_inv(x) if x != (0, 0) else (0, 0) for x in a[:32]]
+
+
+# ---------------------------------------------------------------- group law (RS/curve.cpp)
+def _g1_xyzz(o, p, z=1):
+    """XYZZ encoding (Montgomery) of affine p scaled by z: (x z^2, y z^3, z^2, z^3)."""
+    if p is None:
+        one = o.le32(o.to_mont(1, o.Q_MOD))
+        return one + one + bytes(64)
+    zz, zzz = z * z % o.Q_MOD, z * z * z % o.Q_MOD
+    return b"".join(o.le32(o.to_mont(v % o.Q_MOD, o.Q_MOD)) for v in (p[0] * zz, p[1] * zzz, zz, zzz))
+
+
+def _g1_from_xyzz(o, blob):
+    x, y, zz, zzz = (o.from_mont(o.from_le(blob[i * 32:(i + 1) * 32]), o.Q_MOD) for i in range(4))
+    if zz == 0:
+        return None
+    return (x * pow(zz, -1, o.Q_MOD) % o.Q_MOD, y * pow(zzz, -1, o.Q_MOD) % o.Q_MOD)
+
+
+def test_g1_point_ops_with_exceptional_cases(gpu, kzp, oracle):
+    o = oracle
+    rnd = random.Random(9)
+    pts = [o.g1_mul(o.G1_GEN, rnd.randrange(1, o.R_MOD)) for _ in range(40)]
+    P, Q = [], []
+    for i in range(32):
+        P.append((pts[i], rnd.randrange(1, o.Q_MOD)))
+        Q.append(pts[i + 1])
+    P[0] = (None, 1); Q[1] = None                      # infinity operands
+    P[2] = (pts[5], 77); Q[2] = pts[5]                 # P == Q  -> doubling branch (curve.cpp:219)
+    P[3] = (pts[6], 99); Q[3] = o.g1_neg(pts[6])       # P == -Q -> infinity
+    P[4] = (None, 1); Q[4] = None
+    pb = b"".join(_g1_xyzz(o, p, z) for p, z in P)
+    qa = b"".join(o.g1_to_zkey_bytes(q) for q in Q)
+    out = kzp.point_op(0, 0, pb, qa)
+    got = [_g1_from_xyzz(o, out[i * 128:(i + 1) * 128]) for i in range(32)]
+    assert got == [o.g1_add(p, q) for (p, _), q in zip(P, Q)]
+    qx = b"".join(_g1_xyzz(o, q, rnd.randrange(1, o.Q_MOD)) for q in Q)
+    out = kzp.point_op(0, 1, pb, qx)
+    got = [_g1_from_xyzz(o, out[i * 128:(i + 1) * 128]) for i in range(32)]
+    assert got == [o.g1_add(p, q) for (p, _), q in zip(P, Q)]
+    out = kzp.point_op(0, 2, pb, None)
+    got = [_g1_from_xyzz(o, out[i * 128:(i + 1) * 128]) for i in range(32)]
+    assert got == [o.g1_add(p, p) for (p, _) in P]
+
+
+def test_g2_point_ops(gpu, kzp, oracle):
+    o = oracle
+    rnd = random.Random(10)
+    pts = [o.g2_mul(o.G2_GEN, rnd.randrange(1, o.R_MOD)) for _ in range(10)]
+    one = o.le32(o.to_mont(1, o.Q_MOD))
+
+    def xyzz(p):
+        if p is None:
+            return one + bytes(32) + one + bytes(32) + bytes(128)
+        return o.g2_to_zkey_bytes(p) + one + bytes(32) + one + bytes(32)
+
+    def dec(blob):
+        v = [o.from_mont(o.from_le(blob[i * 32:(i + 1) * 32]), o.Q_MOD) for i in range(8)]
+        x, y, zz, zzz = (v[0], v[1]), (v[2], v[3]), (v[4], v[5]), (v[6], v[7])
+        if zz == (0, 0):
+            return None
+        return (o.f2_mul(x, o.f2_inv(zz)), o.f2_mul(y, o.f2_inv(zzz)))
+
+    P = [pts[0], pts[1], None, pts[3], pts[4], pts[5]]
+    Q = [pts[1], None, pts[2], pts[3], o.g2_neg(pts[4]), pts[6]]
+    pb = b"".join(xyzz(p) for p in P)
+    out = kzp.point_op(1, 0, pb, b"".join(o.g2_to_zkey_bytes(q) for q in Q))
+    assert [dec(out[i * 256:(i + 1) * 256]) for i in range(6)] == [o.g2_add(p, q) for p, q in zip(P, Q)]
+    out = kzp.point_op(1, 1, pb, b"".join(xyzz(q) for q in Q))
+    assert [dec(out[i * 256:(i + 1) * 256]) for i in range(6)] == [o.g2_add(p, q) for p, q in zip(P, Q)]
+    out = kzp.point_op(1, 2, pb, None)
+    assert [dec(out[i * 256:(i + 1) * 256]) for i in range(6)] == [o.g2_add(p, p) for p in P]
+
+
+# ---------------------------------------------------------------- NTT (RS/fft.cpp)
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 8, 10, 13, 16])
+def test_ntt_matches_reference(gpu, kzp, oracle, port, log_n):
+    o = oracle
+    n = 1 << log_n
+    rnd = random.Random(log_n)
+    x = [rnd.randrange(o.R_MOD) for _ in range(n)]
+    if n >= 4:
+        x[1] = 0
+        x[2] = o.R_MOD - 1
+    X = _fr_bytes(o, x)  # any canonical value is a valid Montgomery element
+    want_f = port.ntt(X, False) if n > 1 else X
+    want_i = port.ntt(X, True) if n > 1 else X
+    assert kzp.fr_ntt(X, False) == want_f
+    assert kzp.fr_ntt(X, True) == want_i
+    if log_n <= 10 and n > 1:  # the Python restatement, small sizes
+        xs = [o.from_mont(v, o.R_MOD) for v in x]
+        assert _ints(o, want_f) == [o.to_mont(v, o.R_MOD) for v in o.fr_fft(xs)]
+
+
+def test_ntt_reference_roundtrip_kat(gpu, kzp, oracle, ref):
+    # RS/alt_bn128_test.cpp:250-271 : a[i] = i+1, n = 2^10, ifft(fft(a)) == a ; and equality with the reference's fft
+    n = 1 << 10
+    data = _fr_bytes(oracle, range(1, n + 1), mont=True)
+    f = kzp.fr_ntt(data, False)
+    assert f == ref.ntt(data, False)
+    assert kzp.fr_ntt(f, True) == data
+
+
+@pytest.mark.parametrize("log_n", [2, 9, 14])
+def test_coset_chain_matches_reference(gpu, kzp, oracle, port, log_n):
+    """ifft -> multiply by w_2n^i -> fft, the per-vector chain of groth16.cpp:172-203."""
+    o = oracle
+    n = 1 << log_n
+    rnd = random.Random(50 + log_n)
+    X = _fr_bytes(o, [rnd.randrange(o.R_MOD) for _ in range(n)])
+    w2n = o.to_mont(o.fr_root_of_unity(log_n + 1), o.R_MOD)
+    coef = _ints(o, port.ntt(X, True))
+    shift, acc = [], o.to_mont(1, o.R_MOD)
+    for i in range(n):
+        shift.append(o.mont_mul(coef[i], acc, o.R_MOD))
+        acc = o.mont_mul(acc, w2n, o.R_MOD)
+    want = port.ntt(_fr_bytes(o, shift), False)
+    assert kzp.fr_coset_chain(X) == want
+
+
+@pytest.mark.slow
+def test_ntt_full_size_properties(gpu, kzp, oracle):
+    """2^21 (the keyless domain): round trip and linearity, size-independent checks."""
+    o = oracle
+    n = 1 << 21
+    rnd = random.Random(21)
+    import numpy as np
+    raw = np.frombuffer(rnd.randbytes(n * 32), dtype=np.uint8).reshape(n, 32).copy()
+    raw[:, 31] &= 0x1F  # < 2^253 < r : canonical
+    X = raw.tobytes()
+    F = kzp.fr_ntt(X, False)
+    assert kzp.fr_ntt(F, True) == X
+    Y = np.roll(raw, 1, axis=0).tobytes()
+    S = kzp.field_op(0, 1, X, Y)
+    assert kzp.fr_ntt(S, False) == kzp.field_op(0, 1, F, kzp.fr_ntt(Y, False))
+
+
+# ---------------------------------------------------------------- MSM (RS/multiexp.cpp)
+def _rand_g1(o, rnd, n):
+    # k_i * G with k_i chained so generation is cheap: P_{i+1} = P_i + d_i G
+    pts, acc = [], o.g1_mul(o.G1_GEN, rnd.randrange(1, o.R_MOD))
+    step = [o.g1_mul(o.G1_GEN, rnd.randrange(1, o.R_MOD)) for _ in range(4)]
+    for i in range(n):
+        pts.append(acc)
+        acc = o.g1_add(acc, step[i & 3])
+    return pts
+
+
+SCALAR_MIXES = ["uniform", "bits", "bytes", "keyless", "edges", "zeros", "noncanonical"]
+
+
+def _scalars(o, rnd, n, mix):
+    if mix == "uniform":
+        return [rnd.randrange(o.R_MOD) for _ in range(n)]
+    if mix == "bits":
+        return [rnd.randrange(2) for _ in range(n)]
+    if mix == "bytes":
+        return [rnd.randrange(256) for _ in range(n)]
+    if mix == "keyless":
+        return [rnd.choice([0, 1]) if rnd.random() < 0.8 else (rnd.randrange(1 << 16) if rnd.random() < 0.75 else rnd.randrange(o.R_MOD))
+                for _ in range(n)]
+    if mix == "edges":
+        e = [0x7FFF, 0x8000, 0x8001, 0xFFFF, 0x10000, 0x18000, 0xFFFF8000, o.R_MOD - 1, o.R_MOD - 2, (1 << 253) + 0x8000,
+             int("8000" * 15, 16), int("7fff8001" * 7, 16)]
+        return [e[i % len(e)] for i in range(n)]
+    if mix == "zeros":
+        return [0] * n
+    if mix == "noncanonical":  # >= r : the reference uses the raw 256-bit integer (multiexp.cpp:26-41)
+        return [min((1 << 256) - 1, o.R_MOD + rnd.randrange(1 << 200)) if i % 3 == 0 else (1 << 256) - 1 - i for i in range(n)]
+    raise ValueError(mix)
+
+
+@pytest.mark.parametrize("mix", SCALAR_MIXES)
+def test_msm_g1_matches_reference(gpu, kzp, oracle, ref, mix):
+    o = oracle
+    rnd = random.Random(sum(map(ord, mix)))
+    n = 2500
+    pts = _rand_g1(o, rnd, n)
+    pts[5] = None                       # infinity base (multiexp.cpp:57)
+    pts[7] = pts[6]                     # equal bases meeting in one bucket -> doubling branch
+    pts[9] = o.g1_neg(pts[8])           # opposite bases -> bucket returns to infinity
+    sc = _scalars(o, rnd, n, mix)
+    if mix in ("uniform", "keyless"):
+        sc[6] = sc[7] = 0x1234
+        sc[8] = sc[9] = 0x4321
+    bases = b"".join(o.g1_to_zkey_bytes(p) for p in pts)
+    S = b"".join(o.le32(v) for v in sc)
+    for m in (n, 0, 1, 2, 3, 33, 1000):
+        msm = kzp.Msm(0, bases[:64 * m])
+        got = msm.run(S[:32 * m])
+        msm.close()
+        assert got == ref.msm(0, bases[:64 * m], S[:32 * m]), (mix, m)
+
+
+@pytest.mark.parametrize("mix", ["uniform", "keyless", "edges"])
+def test_msm_g2_matches_reference(gpu, kzp, oracle, ref, mix):
+    o = oracle
+    rnd = random.Random(77)
+    n = 300
+    pts, acc = [], o.g2_mul(o.G2_GEN, rnd.randrange(1, o.R_MOD))
+    step = o.g2_mul(o.G2_GEN, rnd.randrange(1, o.R_MOD))
+    for _ in range(n):
+        pts.append(acc)
+        acc = o.g2_add(acc, step)
+    pts[3] = None
+    pts[5] = pts[4]
+    sc = _scalars(o, rnd, n, mix)
+    sc[4] = sc[5] = 99
+    bases = b"".join(o.g2_to_zkey_bytes(p) for p in pts)
+    S = b"".join(o.le32(v) for v in sc)
+    for m in (n, 1, 2, 50):
+        msm = kzp.Msm(1, bases[:128 * m])
+        got = msm.run(S[:32 * m])
+        msm.close()
+        assert got == ref.msm(1, bases[:128 * m], S[:32 * m]), (mix, m)
+
+
+def test_msm_reference_kats(gpu, kzp, oracle):
+    o = oracle
+    # multiExp2, RS/alt_bn128_test.cpp:215-248
+    b0 = (1626275109576878988287730541908027724405348106427831594181487487855202143055,
+          18706364085805828895917702468512381358405767972162700276238017959231481018884)
+    b1 = (17245156998235704504461341147511350131061011207199931581281143511105381019978,
+          3858908536032228066651712470282632925312300188207189106507111128103204506804)
+    s = [1, 20187316456970436521602619671088988952475789765726813868033071292105413408473]
+    want = (9163953212624378696742080269971059027061360176019470242548968584908855004282,
+            20922060990592511838374895951081914567856345629513259026540392951012456141360)
+    m = kzp.Msm(0, o.g1_to_zkey_bytes(b0) + o.g1_to_zkey_bytes(b1))
+    assert m.run(o.le32(s[0]) + o.le32(s[1])) == o.g1_to_canonical_bytes(want)
+    m.close()
+    # multiExp, :172-212 : bases (i+1)G, scalars (i+1), n = 40000 -> (sum (i+1)^2) G
+    n = 40000
+    pts, acc = [], None
+    for _ in range(n):
+        acc = o.g1_add(acc, o.G1_GEN)
+        pts.append(acc)
+    m = kzp.Msm(0, b"".join(o.g1_to_zkey_bytes(p) for p in pts))
+    got = m.run(b"".join(o.le32(i + 1) for i in range(n)))
+    m.close()
+    assert got == o.g1_to_canonical_bytes(o.g1_mul(o.G1_GEN, sum((i + 1) ** 2 for i in range(n))))
+    # expToOrder, :138-170 : r * G = infinity (single-base MSM with a non-canonical scalar)
+    m = kzp.Msm(0, o.g1_to_zkey_bytes(o.G1_GEN))
+    assert m.run(o.le32(o.R_MOD)) == bytes(64)
+    m.close()
+    m = kzp.Msm(1, o.g2_to_zkey_bytes(o.G2_GEN))
+    assert m.run(o.le32(o.R_MOD)) == bytes(128)
+    m.close()
+
+
+# ---------------------------------------------------------------- whole proofs
+def _check_against_expected(o, p, zkey, wtns, exp):
+    r, s = bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"])
+    p.keep_ab(True)
+    js, metrics = p.prove(wtns, r, s)
+    assert js == exp["proof"]                      # final proof bytes
+    assert p.h_coefficients().hex() == exp["h"]    # H coefficients, natural order, canonical
+    assert p.msm_results().hex() == exp["msm"]     # A, B1, B2, C, H affine canonical
+    assert p.ab().hex() == exp["ab"]               # a, b after the SpMV (Montgomery)
+    assert metrics["prover_time"] >= 0
+
+
+@pytest.mark.parametrize("name,zkey,wtns", [("toy", "toy_1.zkey", "toy.wtns"), ("syn256", "syn256.zkey", "syn256.wtns")])
+def test_proof_matches_golden(gpu, kzp, oracle, name, zkey, wtns):
+    d = os.path.join(GOLDEN, name)
+    exp = json.load(open(os.path.join(d, "expected.json")))
+    with kzp.FullProver(os.path.join(d, zkey)) as p:
+        _check_against_expected(oracle, p, os.path.join(d, zkey), os.path.join(d, wtns), exp)
+        # prove_mem (additive entry point) gives the same bytes
+        w = oracle.read_wtns(os.path.join(d, wtns))
+        js, _ = p.prove_mem(b"".join(oracle.le32(v) for v in w), bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"]))
+        assert js == exp["proof"]
+        # fresh blinding: different bytes, still verifies under the circuit's VK (prover_handler.rs:329-336)
+        js2, _ = p.prove(os.path.join(d, wtns))
+        assert js2 != exp["proof"]
+        zk = oracle.read_zkey(os.path.join(d, zkey))
+        pa, pb, pc = oracle.proof_from_json(js2)
+        assert oracle.groth16_verify(oracle.vk_from_zkey(zk), exp["public"], pa, pb, pc)
+        assert not oracle.groth16_verify(oracle.vk_from_zkey(zk), [exp["public"][0] + 1], pa, pb, pc)
+
+
+def test_toy_load_test(gpu, kzp, oracle):
+    """dummy_circuit_load_test (prover-service/src/tests/prover_handler.rs:279-290): prove toy.wtns repeatedly
+    (100 here, 1000 there) with fresh randomness and verify the last proof with public input 2."""
+    d = os.path.join(GOLDEN, "toy")
+    with kzp.FullProver(os.path.join(d, "toy_1.zkey")) as p:
+        seen = set()
+        for _ in range(100):
+            js, _ = p.prove(os.path.join(d, "toy.wtns"))
+            seen.add(js)
+        assert len(seen) == 100
+    vk = oracle.vk_from_snarkjs_json(json.load(open(os.path.join(d, "toy_vk.json"))))
+    pa, pb, pc = oracle.proof_from_json(js)
+    assert oracle.groth16_verify(vk, [2], pa, pb, pc)
+
+
+@pytest.mark.parametrize("n_constraints,n_vars,seed", [(4000, 3800, 3), (60000, 58000, 1)])
+def test_proof_matches_reference_generated(gpu, kzp, oracle, ref, port, workdir, n_constraints, n_vars, seed):
+    """Synthetic keyless-shaped circuits generated on the box (2^12 and the BASELINE config-1 size 2^16):
+    proof bytes, H coefficients and every MSM result equal the reference's."""
+    z = os.path.join(workdir, "g%d.zkey" % n_vars)
+    w = os.path.join(workdir, "g%d.wtns" % n_vars)
+    info = port.make_setup(n_constraints, n_vars, seed, z, w)
+    rnd = random.Random(seed)
+    r, s = oracle.le32(rnd.randrange(oracle.R_MOD >> 2)), oracle.le32(rnd.randrange(oracle.R_MOD >> 2))
+    rj, _ = ref.prove(z, w, r, s)
+    _, rh, rm = ref.dump(z, w, info["domain"])
+    with kzp.FullProver(z) as p:
+        assert (p.n_vars, p.domain_size) == (info["n_vars"], info["domain"])
+        js, _ = p.prove(w, r, s)
+        assert js == rj
+        assert p.h_coefficients() == rh
+        assert p.msm_results() == rm
+        # sharded mode on one GPU: 2 and 3 shards' partials assemble to the same proof
+    for world in (2, 3):
+        parts = []
+        for k in range(world):
+            with kzp.FullProver(z, shard=(k, world)) as ps:
+                ps.upload_witness_file(w)
+                ps.run_gpu()
+                parts.append(ps.partials())
+        js_sharded, msm = kzp.host_assemble(z, parts, r, s)
+        assert js_sharded == rj and msm == rm, world
+    pa, pb, pc = oracle.proof_from_json(rj)
+    zk_vk = oracle.read_zkey(z) if n_vars < 5000 else None
+    if zk_vk is not None:
+        assert oracle.groth16_verify(oracle.vk_from_zkey(zk_vk), [info["public_input"]], pa, pb, pc)
+
+
+# ---------------------------------------------------------------- boundary behaviour (RS/fullprover.cpp:80-125,204-250)
+def test_error_behaviour(gpu, kzp, oracle, workdir):
+    toy = os.path.join(GOLDEN, "toy")
+    with pytest.raises(kzp.ZKeyFileLoadError):
+        kzp.FullProver("/nonexistent/file.zkey")
+    with pytest.raises(kzp.UnsupportedZKeyCurve):
+        kzp.FullProver(os.path.join(toy, "toy.wtns"))  # wrong magic
+    data = bytearray(open(os.path.join(toy, "toy_1.zkey"), "rb").read())
+    i = data.index(bytes.fromhex("010000f093f5e143"))
+    data[i] ^= 2
+    bad = os.path.join(workdir, "badprime.zkey")
+    open(bad, "wb").write(bytes(data))
+    with pytest.raises(kzp.UnsupportedZKeyCurve):
+        kzp.FullProver(bad)
+    with kzp.FullProver(os.path.join(toy, "toy_1.zkey")) as p:
+        # witness over another prime -> WITNESS_GENERATION_INVALID_CURVE (fullprover.cpp:216-221)
+        w = bytearray(open(os.path.join(toy, "toy.wtns"), "rb").read())
+        j = w.index(bytes.fromhex("010000f093f5e143"))
+        w[j] ^= 2
+        wp = os.path.join(workdir, "badprime.wtns")
+        open(wp, "wb").write(bytes(w))
+        with pytest.raises(kzp.WitnessGenerationInvalidCurve):
+            p.prove(wp)
+        # unreadable / short witness -> INVALID_INPUT (the reference throws)
+        with pytest.raises(kzp.InvalidInput):
+            p.prove("/nonexistent.wtns")
+        with pytest.raises(kzp.InvalidInput):
+            p.prove_mem(bytes(64))
+        # the prover is still usable afterwards
+        exp = json.load(open(os.path.join(toy, "expected.json")))
+        js, _ = p.prove(os.path.join(toy, "toy.wtns"), bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"]))
+        assert js == exp["proof"]
+
+
+def test_cxx_abi_drop_in(gpu, kzp, oracle, workdir):
+    """The Itanium-ABI class the Rust binding links against (include/fullprover_b200.hpp), driven from C++ with the
+    blinding scalars injected through KZP_FIXED_RS: same bytes as the reference."""
+    toy = os.path.join(GOLDEN, "toy")
+    exp = json.load(open(os.path.join(toy, "expected.json")))
+    src, exe = os.path.join(workdir, "abi_run.cpp"), os.path.join(workdir, "abi_run")
+    open(src, "w").write(r'''
+#include <cstdio>
+#include <cstring>
+#include "fullprover_b200.hpp"
+int main(int argc, char** argv) {
+    FullProver p(argv[1]);
+    int state; memcpy(&state, reinterpret_cast<char*>(&p) + 8, 4);
+    ProverResponse r = p.prove(argv[2]);
+    printf("%d %d %d %s\n", state, (int)r.type, (int)r.error, r.raw_json);
+    return 0;
+}
+''')
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           kzp.LIB_PATH, "-Wl,-rpath," + os.path.dirname(kzp.LIB_PATH)])
+    env = dict(os.environ, KZP_FIXED_RS=exp["r"] + exp["s"])
+    out = subprocess.check_output([exe, os.path.join(toy, "toy_1.zkey"), os.path.join(toy, "toy.wtns")], text=True, env=env)
+    state, rtype, err, js = out.strip().split(" ", 3)
+    assert (state, rtype, err) == ("0", "0", "0")
+    assert js == exp["proof"]
+
+
+@pytest.mark.slow
+def test_keyless_shape_full_size(gpu, kzp, oracle, ref, port, workdir):
+    """BASELINE config 2: nVars 1,343,588, 1,376,867 constraints (+2 public rows) -> domain 2^21. The GPU proof
+    equals the reference prover's bytes on the same zkey/witness/(r,s), and verifies under the trapdoor VK."""
+    z, w = os.path.join(workdir, "keyless.zkey"), os.path.join(workdir, "keyless.wtns")
+    info = port.make_setup(1376867, 1343588, 2, z, w)
+    assert info["domain"] == 1 << 21 and info["n_vars"] == 1343588
+    r, s = oracle.le32(random.Random(11).randrange(oracle.R_MOD >> 2)), oracle.le32(random.Random(12).randrange(oracle.R_MOD >> 2))
+    with kzp.FullProver(z) as p:
+        js, _ = p.prove(w, r, s)
+        gh, gm = p.h_coefficients(), p.msm_results()
+    rj, _ = ref.prove(z, w, r, s)
+    assert js == rj
+    _, rh, rm = ref.dump(z, w, info["domain"])
+    assert gh == rh and gm == rm
+    pa, pb, pc = oracle.proof_from_json(js)
+    # VK from the zkey header + IC section only (reading 1.3M points in Python would be slow)
+    sec = oracle.read_binfile(z, b"zkey", 1)
+    hdr = sec[2][0]
+    vk = oracle.VerifyingKey(oracle.g1_from_zkey_bytes(hdr[84:148]), oracle.g2_from_zkey_bytes(hdr[212:340]),
+                             oracle.g2_from_zkey_bytes(hdr[340:468]), oracle.g2_from_zkey_bytes(hdr[532:660]),
+                             [oracle.g1_from_zkey_bytes(sec[3][0][i * 64:(i + 1) * 64]) for i in range(2)])
+    assert oracle.groth16_verify(vk, [info["public_input"]], pa, pb, pc)

@@ -1,0 +1,229 @@
+"""CPU-side tests of the product library: it loads, exports every symbol the headers declare, its host-only helpers
+agree with the oracle, and every compute entry point refuses to run without a GPU (no CPU fallback exists)."""
+import ctypes
+import json
+import os
+import random
+import re
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def _declared_c_symbols():
+    text = open(os.path.join(ROOT, "include", "kzp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kzp_[a-z0-9_]+)\s*\(", text)))
+
+
+MANGLED = [
+    "_ZN10FullProverC1EPKc", "_ZN10FullProverD1Ev", "_ZNK10FullProver5proveEPKc",
+    "_ZN14ProverResponseC1E11ProverError", "_ZN14ProverResponseC1EPKc21ProverResponseMetrics",
+    "_ZN14ProverResponseD1Ev", "_ZN14ProverResponse12empty_stringE",
+]
+
+
+def test_library_exports_every_declared_symbol(kzp):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", kzp.LIB_PATH], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    declared = _declared_c_symbols()
+    assert len(declared) >= 30
+    missing = [s for s in declared if s not in exported]
+    assert not missing, "declared in include/kzp_b200.h but not exported: %s" % missing
+    # the Itanium-ABI symbols bindgen binds for rust-rapidsnark
+    assert not [s for s in MANGLED if s not in exported]
+    L = kzp.lib()
+    for s in declared:
+        getattr(L, s)
+
+
+def test_no_oracle_in_product(kzp):
+    """The product library must not link or embed the CPU checkers."""
+    out = subprocess.check_output(["ldd", kzp.LIB_PATH], text=True)
+    assert "kzp_ref" not in out and "kzp_port" not in out and "gmp" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "keyless-zk-proofs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "import bn254" not in src and "libkzp_port" not in src and "libkzp_ref" not in src, f
+
+
+def test_host_field_ops_match_oracle(kzp, oracle):
+    rnd = random.Random(7)
+    L = kzp.lib()
+    # 0/1/2: 64-bit-limb host fields used by the proof assembly; 10/11/12: the portable path of the device templates
+    for field, mod in ((0, oracle.R_MOD), (1, oracle.Q_MOD), (10, oracle.R_MOD), (11, oracle.Q_MOD)):
+        for i in range(300):
+            a, b = rnd.randrange(mod), rnd.randrange(mod)
+            if i % 11 == 0:
+                a = mod - 1
+            if i % 13 == 0:
+                b = 0
+            for op, want in ((0, oracle.mont_mul(a, b, mod)), (1, (a + b) % mod), (2, (a - b) % mod), (3, (-a) % mod),
+                             (4, oracle.to_mont(a, mod)), (5, oracle.from_mont(a, mod)), (6, oracle.mont_mul(a, a, mod))):
+                out = ctypes.create_string_buffer(32)
+                assert L.kzp_host_field_op(field, op, oracle.le32(a), oracle.le32(b), out) == 0
+                assert oracle.from_le(out.raw) == want, (field, op, hex(a), hex(b))
+        a = rnd.randrange(1, mod)
+        out = ctypes.create_string_buffer(32)
+        L.kzp_host_field_op(field, 7, oracle.le32(oracle.to_mont(a, mod)), None, out)
+        assert oracle.from_mont(oracle.from_le(out.raw), mod) == pow(a, -1, mod)
+    for field in (2, 12):
+        enc = lambda x: oracle.le32(oracle.to_mont(x[0], oracle.Q_MOD)) + oracle.le32(oracle.to_mont(x[1], oracle.Q_MOD))
+        dec = lambda r: (oracle.from_mont(oracle.from_le(r[:32]), oracle.Q_MOD), oracle.from_mont(oracle.from_le(r[32:]), oracle.Q_MOD))
+        for _ in range(40):
+            a = (rnd.randrange(oracle.Q_MOD), rnd.randrange(oracle.Q_MOD))
+            b = (rnd.randrange(oracle.Q_MOD), rnd.randrange(oracle.Q_MOD))
+            out = ctypes.create_string_buffer(64)
+            L.kzp_host_field_op(field, 0, enc(a), enc(b), out)
+            assert dec(out.raw) == oracle.f2_mul(a, b)
+            L.kzp_host_field_op(field, 6, enc(a), None, out)
+            assert dec(out.raw) == oracle.f2_sqr(a)
+            L.kzp_host_field_op(field, 7, enc(a), None, out)
+            assert dec(out.raw) == oracle.f2_inv(a)
+
+
+def test_field_kats_on_host_paths(kzp, oracle):
+    """The reference's limb-level KATs (canonical inputs) through both host instantiations of the field code."""
+    L = kzp.lib()
+    opcode = {"mul": 0, "add": 1, "sub": 2, "square": 6}
+    n = 0
+    for rec in json.load(open(os.path.join(GOLDEN, "field_kats.json"))):
+        mod = oracle.R_MOD if rec["field"] == "Fr" else oracle.Q_MOD
+        a, b = int(rec["a"], 16), int(rec.get("b", "0x0"), 16)
+        if a >= mod or b >= mod:
+            continue
+        for field in ((0, 10) if rec["field"] == "Fr" else (1, 11)):
+            out = ctypes.create_string_buffer(32)
+            L.kzp_host_field_op(field, opcode[rec["op"]], oracle.le32(a), oracle.le32(b), out)
+            assert oracle.from_le(out.raw) == int(rec["expected"], 16), rec
+            n += 1
+    assert n >= 40
+
+
+def test_decimal_printing(kzp, oracle):
+    L = kzp.lib()
+    buf = ctypes.create_string_buffer(100)
+    rnd = random.Random(3)
+    vals = [0, 1, 9, 10, 999999999, 1000000000, 10 ** 18, oracle.Q_MOD - 1] + [rnd.randrange(oracle.Q_MOD) for _ in range(50)]
+    for v in vals:
+        assert L.kzp_host_fq_decimal(oracle.le32(oracle.to_mont(v, oracle.Q_MOD)), buf, 100) == 0
+        assert buf.value.decode() == str(v)
+    assert L.kzp_host_fq_decimal(oracle.le32(5), buf, 1) != 0  # buffer too small
+
+
+def test_zkey_parsing_and_error_classes(kzp, oracle, workdir):
+    L = kzp.lib()
+    nv, npub, dom, nc, st = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64(), ctypes.c_int()
+    args = (ctypes.byref(nv), ctypes.byref(npub), ctypes.byref(dom), ctypes.byref(nc), ctypes.byref(st))
+    toy = os.path.join(GOLDEN, "toy", "toy_1.zkey")
+    assert L.kzp_host_parse_zkey(toy.encode(), *args) == 0
+    assert (nv.value, npub.value, dom.value, nc.value, st.value) == (3, 1, 4, 4, 0)
+    syn = os.path.join(GOLDEN, "syn256", "syn256.zkey")
+    assert L.kzp_host_parse_zkey(syn.encode(), *args) == 0
+    zk = oracle.read_zkey(syn)
+    assert (nv.value, npub.value, dom.value, nc.value) == (zk.n_vars, zk.n_public, zk.domain_size, len(zk.coefs))
+    # missing file -> ZKEY_FILE_LOAD_ERROR (std::system_error in the reference, fullprover.cpp:96-100)
+    assert L.kzp_host_parse_zkey(b"/nonexistent/x.zkey", *args) == 3 and st.value == 1
+    # wrong magic / version / protocol / prime -> UNSUPPORTED_ZKEY_CURVE (std::invalid_argument, fullprover.cpp:91-95)
+    data = bytearray(open(toy, "rb").read())
+    cases = {}
+    cases["magic"] = bytes(b"wtns") + bytes(data[4:])
+    v = bytearray(data); v[4] = 2; cases["version"] = bytes(v)
+    p = bytearray(data); i = data.index(bytes.fromhex("010000f093f5e143")); p[i] ^= 0x02; cases["prime"] = bytes(p)
+    cases["truncated"] = bytes(data[:200])
+    for name, blob in cases.items():
+        path = os.path.join(workdir, "bad_%s.zkey" % name)
+        open(path, "wb").write(blob)
+        assert L.kzp_host_parse_zkey(path.encode(), *args) == 2, name
+        assert st.value == 2, name
+
+
+def test_everything_refuses_without_gpu(kzp, oracle):
+    if kzp.device_count() > 0:
+        pytest.skip("a GPU is present; the refusal path is exercised on the CPU-only box")
+    with pytest.raises(kzp.ZKeyFileLoadError) as e:
+        kzp.FullProver(os.path.join(GOLDEN, "toy", "toy_1.zkey"))
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(kzp.KzpError):
+        kzp.fr_ntt(bytes(64))
+    with pytest.raises(kzp.KzpError):
+        kzp.Msm(0, bytes(64))
+    with pytest.raises(kzp.KzpError):
+        kzp.field_op(0, 0, bytes(32), bytes(32))
+    with pytest.raises(kzp.KzpError):
+        kzp.imad_peak(16)
+
+
+def _partials_from_oracle(oracle, zk, w, lo_hi):
+    """What one shard must produce, computed by the oracle: MSM sums over the shard's base ranges, XYZZ-encoded."""
+    (alo, ahi), (clo, chi), (hlo, hhi), h = lo_hi
+    A = oracle.msm_naive_g1(zk.points_a[alo:ahi], w[alo:ahi])
+    B1 = oracle.msm_naive_g1(zk.points_b1[alo:ahi], w[alo:ahi])
+    B2 = oracle.msm_naive_g2(zk.points_b2[alo:ahi], w[alo:ahi])
+    cw = w[zk.n_public + 1:]
+    C = oracle.msm_naive_g1(zk.points_c[clo:chi], cw[clo:chi])
+    H = oracle.msm_naive_g1(zk.points_h[hlo:hhi], h[hlo:hhi])
+    one = oracle.le32(oracle.to_mont(1, oracle.Q_MOD))
+
+    def g1(p):
+        return (oracle.g1_to_zkey_bytes(p) + one + one) if p is not None else (one + one + bytes(64))
+
+    def g2(p):
+        return (oracle.g2_to_zkey_bytes(p) + one + bytes(32) + one + bytes(32)) if p is not None else \
+            (one + bytes(32) + one + bytes(32) + bytes(128))
+
+    return g1(A) + g1(B1) + g1(C) + g1(H) + g2(B2)
+
+
+def test_host_assemble_of_sharded_partials(kzp, oracle):
+    """Rank-0 step of the sharded mode with partials supplied by the oracle: the product's host
+    assembly must reproduce the reference's proof bytes for 1, 2 and 3 shards."""
+    d = os.path.join(GOLDEN, "syn256")
+    exp = json.load(open(os.path.join(d, "expected.json")))
+    zk = oracle.read_zkey(os.path.join(d, "syn256.zkey"))
+    w = oracle.read_wtns(os.path.join(d, "syn256.wtns"))
+    h = [oracle.from_le(bytes.fromhex(exp["h"])[i * 32:(i + 1) * 32]) for i in range(zk.domain_size)]
+    r, s = bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"])
+    for world in (1, 2, 3):
+        parts = []
+        for k in range(world):
+            rng = lambda n: (k * n // world, (k + 1) * n // world)
+            parts.append(_partials_from_oracle(oracle, zk, w, (rng(zk.n_vars), rng(zk.n_vars - zk.n_public - 1),
+                                                                  rng(zk.domain_size), h)))
+        js, msm = kzp.host_assemble(os.path.join(d, "syn256.zkey"), parts, r, s)
+        assert js == exp["proof"], world
+        assert msm.hex() == exp["msm"], world
+    # fresh randomness: still a valid proof
+    js, _ = kzp.host_assemble(os.path.join(d, "syn256.zkey"), parts, None, None)
+    assert js != exp["proof"]
+    pa, pb, pc = oracle.proof_from_json(js)
+    assert oracle.groth16_verify(oracle.vk_from_zkey(zk), exp["public"], pa, pb, pc)
+
+
+def test_cxx_abi_header_compiles_and_links(kzp, workdir):
+    """A C++ translation unit written against include/fullprover_b200.hpp links against libkzp_b200.so and sees the
+    reference's object layouts; without a GPU the constructor reports a state instead of throwing."""
+    src = os.path.join(workdir, "abi_check.cpp")
+    exe = os.path.join(workdir, "abi_check")
+    open(src, "w").write(r'''
+#include <cstdio>
+#include <cstring>
+#include "fullprover_b200.hpp"
+int main(int argc, char** argv) {
+    static_assert(sizeof(FullProver) == 16, "FullProver size");
+    static_assert(sizeof(ProverResponse) == 24, "ProverResponse size");
+    FullProver p(argv[1]);
+    int state; memcpy(&state, reinterpret_cast<char*>(&p) + 8, 4);
+    ProverResponse r = p.prove(argc > 2 ? argv[2] : "/nonexistent.wtns");
+    printf("%d %d %d %d %s\n", state, (int)r.type, (int)r.error, r.metrics.prover_time, r.raw_json);
+    return 0;
+}
+''')
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           kzp.LIB_PATH, "-Wl,-rpath," + os.path.dirname(kzp.LIB_PATH)])
+    out = subprocess.check_output([exe, "/nonexistent/k.zkey"], text=True).split()
+    # state ZKEY_FILE_LOAD_ERROR(1), response ERROR(1), error PROVER_NOT_READY(1)
+    assert out[:3] == ["1", "1", "1"]
