@@ -90,6 +90,8 @@ template <class XY>
 struct MsmScratch
 {
     uint32_t  cap_entries = 0;
+    uint32_t  chunk       = kMsmChunk; // sorted entries per accumulate thread for this MSM
+    uint32_t* heavy       = nullptr;   // [0] = number of heavy buckets, [1..] their ids
     uint32_t* counts      = nullptr; // kMsmBuckets + 2
     uint32_t* offsets     = nullptr; // kMsmBuckets + 2 (offsets[b] = first entry of bucket b; [B+1] = total)
     uint32_t* cursor      = nullptr; // kMsmBuckets + 2

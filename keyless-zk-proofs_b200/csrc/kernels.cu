@@ -12,6 +12,7 @@
 
 #include "device.hpp"
 #include "hostff.hpp"
+#include "ntt_tiled.cuh"
 
 namespace kzp
 {
@@ -167,6 +168,17 @@ void fr_scale(Fr* x, uint64_t n, const Fr& k, cudaStream_t st)
     KZP_CUDA_CHECK(cudaGetLastError());
 }
 
+static void ntt_level_attrs()
+{
+    // per device; cheap enough to repeat
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
+}
+
+// Sizes with k >= 11 run as 7-stage shared-memory levels (ntt_tiled.cuh) plus at most 6 plain stages; smaller ones
+// (2^k < one CTA's 16 tiles) run entirely as plain stages.
+static bool ntt_use_levels(uint32_t log_n) { return log_n >= kNttTileBits + 4; }
+
 void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st)
 {
     uint32_t log_n = d.log_n;
@@ -179,8 +191,23 @@ void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st)
         }
         return;
     }
+    uint32_t hi = log_n;
+    if (ntt_use_levels(log_n))
+    {
+        ntt_level_attrs();
+        unsigned int grid = 1u << (log_n - kNttTileBits - 4);
+        while (hi >= (uint32_t)kNttTileBits)
+        {
+            uint32_t lo = hi - kNttTileBits;
+            k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(x, d.tw_inv, log_n, lo, 0, lo == 0 ? post : nullptr);
+            KZP_CUDA_CHECK(cudaGetLastError());
+            hi = lo;
+        }
+        if (hi == 0)
+            return;
+    }
     unsigned int grid = div_up(1ull << (log_n - 1), 256);
-    for (int lh = (int)log_n - 1; lh >= 0; lh--)
+    for (int lh = (int)hi - 1; lh >= 0; lh--)
     {
         k_ntt_dif_stage<<<grid, 256, 0, st>>>(x, d.tw_inv, log_n, (uint32_t)lh, lh == 0 ? post : nullptr);
         KZP_CUDA_CHECK(cudaGetLastError());
@@ -192,11 +219,24 @@ void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st)
     uint32_t log_n = d.log_n;
     if (log_n == 0)
         return;
-    unsigned int grid = div_up(1ull << (log_n - 1), 256);
-    for (uint32_t lh = 0; lh < log_n; lh++)
+    bool         levels = ntt_use_levels(log_n);
+    uint32_t     r      = levels ? log_n % kNttTileBits : log_n;
+    unsigned int grid   = div_up(1ull << (log_n - 1), 256);
+    for (uint32_t lh = 0; lh < r; lh++)
     {
         k_ntt_dit_stage<<<grid, 256, 0, st>>>(x, d.tw_fwd, log_n, lh);
         KZP_CUDA_CHECK(cudaGetLastError());
+    }
+    if (!levels)
+        return;
+    ntt_level_attrs();
+    unsigned int lgrid = 1u << (log_n - kNttTileBits - 4);
+    uint32_t     plo   = 0;
+    for (uint32_t lo = r; lo + kNttTileBits <= log_n; lo += kNttTileBits)
+    {
+        k_ntt_level<true><<<lgrid, kNttThreads, kNttLevelSmem, st>>>(x, d.tw_fwd, log_n, lo, plo, nullptr);
+        KZP_CUDA_CHECK(cudaGetLastError());
+        plo = lo;
     }
 }
 

@@ -210,17 +210,17 @@ static __global__ void __launch_bounds__(256)
 template <class XY>
 __global__ void __launch_bounds__(128)
     k_msm_accumulate(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
-                     const typename XY::Affine* __restrict__ table, XY* __restrict__ records)
+                     const typename XY::Affine* __restrict__ table, XY* __restrict__ records, uint32_t chunk)
 {
     typedef typename XY::Affine Affine;
     typedef typename XY::Field  F;
     uint32_t t     = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t total = offsets[kMsmBuckets + 1];
-    uint64_t start64 = (uint64_t)t * kMsmChunk;
+    uint64_t start64 = (uint64_t)t * chunk;
     if (start64 >= total)
         return;
     uint32_t start = (uint32_t)start64;
-    uint32_t end   = min(start + kMsmChunk, total);
+    uint32_t end   = min(start + chunk, total);
     // largest b in [1, B] with offsets[b] <= start
     uint32_t lo = 1, hi = kMsmBuckets;
     while (lo < hi)
@@ -287,54 +287,77 @@ __device__ __forceinline__ void block_tree_sum(XY* sm, uint32_t active, uint32_t
     __syncthreads();
 }
 
-// One block per bucket: sum that bucket's records.
+// Bucket finalisation: sum the records of each bucket. Light buckets (the common case: a few dozen records) take
+// one thread each; buckets with more than kHeavyRecords records (a bit-heavy witness puts ~half of all entries in
+// bucket 1) are queued and summed by whole blocks in a second kernel, so no thread serialises a long run.
+constexpr uint32_t kHeavyRecords = 96;
+
+template <class XY>
+__global__ void __launch_bounds__(128)
+    k_msm_bucket_finalize(const uint32_t* __restrict__ offsets, const XY* __restrict__ records,
+                          XY* __restrict__ buckets, uint32_t chunk, uint32_t* __restrict__ heavy_count,
+                          uint32_t* __restrict__ heavy_ids)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (b > kMsmBuckets)
+        return;
+    uint32_t lo = offsets[b], hi = offsets[b + 1];
+    XY       acc;
+    XY::set_inf(acc);
+    if (lo != hi)
+    {
+        uint32_t t0  = lo / chunk;
+        uint32_t t1  = (hi - 1) / chunk;
+        uint32_t cnt = t1 - t0 + 1;
+        if (cnt > kHeavyRecords)
+        {
+            heavy_ids[atomicAdd(heavy_count, 1u)] = b;
+            return;
+        }
+        const XY* rec = records + (size_t)t0 + b;
+        acc           = rec[0];
+        for (uint32_t k = 1; k < cnt; k++)
+        {
+            XY r = rec[k];
+            if (sizeof(XY) > 128)
+                cold_add(acc, r);
+            else
+                XY::add(acc, r);
+        }
+    }
+    buckets[b] = acc;
+}
+
 template <class XY>
 __global__ void __launch_bounds__(256)
-    k_msm_bucket_finalize(const uint32_t* __restrict__ offsets, const XY* __restrict__ records,
-                          XY* __restrict__ buckets)
+    k_msm_bucket_finalize_heavy(const uint32_t* __restrict__ offsets, const XY* __restrict__ records,
+                                XY* __restrict__ buckets, uint32_t chunk, const uint32_t* __restrict__ heavy_count,
+                                const uint32_t* __restrict__ heavy_ids)
 {
     extern __shared__ uint4 smem_raw[];
-    XY*                     sm = reinterpret_cast<XY*>(smem_raw);
-    uint32_t                b  = blockIdx.x + 1;
-    uint32_t                lo = offsets[b], hi = offsets[b + 1];
+    XY*                     sm  = reinterpret_cast<XY*>(smem_raw);
     uint32_t                tid = threadIdx.x;
-    if (lo == hi)
+    uint32_t                n   = *heavy_count;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x)
     {
-        if (tid == 0)
-        {
-            XY z;
-            XY::set_inf(z);
-            buckets[b] = z;
-        }
-        return;
-    }
-    uint32_t t0  = lo / kMsmChunk;
-    uint32_t t1  = (hi - 1) / kMsmChunk;
-    uint32_t cnt = t1 - t0 + 1;
-    const XY* rec = records + (size_t)t0 + b;
-    if (cnt == 1)
-    {
-        if (tid == 0)
-            buckets[b] = rec[0];
-        return;
-    }
-    uint32_t active = 2;
-    while (active < cnt && active < blockDim.x)
-        active <<= 1;
-    if (tid < active)
-    {
-        XY acc;
+        uint32_t  b   = heavy_ids[i];
+        uint32_t  lo  = offsets[b], hi = offsets[b + 1];
+        uint32_t  t0  = lo / chunk;
+        uint32_t  cnt = (hi - 1) / chunk - t0 + 1;
+        const XY* rec = records + (size_t)t0 + b;
+        XY        acc;
         XY::set_inf(acc);
-        for (uint32_t k = tid; k < cnt; k += active)
+        for (uint32_t k = tid; k < cnt; k += blockDim.x)
         {
             XY r = rec[k];
             cold_add(acc, r);
         }
         sm[tid] = acc;
+        block_tree_sum(sm, blockDim.x, tid);
+        if (tid == 0)
+            buckets[b] = sm[0];
+        __syncthreads();
     }
-    block_tree_sum(sm, active, tid);
-    if (tid == 0)
-        buckets[b] = sm[0];
 }
 
 // ---- bucket reduction: sum_b b * bucket[b] ------------------------------------------------------------
@@ -561,7 +584,7 @@ void msm_bases_destroy(MsmBases<XY>& b)
 template <class XY>
 static void msm_set_smem_attrs()
 {
-    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_bucket_finalize<XY>,
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_bucket_finalize_heavy<XY>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(256 * sizeof(XY))));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_reduce1<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -581,7 +604,9 @@ void msm_scratch_create(MsmScratch<XY>& s, uint32_t n_active)
     KZP_CUDA_CHECK(cudaMalloc(&s.offsets, nb * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.cursor, nb * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.sorted, std::max<uint64_t>(cap, 1) * 4));
-    KZP_CUDA_CHECK(cudaMalloc(&s.records, (cap / kMsmChunk + nb + 1) * sizeof(XY)));
+    s.chunk = cap >= (1u << 24) ? 2 * kMsmChunk : kMsmChunk; // fewer, longer runs for the big MSMs
+    KZP_CUDA_CHECK(cudaMalloc(&s.records, (cap / s.chunk + nb + 1) * sizeof(XY)));
+    KZP_CUDA_CHECK(cudaMalloc(&s.heavy, (nb + 1) * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.buckets, (kMsmBuckets + 1) * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.partial, 2 * (kMsmBuckets / 256) * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.result, sizeof(XY)));
@@ -597,6 +622,7 @@ void msm_scratch_destroy(MsmScratch<XY>& s)
     cudaFree(s.cursor);
     cudaFree(s.sorted);
     cudaFree(s.records);
+    cudaFree(s.heavy);
     cudaFree(s.buckets);
     cudaFree(s.partial);
     cudaFree(s.result);
@@ -625,13 +651,16 @@ void msm_run(const MsmBases<XY>& b, MsmScratch<XY>& s, const uint32_t* scalars, 
     {
         k_msm_scatter<<<msm_div_up(b.n, 256), 256, 0, st>>>(scalars, b.scalar_idx, b.n, s.cursor, s.sorted);
         KZP_CUDA_CHECK(cudaGetLastError());
-        uint64_t threads = ((uint64_t)b.n * kMsmWindows + kMsmChunk - 1) / kMsmChunk;
+        uint64_t threads = ((uint64_t)b.n * kMsmWindows + s.chunk - 1) / s.chunk;
         KZP_CUDA_CHECK(cudaEventRecord(s.ev_acc0, st));
-        k_msm_accumulate<XY><<<msm_div_up(threads, 128), 128, 0, st>>>(s.offsets, s.sorted, b.table, s.records);
+        k_msm_accumulate<XY><<<msm_div_up(threads, 128), 128, 0, st>>>(s.offsets, s.sorted, b.table, s.records, s.chunk);
         KZP_CUDA_CHECK(cudaGetLastError());
         KZP_CUDA_CHECK(cudaEventRecord(s.ev_acc1, st));
     }
-    k_msm_bucket_finalize<XY><<<kMsmBuckets, 256, 256 * sizeof(XY), st>>>(s.offsets, s.records, s.buckets);
+    KZP_CUDA_CHECK(cudaMemsetAsync(s.heavy, 0, 4, st));
+    k_msm_bucket_finalize<XY><<<msm_div_up(kMsmBuckets, 128), 128, 0, st>>>(s.offsets, s.records, s.buckets, s.chunk, s.heavy, s.heavy + 1);
+    KZP_CUDA_CHECK(cudaGetLastError());
+    k_msm_bucket_finalize_heavy<XY><<<128, 256, 256 * sizeof(XY), st>>>(s.offsets, s.records, s.buckets, s.chunk, s.heavy, s.heavy + 1);
     KZP_CUDA_CHECK(cudaGetLastError());
     k_msm_reduce1<XY><<<kMsmBuckets / 256, 256, 512 * sizeof(XY), st>>>(s.buckets, s.partial);
     KZP_CUDA_CHECK(cudaGetLastError());

@@ -1,0 +1,259 @@
+// Shared-memory radix-128 NTT levels for sm_100a.
+//
+// A transform of size 2^k is split into levels of 7 stages. One level applied to index bits [lo, lo+7) is a plain
+// 128-point DFT along those bits (twiddles are powers of w_128 only) plus one "boundary" twiddle per element that
+// connects it to the remaining levels (the classic four-step factorisation, applied recursively):
+//   DIF (inverse direction here, natural in -> bit-reversed out): levels from the top bits down, boundary twiddle
+//        w^( (pos mod 2^lo) * bitrev7(t) * 2^(k-hi) ) applied on the way out;
+//   DIT (forward, bit-reversed in -> natural out): levels from the low bits up, boundary twiddle
+//        w^( bitrev_{k-lo}(pos >> lo) * ((pos >> plo) mod 2^(lo-plo)) * 2^plo ) applied on the way in.
+// Stages left over when k is not a multiple of 7 run as plain radix-2 stages (kernels.cu), which compose with the
+// levels because both are exact factorisations of the same DFT (validated stage by stage in tests).
+//
+// One CTA = 256 threads = 16 tiles x 128 points = 2048 elements = 64 KiB of shared memory, stored as two planes of
+// uint4 with the column index rotated by the row (phys = 16 t + ((c + t) & 15)) so that both the column-fastest
+// accesses of the butterfly rounds and the row-fastest accesses of the contiguous level are bank-conflict free.
+// Global traffic is coalesced 128-bit accesses in runs of >= 512 B; every element is read and written once per
+// level. Each thread runs radix-8 butterflies on 8 elements held in registers (rounds of 3, 3 and 1 stages).
+// Replaces FFT<Fr>::fft / ifft (rust-rapidsnark/rapidsnark/src/fft.cpp:192-246) together with kernels.cu.
+#pragma once
+
+#include "device.hpp"
+
+namespace kzp
+{
+
+constexpr int kNttTileBits = 7;
+constexpr int kNttTileCols = 16;
+constexpr int kNttThreads  = 256;
+
+__device__ __forceinline__ uint32_t ntt_phys(uint32_t t, uint32_t c) { return 16u * t + ((c + t) & 15u); }
+
+__device__ __forceinline__ void ntt_sm_store(uint4* sm, uint32_t t, uint32_t c, const Fr& v)
+{
+    uint32_t p   = ntt_phys(t, c);
+    sm[p]        = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    sm[2048 + p] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+}
+
+__device__ __forceinline__ void ntt_sm_load(const uint4* sm, uint32_t t, uint32_t c, Fr& v)
+{
+    uint32_t p  = ntt_phys(t, c);
+    uint4    lo = sm[p], hi = sm[2048 + p];
+    v.v[0] = lo.x; v.v[1] = lo.y; v.v[2] = lo.z; v.v[3] = lo.w;
+    v.v[4] = hi.x; v.v[5] = hi.y; v.v[6] = hi.z; v.v[7] = hi.w;
+}
+
+// w^e for e < 2^k from the half table tw[i] = w^i, i < 2^(k-1)   (w^(2^(k-1)) = -1)
+__device__ __forceinline__ void ntt_root(Fr& r, const Fr* __restrict__ tw, uint32_t e, uint32_t k)
+{
+    uint32_t half = 1u << (k - 1);
+    if (e < half)
+        r = tw[e];
+    else
+    {
+        Fr t = tw[e - half];
+        Fr::neg(r, t);
+    }
+}
+
+// Radix-8 butterflies on v[0..7] = elements t = t_rest + (q << sh), q = 0..7, covering the stages with half-distance
+// 2^(sh+2), 2^(sh+1), 2^sh (DIF order) or the reverse (DIT order). nst = number of stages (3, or 1 for the last round,
+// where only the half-distance-2^sh stage runs on pairs (q, q+1)). twT[j] = w_128^j, j < 64.
+template <bool DIT>
+__device__ __forceinline__ void ntt_round(Fr (&v)[8], const Fr* twT, uint32_t t_low, uint32_t sh, int nst)
+{
+    if (nst == 1)
+    {
+        // single stage, half-distance 2^sh with sh == 0: twiddle index j = t mod 1 = 0 -> no multiplication
+#pragma unroll
+        for (int q = 0; q < 8; q += 2)
+        {
+            Fr u = v[q], w = v[q + 1];
+            Fr::add(v[q], u, w);
+            Fr::sub(v[q + 1], u, w);
+        }
+        return;
+    }
+    if (!DIT)
+    {
+#pragma unroll
+        for (int u = 2; u >= 0; u--)
+        {
+            // stage h = 2^(sh+u): pairs differ in bit u of q; j = t mod h = t_low + ((q & (2^u - 1)) << sh)
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+            {
+                if (q & (1 << u))
+                    continue;
+                int      q2  = q | (1 << u);
+                uint32_t j   = t_low + ((uint32_t)(q & ((1 << u) - 1)) << sh);
+                uint32_t idx = j << (6 - sh - u);
+                Fr       a = v[q], b = v[q2], d;
+                Fr::add(v[q], a, b);
+                Fr::sub(d, a, b);
+                if (idx != 0)
+                    Fr::mul(v[q2], d, twT[idx]);
+                else
+                    v[q2] = d;
+            }
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int u = 0; u <= 2; u++)
+        {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+            {
+                if (q & (1 << u))
+                    continue;
+                int      q2  = q | (1 << u);
+                uint32_t j   = t_low + ((uint32_t)(q & ((1 << u) - 1)) << sh);
+                uint32_t idx = j << (6 - sh - u);
+                Fr       a = v[q], b = v[q2];
+                if (idx != 0)
+                    Fr::mul(b, b, twT[idx]);
+                Fr::add(v[q], a, b);
+                Fr::sub(v[q2], a, b);
+            }
+        }
+    }
+}
+
+// One level on bits [lo, lo+7) of a size-2^k transform. tw: w^i (forward) or w^-i (inverse), i < 2^(k-1).
+// post (DIF only, may be null): element at position pos is multiplied by post[pos] on the way out.
+template <bool DIT>
+__global__ void __launch_bounds__(kNttThreads, 2)
+    k_ntt_level(Fr* __restrict__ x, const Fr* __restrict__ tw, uint32_t k, uint32_t lo, uint32_t plo,
+                const Fr* __restrict__ post)
+{
+    extern __shared__ uint4 ntt_smem[];
+    uint4*                  sm  = ntt_smem;                                   // 2 planes x 2048 uint4
+    Fr*                     twT = reinterpret_cast<Fr*>(ntt_smem + 2 * 2048); // 64 roots of order 128
+    const uint32_t          tid = threadIdx.x;
+    const uint32_t          hi  = lo + kNttTileBits;
+    if (tid < 64)
+        twT[tid] = tw[(size_t)tid << (k - kNttTileBits)];
+
+    const uint32_t rest0    = blockIdx.x * kNttTileCols;
+    const uint32_t low_mask = (1u << lo) - 1u;
+    // element (t, c) of this CTA lives at global position pos(t, c)
+    auto pos_of = [&](uint32_t t, uint32_t c) -> uint32_t {
+        uint32_t rest = rest0 + c;
+        return ((rest >> lo) << hi) | (t << lo) | (rest & low_mask);
+    };
+
+    // ---- load (coalesced), boundary twiddle for DIT
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+    {
+        uint32_t e = tid + 256u * q;
+        uint32_t t, c;
+        if (lo == 0)
+        {
+            c = e >> 7;
+            t = e & 127u;
+        }
+        else
+        {
+            t = e >> 4;
+            c = e & 15u;
+        }
+        uint32_t pos = pos_of(t, c);
+        Fr       val = x[pos];
+        if (DIT && lo > 0)
+        {
+            uint32_t upper = pos >> lo;
+            uint32_t brv   = __brev(upper) >> (32 - (k - lo));
+            uint32_t kt    = (pos >> plo) & ((1u << (lo - plo)) - 1u);
+            uint32_t ex    = (brv * kt) << plo;
+            if (ex != 0)
+            {
+                Fr w;
+                ntt_root(w, tw, ex, k);
+                Fr::mul(val, val, w);
+            }
+        }
+        ntt_sm_store(sm, t, c, val);
+    }
+    __syncthreads();
+
+    // ---- three rounds of radix-8 butterflies in registers
+    const uint32_t c = tid & 15u;
+    const uint32_t g = tid >> 4; // 0..15
+    Fr             v[8];
+#pragma unroll 1
+    for (int r = 0; r < 3; r++)
+    {
+        int      round = DIT ? 2 - r : r; // DIF: A, B, C ; DIT: C, B, A
+        uint32_t t_rest, sh;
+        int      nst;
+        if (round == 0)
+        {
+            t_rest = g;
+            sh     = 4;
+            nst    = 3;
+        }
+        else if (round == 1)
+        {
+            t_rest = (g >> 1) * 16u + (g & 1u);
+            sh     = 1;
+            nst    = 3;
+        }
+        else
+        {
+            t_rest = g * 8u;
+            sh     = 0;
+            nst    = 1;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            ntt_sm_load(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
+        ntt_round<DIT>(v, twT, t_rest & ((1u << sh) - 1u), sh, nst);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            ntt_sm_store(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
+        __syncthreads();
+    }
+
+    // ---- store (coalesced), boundary twiddle for DIF, optional pointwise post-multiplier
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+    {
+        uint32_t e = tid + 256u * q;
+        uint32_t t, cc;
+        if (lo == 0)
+        {
+            cc = e >> 7;
+            t  = e & 127u;
+        }
+        else
+        {
+            t  = e >> 4;
+            cc = e & 15u;
+        }
+        uint32_t pos = pos_of(t, cc);
+        Fr       val;
+        ntt_sm_load(sm, t, cc, val);
+        if (!DIT && lo > 0)
+        {
+            uint32_t m  = pos & low_mask;
+            uint32_t ex = (m * (__brev(t) >> 25)) << (k - hi);
+            if (ex != 0)
+            {
+                Fr w;
+                ntt_root(w, tw, ex, k);
+                Fr::mul(val, val, w);
+            }
+        }
+        if (!DIT && post)
+            Fr::mul(val, val, post[pos]);
+        x[pos] = val;
+    }
+}
+
+constexpr size_t kNttLevelSmem = 2 * 2048 * sizeof(uint4) + 64 * sizeof(Fr);
+
+} // namespace kzp

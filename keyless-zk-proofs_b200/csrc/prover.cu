@@ -502,7 +502,7 @@ public:
         tm.msm_b2_ms = el(8, 9);
         tm.msm_c_ms  = el(9, 10);
         tm.gpu_ms    = std::max(el(2, 5), el(2, 10));
-        uint32_t per_msm   = 7;
+        uint32_t per_msm   = 8;
         tm.kernel_launches = 1 + 3 * 2 * log_domain + 1 + 5 * per_msm;
     }
 

@@ -160,7 +160,7 @@ def test_g2_point_ops(gpu, kzp, oracle):
 
 
 # ---------------------------------------------------------------- NTT (RS/fft.cpp)
-@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 8, 10, 13, 16])
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 8, 10, 11, 12, 13, 14, 16, 17, 18, 21])
 def test_ntt_matches_reference(gpu, kzp, oracle, port, log_n):
     o = oracle
     n = 1 << log_n
@@ -188,7 +188,7 @@ def test_ntt_reference_roundtrip_kat(gpu, kzp, oracle, ref):
     assert kzp.fr_ntt(f, True) == data
 
 
-@pytest.mark.parametrize("log_n", [2, 9, 14])
+@pytest.mark.parametrize("log_n", [2, 9, 11, 14, 15])
 def test_coset_chain_matches_reference(gpu, kzp, oracle, port, log_n):
     """ifft -> multiply by w_2n^i -> fft, the per-vector chain of groth16.cpp:172-203."""
     o = oracle
