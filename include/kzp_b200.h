@@ -88,11 +88,12 @@ int kzp_prover_assemble(kzp_prover* p, const uint8_t* partials, int count, const
 /* introspection */
 int kzp_prover_info(kzp_prover* p, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size,
                     uint64_t* n_coefs, int* device);
-/* last proof: floats {h2d, spmv, ntt, msm_h, msm_a, msm_b1, msm_b2, msm_c, gpu, assemble_host, total_host,
- * kernel_launches}; returns the number of values written (<= cap) */
+/* last proof: floats {h2d, spmv, ntt, msm_h, msm_witness_sort, msm_witness_g1 (A,B1,C batched), msm_witness_g2 (B2),
+ * reserved, gpu, assemble_host, total_host, kernel_launches}; returns the number of values written (<= cap) */
 int kzp_prover_timings(kzp_prover* p, float* out, int cap);
 /* bucket-accumulation kernel (the dominant kernel) of MSM `which` (0 A, 1 B1, 2 B2, 3 C, 4 H) in the last proof:
- * its duration from CUDA events on its stream and the number of (point, bucket) entries it summed */
+ * its duration from CUDA events on its stream and the number of (point, bucket) entries it summed. A, B1 and C
+ * share one batched launch over one digit sort: 0, 1 and 3 return that launch and the shared entry count. */
 int kzp_prover_msm_profile(kzp_prover* p, int which, float* accumulate_ms, uint64_t* entries);
 /* parity artefacts of the last proof */
 int kzp_prover_get_h(kzp_prover* p, uint8_t* out, uint64_t out_bytes);       /* domain x 32, canonical */
@@ -124,7 +125,7 @@ int kzp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t*
 /* group: 0 G1, 1 G2; op: 0 xyzz += affine, 1 xyzz += xyzz, 2 double. p/out XYZZ (128/256 B per point). */
 int kzp_point_op(int group, int op, const uint8_t* p, const uint8_t* q, uint8_t* out, uint64_t count,
                  int device);
-/* integer-pipe roofline probe: independent 32x32+64 multiply-adds on every SM */
+/* integer-pipe roofline probe: carry-chained 32x32+64 multiply-adds (IMAD.WIDE.U32[.X]) on every SM */
 int kzp_imad_peak(int iters, int device, float* ms, uint64_t* multiply_adds);
 
 /* host-only helpers (no GPU needed): decimal printing and file parsing, for the CPU test suite */

@@ -161,7 +161,7 @@ def _take_string(ptr: ctypes.c_void_p) -> str:
     return s
 
 
-TIMING_KEYS = ("h2d_ms", "spmv_ms", "ntt_ms", "msm_h_ms", "msm_a_ms", "msm_b1_ms", "msm_b2_ms", "msm_c_ms",
+TIMING_KEYS = ("h2d_ms", "spmv_ms", "ntt_ms", "msm_h_ms", "msm_wsort_ms", "msm_wg1_ms", "msm_wg2_ms", "reserved_ms",
                "gpu_ms", "assemble_host_ms", "total_host_ms", "kernel_launches")
 
 

@@ -314,8 +314,8 @@ int kzp_prover_timings(kzp_prover* p, float* out, int cap)
     if (!p || !p->prover || !out)
         return 0;
     const ProveTimings& t = p->prover->timings();
-    float v[12] = {t.h2d_ms,    t.spmv_ms,   t.ntt_ms, t.msm_h_ms,         t.msm_a_ms,      t.msm_b1_ms,
-                   t.msm_b2_ms, t.msm_c_ms,  t.gpu_ms, t.assemble_host_ms, t.total_host_ms,
+    float v[12] = {t.h2d_ms,     t.spmv_ms,     t.ntt_ms, t.msm_h_ms,         t.msm_wsort_ms,  t.msm_wg1_ms,
+                   t.msm_wg2_ms, t.reserved_ms, t.gpu_ms, t.assemble_host_ms, t.total_host_ms,
                    (float)t.kernel_launches};
     int   n     = cap < 12 ? cap : 12;
     for (int i = 0; i < n; i++)
@@ -494,11 +494,29 @@ struct kzp_msm
     int                group  = 0;
     int                device = 0;
     uint64_t           n      = 0;
+    MsmSort            sort;
     MsmBases<G1Xyzz>   b1;
     MsmScratch<G1Xyzz> s1;
     MsmBases<G2Xyzz>   b2;
     MsmScratch<G2Xyzz> s2;
 };
+
+static void msm_launch(kzp_msm* m, const uint32_t* scalars)
+{
+    msm_sort_run(m->sort, scalars, 0);
+    if (m->group == 0)
+    {
+        const MsmBases<G1Xyzz>* b[1] = {&m->b1};
+        MsmScratch<G1Xyzz>*     s[1] = {&m->s1};
+        msm_reduce_batch<G1Xyzz>(m->sort, b, s, 1, 0);
+    }
+    else
+    {
+        const MsmBases<G2Xyzz>* b[1] = {&m->b2};
+        MsmScratch<G2Xyzz>*     s[1] = {&m->s2};
+        msm_reduce_batch<G2Xyzz>(m->sort, b, s, 1, 0);
+    }
+}
 
 kzp_msm* kzp_msm_new(int group, const uint8_t* bases, uint64_t n, int device)
 {
@@ -513,13 +531,15 @@ kzp_msm* kzp_msm_new(int group, const uint8_t* bases, uint64_t n, int device)
         m->n      = n;
         if (group == 0)
         {
-            msm_bases_create<G1Xyzz>(m->b1, bases, 0, n, 0, 0);
-            msm_scratch_create<G1Xyzz>(m->s1, m->b1.n);
+            msm_bases_create<G1Xyzz>(m->b1, bases, n, true, 0);
+            msm_sort_create(m->sort, m->b1.n, m->b1.scalar_idx, 0, 0);
+            msm_scratch_create<G1Xyzz>(m->s1, m->sort);
         }
         else
         {
-            msm_bases_create<G2Xyzz>(m->b2, bases, 0, n, 0, 0);
-            msm_scratch_create<G2Xyzz>(m->s2, m->b2.n);
+            msm_bases_create<G2Xyzz>(m->b2, bases, n, true, 0);
+            msm_sort_create(m->sort, m->b2.n, m->b2.scalar_idx, 0, 0);
+            msm_scratch_create<G2Xyzz>(m->s2, m->sort);
         }
     });
     if (rc != KZP_OK)
@@ -535,6 +555,7 @@ void kzp_msm_free(kzp_msm* m)
     if (!m)
         return;
     cudaSetDevice(m->device);
+    msm_sort_destroy(m->sort);
     msm_bases_destroy(m->b1);
     msm_scratch_destroy(m->s1);
     msm_bases_destroy(m->b2);
@@ -589,10 +610,7 @@ int kzp_msm_run(kzp_msm* m, const uint8_t* scalars, uint8_t* out)
         KZP_CUDA_CHECK(cudaSetDevice(m->device));
         DevBuf sc(m->n * 32);
         KZP_CUDA_CHECK(cudaMemcpy(sc.p, scalars, m->n * 32, cudaMemcpyHostToDevice));
-        if (m->group == 0)
-            msm_run<G1Xyzz>(m->b1, m->s1, (const uint32_t*)sc.p, 0);
-        else
-            msm_run<G2Xyzz>(m->b2, m->s2, (const uint32_t*)sc.p, 0);
+        msm_launch(m, (const uint32_t*)sc.p);
         KZP_CUDA_CHECK(cudaDeviceSynchronize());
         msm_result_to_canonical(m, out);
     });
@@ -609,12 +627,7 @@ int kzp_msm_bench(kzp_msm* m, const uint8_t* scalars, int iters, float* ms_per_m
         KZP_CUDA_CHECK(cudaSetDevice(m->device));
         DevBuf sc(m->n * 32);
         KZP_CUDA_CHECK(cudaMemcpy(sc.p, scalars, m->n * 32, cudaMemcpyHostToDevice));
-        auto run = [&] {
-            if (m->group == 0)
-                msm_run<G1Xyzz>(m->b1, m->s1, (const uint32_t*)sc.p, 0);
-            else
-                msm_run<G2Xyzz>(m->b2, m->s2, (const uint32_t*)sc.p, 0);
-        };
+        auto run = [&] { msm_launch(m, (const uint32_t*)sc.p); };
         for (int w = 0; w < 2; w++)
             run();
         KZP_CUDA_CHECK(cudaDeviceSynchronize());
@@ -634,9 +647,8 @@ int kzp_msm_bench(kzp_msm* m, const uint8_t* scalars, int iters, float* ms_per_m
             *ms_per_msm = ms / (float)(iters > 0 ? iters : 1);
         if (entries)
         {
-            uint32_t        total = 0;
-            const uint32_t* off   = m->group == 0 ? m->s1.offsets : m->s2.offsets;
-            KZP_CUDA_CHECK(cudaMemcpy(&total, off + kMsmBuckets + 1, 4, cudaMemcpyDeviceToHost));
+            uint32_t total = 0;
+            KZP_CUDA_CHECK(cudaMemcpy(&total, m->sort.offsets + kMsmBuckets + 1, 4, cudaMemcpyDeviceToHost));
             *entries = total;
         }
     });

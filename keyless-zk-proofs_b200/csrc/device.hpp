@@ -50,6 +50,7 @@ void ntt_domain_destroy(NttDomain& d);
 //   ntt_forward_dit : bit-reversed in -> natural out.
 void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st);
 void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st);
+uint32_t ntt_launches(uint32_t log_n); // kernels per transform
 // natural <-> bit-reversed permutation (only used by the component-level entry points that expose
 // the reference's natural-in/natural-out FFT::fft / FFT::ifft contract, fft.cpp:192-246)
 void ntt_bitrev_permute(Fr* x, uint32_t log_n, cudaStream_t st);
@@ -72,56 +73,87 @@ void h_pointwise(const Fr* a, const Fr* b, const Fr* c, Fr* h, uint64_t n, cudaS
 // ------------------------------------------------------------------ MSM
 // Signed 16-bit windows, 16 windows, and a per-key table of 2^(16 j) * P_i so that all windows share
 // ONE bucket set (2^15 buckets): bucket reduction and window combination happen once per MSM.
-constexpr int      kMsmWindowBits = 16;
-constexpr int      kMsmWindows    = 16;
-constexpr uint32_t kMsmBuckets    = 1u << (kMsmWindowBits - 1); // bucket ids 1..kMsmBuckets
-constexpr uint32_t kMsmChunk      = 32;                          // sorted entries per accumulate thread
+// The digit sort of a scalar vector (MsmSort) is separate from the group-specific part so that the
+// MSMs that share scalars (A, B1, C in G1 and B2 in G2 all run over the witness, groth16.cpp:88-112)
+// sort once and run their bucket work as one batched launch per stage.
+constexpr int      kMsmWindowBits   = 16;
+constexpr int      kMsmWindows      = 16;
+constexpr uint32_t kMsmBuckets      = 1u << (kMsmWindowBits - 1); // bucket ids 1..kMsmBuckets
+constexpr int      kMsmMaxBatch     = 3;                           // MSMs per batched launch
+constexpr uint32_t kMsmHeavyRecords = 32;   // buckets with more partial sums than this are pre-reduced by whole blocks
+constexpr uint32_t kMsmHeavyBlocks  = 32;   // blocks that cooperate on one heavy bucket
+constexpr uint32_t kMsmMaxHeavy     = 1024; // heavy buckets handled that way (the rest stay thread-serial)
+constexpr uint32_t kMsmFoldBlock    = 128;  // buckets per block of the finalise+fold kernel
+constexpr int      kMsmFoldLevels   = (kMsmWindowBits - 1 + 4) / 5; // base-32 digits of a bucket index
+
+struct MsmSort
+{
+    uint32_t  n             = 0;       // scalars covered
+    uint32_t  scalar_offset = 0;       // scalar index of element 0 when scalar_idx == nullptr
+    const uint32_t* scalar_idx = nullptr; // optional gather list (n entries, not owned)
+    uint32_t  cap_entries   = 0;
+    uint32_t  chunk         = 32;      // sorted entries per accumulate thread
+    uint32_t* counts        = nullptr; // kMsmBuckets + 2; counts[0] doubles as the heavy-bucket counter
+    uint32_t* offsets       = nullptr; // kMsmBuckets + 2 (offsets[b] = first entry of bucket b; [B+1] = total)
+    uint32_t* cursor        = nullptr; // kMsmBuckets + 2
+    uint32_t* sorted        = nullptr; // cap_entries
+    uint32_t* heavy_ids     = nullptr; // kMsmMaxHeavy
+    uint32_t* heavy_slot    = nullptr; // kMsmBuckets + 2: 0 = light bucket, k + 1 = k-th heavy bucket
+};
 
 template <class XY>
 struct MsmBases
 {
     typedef typename XY::Affine Affine;
-    uint32_t  n          = 0;       // active (non-infinity) bases
-    uint32_t* scalar_idx = nullptr; // n : index of each active base's scalar in the scalar vector
+    uint32_t  n          = 0;       // table columns (bases kept)
+    uint32_t* scalar_idx = nullptr; // n, only when infinity bases were filtered out: scalar index of each kept base
     Affine*   table      = nullptr; // kMsmWindows x n affine points: table[j*n + i] = 2^(16 j) * P_i
 };
 
 template <class XY>
 struct MsmScratch
 {
-    uint32_t  cap_entries = 0;
-    uint32_t  chunk       = kMsmChunk; // sorted entries per accumulate thread for this MSM
-    uint32_t* heavy       = nullptr;   // [0] = number of heavy buckets, [1..] their ids
-    uint32_t* counts      = nullptr; // kMsmBuckets + 2
-    uint32_t* offsets     = nullptr; // kMsmBuckets + 2 (offsets[b] = first entry of bucket b; [B+1] = total)
-    uint32_t* cursor      = nullptr; // kMsmBuckets + 2
-    uint32_t* sorted      = nullptr; // cap_entries
-    XY*       records     = nullptr; // cap_entries / kMsmChunk + kMsmBuckets + 2
-    XY*       buckets     = nullptr; // kMsmBuckets + 1
-    XY*       partial     = nullptr; // 2 * (kMsmBuckets / 256)
-    XY*       result      = nullptr; // 1 (device)
+    XY*       records       = nullptr; // cap_entries / chunk + kMsmBuckets + 2 partial sums, grouped by bucket
+    XY*       heavy_partial = nullptr; // kMsmMaxHeavy x kMsmHeavyBlocks
+    XY*       heavy_sum     = nullptr; // kMsmMaxHeavy
+    uint32_t* heavy_done    = nullptr; // kMsmMaxHeavy arrival counters (self-resetting)
+    XY*       s0part        = nullptr; // (kMsmBuckets / kMsmFoldBlock) x 32 : per block, per low digit
+    XY*       s1part        = nullptr; // (kMsmBuckets / kMsmFoldBlock) x 4  : per block, per warp
+    XY*       classes       = nullptr; // kMsmFoldLevels x 32 weighted class sums
+    XY*       result        = nullptr; // 1 (device)
     cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr; // bracket the bucket-accumulation kernel of the last run
 };
 
-// bases_host: n_total affine Montgomery points exactly as in the zkey (64 B G1 / 128 B G2), (0,0) = infinity.
-// Active bases are the non-infinity ones in [first, first+count) — base k takes scalar index scalar_offset + k.
+void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_t scalar_offset, uint32_t chunk);
+void msm_sort_destroy(MsmSort& s);
+// scalars: device array of 32-byte little-endian integers (canonical or not; reduced mod r on the fly).
+void msm_sort_run(MsmSort& s, const uint32_t* scalars, cudaStream_t st);
+uint32_t msm_default_chunk(uint64_t n);
+
+// points_host: `count` affine Montgomery points exactly as in the zkey (64 B G1 / 128 B G2), (0,0) = infinity.
+// filter_inf: drop infinity bases (like multiexp.cpp:57) and remember the scalar index of each kept base;
+// otherwise all `count` columns are kept (infinity columns are all-zero and cost one load per digit).
 template <class XY>
-void msm_bases_create(MsmBases<XY>& out, const uint8_t* bases_host, uint64_t first, uint64_t count,
-                      uint32_t scalar_offset, cudaStream_t st);
+void msm_bases_create(MsmBases<XY>& out, const uint8_t* points_host, uint64_t count, bool filter_inf,
+                      cudaStream_t st);
 template <class XY>
 void msm_bases_destroy(MsmBases<XY>& b);
 template <class XY>
-void msm_scratch_create(MsmScratch<XY>& s, uint32_t n_active);
+void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort);
 template <class XY>
 void msm_scratch_destroy(MsmScratch<XY>& s);
-// scalars: device array of 32-byte little-endian integers (canonical or not; reduced mod r on the fly).
-// Leaves the XYZZ result in s.result (device).
+// Bucket accumulation + reduction of `nb` <= kMsmMaxBatch MSMs that share one digit sort (bases[k]->n == sort.n).
+// Leaves each XYZZ result in scr[k]->result (device).
 template <class XY>
-void msm_run(const MsmBases<XY>& b, MsmScratch<XY>& s, const uint32_t* scalars, cudaStream_t st);
+void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, MsmScratch<XY>* const* scr, int nb,
+                      cudaStream_t st);
 
 // duration of the last bucket-accumulation launch (ms, CUDA events on its stream) and its number of sorted entries
 template <class XY>
-void msm_last_accumulate(const MsmScratch<XY>& s, float* ms, uint64_t* entries);
+void msm_last_accumulate(const MsmSort& sort, const MsmScratch<XY>& s, float* ms, uint64_t* entries);
+// kernels launched by one msm_sort_run / one msm_reduce_batch
+constexpr uint32_t kMsmSortLaunches   = 3;
+constexpr uint32_t kMsmReduceLaunches = 5;
 
 extern template struct MsmBases<G1Xyzz>;
 extern template struct MsmBases<G2Xyzz>;

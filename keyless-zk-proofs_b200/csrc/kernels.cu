@@ -179,6 +179,14 @@ static void ntt_level_attrs()
 // (2^k < one CTA's 16 tiles) run entirely as plain stages.
 static bool ntt_use_levels(uint32_t log_n) { return log_n >= kNttTileBits + 4; }
 
+// kernels launched by one ntt_inverse_dif / ntt_forward_dit call
+uint32_t ntt_launches(uint32_t log_n)
+{
+    if (log_n == 0)
+        return 0;
+    return ntt_use_levels(log_n) ? log_n / kNttTileBits + log_n % kNttTileBits : log_n;
+}
+
 void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st)
 {
     uint32_t log_n = d.log_n;
@@ -398,26 +406,49 @@ void field_op(int field, int op, const void* a, const void* b, void* out, uint64
     KZP_CUDA_CHECK(cudaGetLastError());
 }
 
-// Independent IMAD.WIDE chains, 8 accumulators per thread: the integer-pipe roofline denominator.
+// Integer-pipe roofline denominator: carry-chained 32x32+64 multiply-adds exactly as the Montgomery product issues
+// them (mad.lo.cc / madc.hi.cc pairs -> IMAD.WIDE.U32[.X]), two independent 4-long chains per thread whose
+// multiplicands come from the other chain so that nothing is loop invariant (ptxas hoists a probe with constant
+// operands; measured on B200: IMAD.WIDE issues at half the IMAD rate, profiles/r01_ubench_int_fp64_pipes.txt).
 __global__ void __launch_bounds__(256) k_imad_probe(uint32_t* sink, int iters)
 {
     uint32_t a = threadIdx.x * 2654435761u + 1u, b = blockIdx.x * 40503u + 3u;
-    unsigned long long acc[8];
+    uint32_t x[8], y[8];
 #pragma unroll
     for (int k = 0; k < 8; k++)
-        acc[k] = a + k;
+    {
+        x[k] = a + k;
+        y[k] = b + k;
+    }
     for (int it = 0; it < iters; it++)
     {
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b));
+        asm volatile("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+                     "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+                     "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+                     "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+                     "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+                     "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+                     "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+                     "madc.hi.u32 %7, %11, %12, %7;"
+                     : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7])
+                     : "r"(y[0]), "r"(y[2]), "r"(y[4]), "r"(y[6]), "r"(b));
+        asm volatile("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+                     "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+                     "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+                     "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+                     "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+                     "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+                     "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+                     "madc.hi.u32 %7, %11, %12, %7;"
+                     : "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7])
+                     : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(b));
     }
-    unsigned long long s = 0;
+    uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++)
-        s ^= acc[k];
-    if (s == 0x1234567ull)
-        sink[0] = (uint32_t)s;
+        s ^= x[k] ^ y[k];
+    if (s == 0x1234567u)
+        sink[0] = s;
 }
 
 uint64_t imad_probe(uint32_t* sink, int iters, cudaStream_t st)

@@ -1,7 +1,14 @@
-// Pippenger MSM pipeline templates (signed digits -> counting sort -> chunked bucket accumulation -> bucket
-// reduction) for sm_100a; instantiated for G1 in msm_g1.cu and for G2 in msm_g2.cu so the two build in parallel.
+// Group-specific part of the Pippenger MSM for sm_100a: chunked bucket accumulation over a shared digit sort
+// (msm_sort.cu), heavy-bucket pre-reduction, bucket finalisation fused with a base-32 digit fold, and the final
+// combination. Instantiated for G1 in msm_g1.cu and for G2 in msm_g2.cu so the two build in parallel.
 // Replaces ParallelMultiexp<Curve>::multiexp (rust-rapidsnark/rapidsnark/src/multiexp.cpp:183-245) and the
 // group law it calls (curve.cpp). Integer pipes only.
+//
+// Reduction sum_b b * B_b over bucket ids b = idx + 1, idx = i2 * 1024 + i1 * 32 + i0 (base-32 digits):
+//     result = sum_b B_b + sum_l 32^l * sum_v v * S_l[v],      S_l[v] = sum of the buckets whose digit l equals v
+// so the 2^15 buckets collapse into 3 x 32 plain class sums (perfectly parallel trees, no weights) and one
+// 32-term weighted sum that a single block finishes by bit decomposition. Every stage is sized by sequential
+// point additions, which is what bounds these latency-limited kernels.
 #pragma once
 
 #include <algorithm>
@@ -15,205 +22,35 @@ namespace kzp
 
 static inline unsigned int msm_div_up(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }
 
-// =====================================================================================================
-// MSM
-// =====================================================================================================
-// ---- scalar handling --------------------------------------------------------------------------------
-// Loads a 32-byte little-endian integer and brings it below r by repeated subtraction (at most 5 times
-// for any 256-bit value). For points of order r this matches the reference, which uses the raw bits.
-__device__ __forceinline__ void load_scalar(const uint32_t* __restrict__ scalars, uint32_t idx, Fr& s)
+template <class XY>
+struct MsmBatchArgs
 {
-    const uint4* p  = reinterpret_cast<const uint4*>(scalars + (size_t)idx * 8);
-    uint4        lo = p[0], hi = p[1];
-    s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
-    s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
-    while (s.v[7] >= FrParams::P7 && Fr::geq_p(s))
-    {
-        uint32_t bw = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-        {
-            uint32_t pi = modulus_limb<FrParams>(i);
-            uint64_t d  = (uint64_t)s.v[i] - pi - bw;
-            s.v[i]      = (uint32_t)d;
-            bw          = (uint32_t)(d >> 63);
-        }
-    }
-}
-
-// signed base-2^16 digits d_j in [-2^15, 2^15], sum d_j 2^(16 j) = s, for s < 2^255
-__device__ __forceinline__ int32_t next_digit(const Fr& s, int j, uint32_t& carry)
-{
-    uint32_t raw = (s.v[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-    uint32_t v   = raw + carry;
-    if (v > 0x8000u)
-    {
-        carry = 1;
-        return (int32_t)v - 0x10000;
-    }
-    carry = 0;
-    return (int32_t)v;
-}
-
-__device__ __forceinline__ bool scalar_is_small(const Fr& s)
-{
-    return (s.v[1] | s.v[2] | s.v[3] | s.v[4] | s.v[5] | s.v[6] | s.v[7]) == 0 && s.v[0] <= 0x8000u;
-}
-
-// Pass 1: histogram of bucket ids. Small scalars (one digit; the bulk of a circom witness: bits, bytes)
-// are warp-aggregated so that a million equal digits do not serialise on one counter.
-static __global__ void __launch_bounds__(256)
-    k_msm_count(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ scalar_idx, uint32_t n,
-                uint32_t* __restrict__ counts)
-{
-    uint32_t i     = blockIdx.x * blockDim.x + threadIdx.x;
-    bool     valid = i < n;
-    Fr       s     = Fr::zero();
-    if (valid)
-        load_scalar(scalars, scalar_idx[i], s);
-    bool     small = valid && scalar_is_small(s);
-    uint32_t lane  = threadIdx.x & 31;
-    uint32_t key   = (small && s.v[0] != 0) ? s.v[0] : (0xffff0000u | lane);
-    uint32_t peers = __match_any_sync(0xffffffffu, key);
-    if (small)
-    {
-        if (s.v[0] != 0 && lane == (uint32_t)(__ffs(peers) - 1))
-            atomicAdd(&counts[s.v[0]], (uint32_t)__popc(peers));
-        return;
-    }
-    if (!valid)
-        return;
-    uint32_t carry = 0;
-#pragma unroll
-    for (int j = 0; j < kMsmWindows; j++)
-    {
-        int32_t d = next_digit(s, j, carry);
-        if (d != 0)
-            atomicAdd(&counts[d < 0 ? -d : d], 1u);
-    }
-}
-
-// Exclusive scan of counts[1..B] -> offsets[b] (start of bucket b), offsets[B+1] = total; cursor = offsets.
-static __global__ void __launch_bounds__(1024)
-    k_msm_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-               uint32_t* __restrict__ cursor)
-{
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    const uint32_t      per = (kMsmBuckets + 1023) / 1024; // 32
-    uint32_t            tid = threadIdx.x;
-    uint32_t            b0  = 1 + tid * per;
-    uint32_t            loc[per];
-    uint32_t            sum = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < per; k++)
-    {
-        uint32_t b = b0 + k;
-        uint32_t c = (b <= kMsmBuckets) ? counts[b] : 0;
-        loc[k]     = sum;
-        sum += c;
-    }
-    // block exclusive scan of `sum`
-    uint32_t lane = tid & 31, wid = tid >> 5;
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= (uint32_t)o)
-            inc += t;
-    }
-    if (lane == 31)
-        warp_sums[wid] = inc;
-    __syncthreads();
-    if (wid == 0)
-    {
-        uint32_t ws = warp_sums[lane];
-        uint32_t wi = ws;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= (uint32_t)o)
-                wi += t;
-        }
-        warp_sums[lane] = wi - ws; // exclusive
-        if (lane == 31)
-            carry_s = wi;
-    }
-    __syncthreads();
-    uint32_t base = warp_sums[wid] + inc - sum;
-#pragma unroll
-    for (uint32_t k = 0; k < per; k++)
-    {
-        uint32_t b = b0 + k;
-        if (b <= kMsmBuckets)
-        {
-            offsets[b] = base + loc[k];
-            cursor[b]  = base + loc[k];
-        }
-    }
-    if (tid == 0)
-    {
-        offsets[0]               = 0;
-        offsets[kMsmBuckets + 1] = carry_s;
-    }
-}
-
-// Pass 2: scatter entry = (window * n + base) | sign << 31 into its bucket's range.
-static __global__ void __launch_bounds__(256)
-    k_msm_scatter(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ scalar_idx, uint32_t n,
-                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted)
-{
-    uint32_t i     = blockIdx.x * blockDim.x + threadIdx.x;
-    bool     valid = i < n;
-    Fr       s     = Fr::zero();
-    if (valid)
-        load_scalar(scalars, scalar_idx[i], s);
-    bool     small = valid && scalar_is_small(s);
-    uint32_t lane  = threadIdx.x & 31;
-    uint32_t key   = (small && s.v[0] != 0) ? s.v[0] : (0xffff0000u | lane);
-    uint32_t peers = __match_any_sync(0xffffffffu, key);
-    uint32_t leader = (uint32_t)(__ffs(peers) - 1);
-    uint32_t base   = 0;
-    if (small && s.v[0] != 0 && lane == leader)
-        base = atomicAdd(&cursor[s.v[0]], (uint32_t)__popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (small)
-    {
-        if (s.v[0] != 0)
-            sorted[base + __popc(peers & ((1u << lane) - 1))] = i; // window 0, positive
-        return;
-    }
-    if (!valid)
-        return;
-    uint32_t carry = 0;
-#pragma unroll
-    for (int j = 0; j < kMsmWindows; j++)
-    {
-        int32_t d = next_digit(s, j, carry);
-        if (d != 0)
-        {
-            uint32_t bkt = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-            uint32_t pos = atomicAdd(&cursor[bkt], 1u);
-            sorted[pos]  = ((uint32_t)j * n + i) | (d < 0 ? 0x80000000u : 0u);
-        }
-    }
-}
+    const typename XY::Affine* table[kMsmMaxBatch];
+    XY*                        records[kMsmMaxBatch];
+    XY*                        heavy_partial[kMsmMaxBatch];
+    XY*                        heavy_sum[kMsmMaxBatch];
+    uint32_t*                  heavy_done[kMsmMaxBatch];
+    XY*                        s0part[kMsmMaxBatch];
+    XY*                        s1part[kMsmMaxBatch];
+    XY*                        classes[kMsmMaxBatch];
+    XY*                        result[kMsmMaxBatch];
+};
 
 // ---- bucket accumulation ----------------------------------------------------------------------------
 // Thread t owns sorted[t*L, (t+1)*L). It emits one partial sum ("record") per bucket it touches at slot
 // t + bucket: the map (t, bucket) -> t + bucket is injective and monotone over the pairs that occur, and
 // the records of bucket b are exactly slots [lo/L + b, (hi-1)/L + b] for its range [lo, hi). Work per
 // thread is therefore independent of the digit distribution (a bit-heavy witness puts ~half of all
-// entries in bucket 1).
+// entries in bucket 1). blockIdx.y selects the MSM of the batch (same sort, different base table).
 template <class XY>
 __global__ void __launch_bounds__(128)
     k_msm_accumulate(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
-                     const typename XY::Affine* __restrict__ table, XY* __restrict__ records, uint32_t chunk)
+                     MsmBatchArgs<XY> args, uint32_t chunk)
 {
     typedef typename XY::Affine Affine;
     typedef typename XY::Field  F;
+    const Affine* __restrict__ table   = args.table[blockIdx.y];
+    XY* __restrict__           records = args.records[blockIdx.y];
     uint32_t t     = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t total = offsets[kMsmBuckets + 1];
     uint64_t start64 = (uint64_t)t * chunk;
@@ -287,67 +124,51 @@ __device__ __forceinline__ void block_tree_sum(XY* sm, uint32_t active, uint32_t
     __syncthreads();
 }
 
-// Bucket finalisation: sum the records of each bucket. Light buckets (the common case: a few dozen records) take
-// one thread each; buckets with more than kHeavyRecords records (a bit-heavy witness puts ~half of all entries in
-// bucket 1) are queued and summed by whole blocks in a second kernel, so no thread serialises a long run.
-constexpr uint32_t kHeavyRecords = 96;
 
+// L2-coherent load of a point written by another block of the same launch
 template <class XY>
-__global__ void __launch_bounds__(128)
-    k_msm_bucket_finalize(const uint32_t* __restrict__ offsets, const XY* __restrict__ records,
-                          XY* __restrict__ buckets, uint32_t chunk, uint32_t* __restrict__ heavy_count,
-                          uint32_t* __restrict__ heavy_ids)
+__device__ __forceinline__ XY load_cg(const XY* p)
 {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (b > kMsmBuckets)
-        return;
-    uint32_t lo = offsets[b], hi = offsets[b + 1];
-    XY       acc;
-    XY::set_inf(acc);
-    if (lo != hi)
-    {
-        uint32_t t0  = lo / chunk;
-        uint32_t t1  = (hi - 1) / chunk;
-        uint32_t cnt = t1 - t0 + 1;
-        if (cnt > kHeavyRecords)
-        {
-            heavy_ids[atomicAdd(heavy_count, 1u)] = b;
-            return;
-        }
-        const XY* rec = records + (size_t)t0 + b;
-        acc           = rec[0];
-        for (uint32_t k = 1; k < cnt; k++)
-        {
-            XY r = rec[k];
-            if (sizeof(XY) > 128)
-                cold_add(acc, r);
-            else
-                XY::add(acc, r);
-        }
-    }
-    buckets[b] = acc;
+    XY           r;
+    const uint4* src = reinterpret_cast<const uint4*>(p);
+    uint4*       dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(XY) / 16); i++)
+        dst[i] = __ldcg(src + i);
+    return r;
 }
 
+// ---- heavy buckets -------------------------------------------------------------------------------------
+// A bucket whose range spans more than kMsmHeavyRecords accumulate threads (bucket 1 of a bit-heavy witness holds
+// ~half of all entries) is summed by kMsmHeavyBlocks blocks: each reduces a slice of its records to one point, the
+// last block to arrive (arrival counter) sums the slices. grid = (kMsmHeavyBlocks, batch).
 template <class XY>
 __global__ void __launch_bounds__(256)
-    k_msm_bucket_finalize_heavy(const uint32_t* __restrict__ offsets, const XY* __restrict__ records,
-                                XY* __restrict__ buckets, uint32_t chunk, const uint32_t* __restrict__ heavy_count,
-                                const uint32_t* __restrict__ heavy_ids)
+    k_msm_heavy(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                const uint32_t* __restrict__ heavy_ids, MsmBatchArgs<XY> args, uint32_t chunk)
 {
     extern __shared__ uint4 smem_raw[];
-    XY*                     sm  = reinterpret_cast<XY*>(smem_raw);
-    uint32_t                tid = threadIdx.x;
-    uint32_t                n   = *heavy_count;
-    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x)
+    __shared__ uint32_t     s_last;
+    XY*                     sm      = reinterpret_cast<XY*>(smem_raw);
+    const XY* __restrict__  records = args.records[blockIdx.y];
+    XY*                     partial = args.heavy_partial[blockIdx.y];
+    XY*                     sums    = args.heavy_sum[blockIdx.y];
+    uint32_t*               done    = args.heavy_done[blockIdx.y];
+    uint32_t                tid     = threadIdx.x;
+    uint32_t                n       = min(counts[0], kMsmMaxHeavy);
+    for (uint32_t h = 0; h < n; h++)
     {
-        uint32_t  b   = heavy_ids[i];
+        uint32_t  b   = heavy_ids[h];
         uint32_t  lo  = offsets[b], hi = offsets[b + 1];
         uint32_t  t0  = lo / chunk;
         uint32_t  cnt = (hi - 1) / chunk - t0 + 1;
         const XY* rec = records + (size_t)t0 + b;
+        uint32_t  per = (cnt + gridDim.x - 1) / gridDim.x;
+        uint32_t  s   = blockIdx.x * per;
+        uint32_t  e   = min(s + per, cnt);
         XY        acc;
         XY::set_inf(acc);
-        for (uint32_t k = tid; k < cnt; k += blockDim.x)
+        for (uint32_t k = s + tid; k < e; k += blockDim.x)
         {
             XY r = rec[k];
             cold_add(acc, r);
@@ -355,97 +176,216 @@ __global__ void __launch_bounds__(256)
         sm[tid] = acc;
         block_tree_sum(sm, blockDim.x, tid);
         if (tid == 0)
-            buckets[b] = sm[0];
-        __syncthreads();
-    }
-}
-
-// ---- bucket reduction: sum_b b * bucket[b] ------------------------------------------------------------
-// Weighted tree over a power-of-two run held in shared memory: each node keeps (S, W) = (sum P_i,
-// sum i * P_i) of its segment; merging two segments of length len: S = Sl + Sr, W = Wl + Wr + len * Sr.
-template <class XY>
-__device__ __forceinline__ void weighted_tree(XY* S, XY* W, uint32_t count, uint32_t tid)
-{
-    uint32_t log_len = 0;
-    for (uint32_t cnt = count; cnt > 1; cnt >>= 1, log_len++)
-    {
-        XY   s, w;
-        bool on = tid < (cnt >> 1);
-        __syncthreads();
-        if (on)
         {
-            XY sl = S[2 * tid], sr = S[2 * tid + 1];
-            XY wl = W[2 * tid], wr = W[2 * tid + 1];
-            s     = sl;
-            cold_add(s, sr);
-            w = wl;
-            cold_add(w, wr);
-            for (uint32_t k = 0; k < log_len; k++)
-                cold_dbl(sr);
-            cold_add(w, sr);
+            partial[(size_t)h * kMsmHeavyBlocks + blockIdx.x] = sm[0];
+            __threadfence();
+            uint32_t ticket = atomicAdd(&done[h], 1u);
+            s_last          = (ticket == gridDim.x - 1) ? 1u : 0u;
         }
         __syncthreads();
-        if (on)
+        if (s_last)
         {
-            S[tid] = s;
-            W[tid] = w;
+            __threadfence();
+            if (tid < kMsmHeavyBlocks)
+            {
+                if (tid < gridDim.x)
+                    sm[tid] = load_cg(partial + (size_t)h * kMsmHeavyBlocks + tid);
+                else
+                    XY::set_inf(sm[tid]);
+            }
+            block_tree_sum(sm, kMsmHeavyBlocks, tid);
+            if (tid == 0)
+            {
+                sums[h] = sm[0];
+                done[h] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- bucket finalisation + first fold -------------------------------------------------------------------
+// Block = kMsmFoldBlock (128) consecutive buckets, thread = bucket: sum its records (or take the heavy sum), then
+// fold inside the block: lane sums over the 4 warps (digit 0 classes) and warp sums (digit 1 class of each warp;
+// higher digits are constant over a block). grid = (kMsmBuckets / 128, batch).
+template <class XY>
+__global__ void __launch_bounds__(kMsmFoldBlock)
+    k_msm_finalize_fold(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ heavy_slot,
+                        MsmBatchArgs<XY> args, uint32_t chunk)
+{
+    extern __shared__ uint4 smem_raw[];
+    XY*                     sm      = reinterpret_cast<XY*>(smem_raw);
+    const XY* __restrict__  records = args.records[blockIdx.y];
+    uint32_t                tid     = threadIdx.x;
+    uint32_t                b       = blockIdx.x * kMsmFoldBlock + tid + 1;
+    uint32_t                lo = offsets[b], hi = offsets[b + 1];
+    XY                      acc;
+    XY::set_inf(acc);
+    if (lo != hi)
+    {
+        uint32_t slot = heavy_slot[b];
+        if (slot)
+            acc = args.heavy_sum[blockIdx.y][slot - 1];
+        else
+        {
+            uint32_t  t0  = lo / chunk;
+            uint32_t  cnt = (hi - 1) / chunk - t0 + 1;
+            const XY* rec = records + (size_t)t0 + b;
+            acc           = rec[0];
+            for (uint32_t k = 1; k < cnt; k++)
+            {
+                XY r = rec[k];
+                cold_add(acc, r);
+            }
         }
     }
+    sm[tid] = acc;
     __syncthreads();
-}
-
-// stage 1: block k reduces buckets [256k+1, 256k+256] to (S_k, W_k) with local weights 0..255
-template <class XY>
-__global__ void __launch_bounds__(256)
-    k_msm_reduce1(const XY* __restrict__ buckets, XY* __restrict__ partial)
-{
-    extern __shared__ uint4 smem_raw[];
-    XY*                     S   = reinterpret_cast<XY*>(smem_raw);
-    XY*                     W   = S + 256;
-    uint32_t                tid = threadIdx.x;
-    S[tid]                      = buckets[(size_t)blockIdx.x * 256 + 1 + tid];
-    XY z;
-    XY::set_inf(z);
-    W[tid] = z;
-    weighted_tree(S, W, 256, tid);
-    if (tid == 0)
+    if (tid < 32)
     {
-        partial[2 * blockIdx.x]     = S[0];
-        partial[2 * blockIdx.x + 1] = W[0];
-    }
-}
-
-// stage 2: result = sum_k W_k + sum_k S_k + 256 * sum_k k * S_k      (K = B/256 blocks of stage 1)
-template <class XY>
-__global__ void __launch_bounds__(128)
-    k_msm_reduce2(const XY* __restrict__ partial, XY* __restrict__ result)
-{
-    extern __shared__ uint4 smem_raw[];
-    constexpr uint32_t      K   = kMsmBuckets / 256;
-    XY*                     S   = reinterpret_cast<XY*>(smem_raw);
-    XY*                     W   = S + K;
-    XY*                     T   = W + K;
-    uint32_t                tid = threadIdx.x;
-    XY                      z;
-    XY::set_inf(z);
-    if (tid < K)
-    {
-        S[tid] = partial[2 * tid];
-        T[tid] = partial[2 * tid + 1];
-        W[tid] = z;
+        XY t = sm[tid];
+#pragma unroll 1
+        for (uint32_t w = 1; w < kMsmFoldBlock / 32; w++)
+        {
+            XY u = sm[32 * w + tid];
+            cold_add(t, u);
+        }
+        args.s0part[blockIdx.y][(size_t)blockIdx.x * 32 + tid] = t;
     }
     __syncthreads();
-    block_tree_sum(T, K, tid);
-    weighted_tree(S, W, K, tid);
+    uint32_t lane = tid & 31;
+#pragma unroll 1
+    for (uint32_t stride = 16; stride > 0; stride >>= 1)
+    {
+        if (lane < stride)
+        {
+            XY a = sm[tid], c = sm[tid + stride];
+            cold_add(a, c);
+            sm[tid] = a;
+        }
+        __syncwarp();
+    }
+    if (lane == 0)
+        args.s1part[blockIdx.y][(size_t)blockIdx.x * (kMsmFoldBlock / 32) + (tid >> 5)] = sm[tid];
+}
+
+// ---- second fold: the kMsmFoldLevels x 32 class sums -----------------------------------------------------
+// Block (l, v) sums every partial of the buckets whose base-32 digit l equals v and scales it by 32^l.
+// grid = (32 * kMsmFoldLevels, batch), 256 threads.
+template <class XY>
+__global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args)
+{
+    extern __shared__ uint4 smem_raw[];
+    XY*                     sm   = reinterpret_cast<XY*>(smem_raw);
+    constexpr uint32_t      nblk = kMsmBuckets / kMsmFoldBlock;
+    constexpr uint32_t      wpb  = kMsmFoldBlock / 32; // warps (digit-1 classes) per fold block
+    const XY* __restrict__  s0   = args.s0part[blockIdx.y];
+    const XY* __restrict__  s1   = args.s1part[blockIdx.y];
+    uint32_t                tid  = threadIdx.x;
+    uint32_t                l    = blockIdx.x >> 5;
+    uint32_t                v    = blockIdx.x & 31;
+    XY                      acc;
+    XY::set_inf(acc);
+    if (l == 0)
+    {
+        for (uint32_t t = tid; t < nblk; t += blockDim.x)
+        {
+            XY r = s0[(size_t)t * 32 + v];
+            cold_add(acc, r);
+        }
+    }
+    else if (l == 1)
+    {
+        // fold block blk holds digit-1 values wpb * (blk % (32 / wpb)) + w
+        constexpr uint32_t period = 32 / wpb;
+        for (uint32_t t = tid; t < nblk / period; t += blockDim.x)
+        {
+            XY r = s1[(size_t)(t * period + v / wpb) * wpb + (v % wpb)];
+            cold_add(acc, r);
+        }
+    }
+    else
+    {
+        // digit l of idx = blk * 128 + .. is ((blk >> shift) & 31) with shift = 5 l - 7: whole blocks
+        uint32_t shift = 5 * l - 7;
+        uint32_t span  = 1u << shift;                 // consecutive blocks sharing the digit
+        uint32_t reps  = (nblk + (span << 5) - 1) / (span << 5);
+        uint32_t nterm = reps * span * wpb;
+        for (uint32_t t = tid; t < nterm; t += blockDim.x)
+        {
+            uint32_t w   = t % wpb;
+            uint32_t q   = t / wpb;
+            uint32_t blk = ((q >> shift) << (shift + 5)) | (v << shift) | (q & (span - 1));
+            if (blk < nblk)
+            {
+                XY r = s1[(size_t)blk * wpb + w];
+                cold_add(acc, r);
+            }
+        }
+    }
+    sm[tid] = acc;
+    block_tree_sum(sm, blockDim.x, tid);
     if (tid == 0)
     {
-        XY r = W[0];
-        for (int k = 0; k < 8; k++)
+        XY r = sm[0];
+        for (uint32_t k = 0; k < 5 * l; k++)
             cold_dbl(r);
-        XY s0 = S[0], t0 = T[0];
-        cold_add(r, s0);
-        cold_add(r, t0);
-        result[0] = r;
+        args.classes[blockIdx.y][blockIdx.x] = r;
+    }
+}
+
+// ---- final combination -----------------------------------------------------------------------------------
+// result = T + sum_v v * E[v], E[v] = sum_l classes[l][v] (already scaled), T = sum_v classes[0][v].
+// Warps 0..4 build Z_k = sum of E[v] over v with bit k set, warp 5 builds T, thread 0 runs Horner over k.
+// grid = (1, batch), 192 threads.
+template <class XY>
+__global__ void __launch_bounds__(192) k_msm_final(MsmBatchArgs<XY> args)
+{
+    extern __shared__ uint4 smem_raw[];
+    XY*                     sm  = reinterpret_cast<XY*>(smem_raw);
+    const XY* __restrict__  cls = args.classes[blockIdx.y];
+    uint32_t                tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    XY                      e   = cls[lane];
+    if (w < 5)
+    {
+        if ((lane >> w) & 1u)
+        {
+#pragma unroll 1
+            for (int l = 1; l < kMsmFoldLevels; l++)
+            {
+                XY u = cls[32 * l + lane];
+                cold_add(e, u);
+            }
+        }
+        else
+            XY::set_inf(e);
+    }
+    sm[tid] = e;
+    __syncwarp();
+#pragma unroll 1
+    for (uint32_t stride = 16; stride > 0; stride >>= 1)
+    {
+        if (lane < stride)
+        {
+            XY a = sm[tid], c = sm[tid + stride];
+            cold_add(a, c);
+            sm[tid] = a;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        XY r = sm[4 * 32];
+        for (int k = 3; k >= 0; k--)
+        {
+            cold_dbl(r);
+            XY z = sm[k * 32];
+            cold_add(r, z);
+        }
+        XY t = sm[5 * 32];
+        cold_add(r, t);
+        args.result[blockIdx.y][0] = r;
     }
 }
 
@@ -519,44 +459,54 @@ __global__ void __launch_bounds__(128)
 }
 
 template <class XY>
-void msm_bases_create(MsmBases<XY>& out, const uint8_t* bases_host, uint64_t first, uint64_t count,
-                      uint32_t scalar_offset, cudaStream_t st)
+void msm_bases_create(MsmBases<XY>& out, const uint8_t* points_host, uint64_t count, bool filter_inf,
+                      cudaStream_t st)
 {
     typedef typename XY::Affine Affine;
     const size_t                psz = sizeof(Affine);
     std::vector<uint32_t>       idx;
-    idx.reserve(count);
-    std::vector<uint8_t> packed;
-    packed.reserve(count * psz);
-    for (uint64_t k = 0; k < count; k++)
+    std::vector<uint8_t>        packed;
+    const uint8_t*              src = points_host;
+    if (filter_inf)
     {
-        const uint8_t* p  = bases_host + (first + k) * psz;
-        bool           nz = false;
-        for (size_t q = 0; q < psz / 8; q++)
+        idx.reserve(count);
+        packed.reserve(count * psz);
+        for (uint64_t k = 0; k < count; k++)
         {
-            uint64_t v;
-            memcpy(&v, p + 8 * q, 8);
-            if (v)
+            const uint8_t* p  = points_host + k * psz;
+            bool           nz = false;
+            for (size_t q = 0; q < psz / 8; q++)
             {
-                nz = true;
-                break;
+                uint64_t v;
+                memcpy(&v, p + 8 * q, 8);
+                if (v)
+                {
+                    nz = true;
+                    break;
+                }
             }
+            if (!nz)
+                continue; // infinity base: skipped exactly like multiexp.cpp:57
+            idx.push_back((uint32_t)k);
+            packed.insert(packed.end(), p, p + psz);
         }
-        if (!nz)
-            continue; // infinity base: skipped exactly like multiexp.cpp:57
-        idx.push_back(scalar_offset + (uint32_t)k);
-        packed.insert(packed.end(), p, p + psz);
+        out.n = (uint32_t)idx.size();
+        src   = packed.data();
     }
-    out.n = (uint32_t)idx.size();
+    else
+        out.n = (uint32_t)count;
     if ((uint64_t)out.n * kMsmWindows >= 0x80000000ull)
         throw CudaError("MSM too large for 31-bit entry ids");
     if (out.n == 0)
         return;
     size_t n = out.n;
-    KZP_CUDA_CHECK(cudaMalloc(&out.scalar_idx, n * 4));
+    if (filter_inf)
+    {
+        KZP_CUDA_CHECK(cudaMalloc(&out.scalar_idx, n * 4));
+        KZP_CUDA_CHECK(cudaMemcpyAsync(out.scalar_idx, idx.data(), n * 4, cudaMemcpyHostToDevice, st));
+    }
     KZP_CUDA_CHECK(cudaMalloc(&out.table, n * kMsmWindows * psz));
-    KZP_CUDA_CHECK(cudaMemcpyAsync(out.scalar_idx, idx.data(), n * 4, cudaMemcpyHostToDevice, st));
-    KZP_CUDA_CHECK(cudaMemcpyAsync(out.table, packed.data(), n * psz, cudaMemcpyHostToDevice, st));
+    KZP_CUDA_CHECK(cudaMemcpyAsync(out.table, src, n * psz, cudaMemcpyHostToDevice, st));
     XY* cur = nullptr;
     KZP_CUDA_CHECK(cudaMalloc(&cur, n * sizeof(XY)));
     unsigned int grid = msm_div_up(n, 128);
@@ -584,31 +534,30 @@ void msm_bases_destroy(MsmBases<XY>& b)
 template <class XY>
 static void msm_set_smem_attrs()
 {
-    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_bucket_finalize_heavy<XY>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_heavy<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(256 * sizeof(XY))));
-    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_reduce1<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(512 * sizeof(XY))));
-    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_reduce2<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(3 * (kMsmBuckets / 256) * sizeof(XY))));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_finalize_fold<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(kMsmFoldBlock * sizeof(XY))));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_fold2<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(256 * sizeof(XY))));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_final<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(192 * sizeof(XY))));
 }
 
 template <class XY>
-void msm_scratch_create(MsmScratch<XY>& s, uint32_t n_active)
+void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort)
 {
     msm_set_smem_attrs<XY>(); // function attributes are per device: set on the device that owns the scratch
-    uint64_t cap  = (uint64_t)n_active * kMsmWindows;
-    s.cap_entries = (uint32_t)cap;
-    size_t nb     = kMsmBuckets + 2;
-    KZP_CUDA_CHECK(cudaMalloc(&s.counts, nb * 4));
-    KZP_CUDA_CHECK(cudaMalloc(&s.offsets, nb * 4));
-    KZP_CUDA_CHECK(cudaMalloc(&s.cursor, nb * 4));
-    KZP_CUDA_CHECK(cudaMalloc(&s.sorted, std::max<uint64_t>(cap, 1) * 4));
-    s.chunk = cap >= (1u << 24) ? 2 * kMsmChunk : kMsmChunk; // fewer, longer runs for the big MSMs
-    KZP_CUDA_CHECK(cudaMalloc(&s.records, (cap / s.chunk + nb + 1) * sizeof(XY)));
-    KZP_CUDA_CHECK(cudaMalloc(&s.heavy, (nb + 1) * 4));
-    KZP_CUDA_CHECK(cudaMalloc(&s.buckets, (kMsmBuckets + 1) * sizeof(XY)));
-    KZP_CUDA_CHECK(cudaMalloc(&s.partial, 2 * (kMsmBuckets / 256) * sizeof(XY)));
+    size_t nb   = kMsmBuckets + 2;
+    size_t nblk = kMsmBuckets / kMsmFoldBlock;
+    KZP_CUDA_CHECK(cudaMalloc(&s.records, ((size_t)sort.cap_entries / sort.chunk + nb + 1) * sizeof(XY)));
+    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_partial, (size_t)kMsmMaxHeavy * kMsmHeavyBlocks * sizeof(XY)));
+    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_sum, (size_t)kMsmMaxHeavy * sizeof(XY)));
+    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_done, (size_t)kMsmMaxHeavy * 4));
+    KZP_CUDA_CHECK(cudaMemset(s.heavy_done, 0, (size_t)kMsmMaxHeavy * 4));
+    KZP_CUDA_CHECK(cudaMalloc(&s.s0part, nblk * 32 * sizeof(XY)));
+    KZP_CUDA_CHECK(cudaMalloc(&s.s1part, nblk * (kMsmFoldBlock / 32) * sizeof(XY)));
+    KZP_CUDA_CHECK(cudaMalloc(&s.classes, (size_t)kMsmFoldLevels * 32 * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.result, sizeof(XY)));
     KZP_CUDA_CHECK(cudaEventCreate(&s.ev_acc0));
     KZP_CUDA_CHECK(cudaEventCreate(&s.ev_acc1));
@@ -617,14 +566,13 @@ void msm_scratch_create(MsmScratch<XY>& s, uint32_t n_active)
 template <class XY>
 void msm_scratch_destroy(MsmScratch<XY>& s)
 {
-    cudaFree(s.counts);
-    cudaFree(s.offsets);
-    cudaFree(s.cursor);
-    cudaFree(s.sorted);
     cudaFree(s.records);
-    cudaFree(s.heavy);
-    cudaFree(s.buckets);
-    cudaFree(s.partial);
+    cudaFree(s.heavy_partial);
+    cudaFree(s.heavy_sum);
+    cudaFree(s.heavy_done);
+    cudaFree(s.s0part);
+    cudaFree(s.s1part);
+    cudaFree(s.classes);
     cudaFree(s.result);
     if (s.ev_acc0)
         cudaEventDestroy(s.ev_acc0);
@@ -634,42 +582,54 @@ void msm_scratch_destroy(MsmScratch<XY>& s)
 }
 
 template <class XY>
-void msm_run(const MsmBases<XY>& b, MsmScratch<XY>& s, const uint32_t* scalars, cudaStream_t st)
+void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, MsmScratch<XY>* const* scr, int nb,
+                      cudaStream_t st)
 {
-    size_t nb = kMsmBuckets + 2;
-    KZP_CUDA_CHECK(cudaMemsetAsync(s.counts, 0, nb * 4, st));
-    if (b.n > 0)
+    if (nb < 1 || nb > kMsmMaxBatch)
+        throw CudaError("MSM batch size out of range");
+    MsmBatchArgs<XY> a;
+    for (int k = 0; k < kMsmMaxBatch; k++)
     {
-        if ((uint64_t)b.n * kMsmWindows > s.cap_entries)
-            throw CudaError("MSM scratch too small");
-        k_msm_count<<<msm_div_up(b.n, 256), 256, 0, st>>>(scalars, b.scalar_idx, b.n, s.counts);
+        int j = k < nb ? k : 0;
+        if (bases[j]->n != sort.n)
+            throw CudaError("MSM bases do not match the digit sort");
+        a.table[k]         = bases[j]->table;
+        a.records[k]       = scr[j]->records;
+        a.heavy_partial[k] = scr[j]->heavy_partial;
+        a.heavy_sum[k]     = scr[j]->heavy_sum;
+        a.heavy_done[k]    = scr[j]->heavy_done;
+        a.s0part[k]        = scr[j]->s0part;
+        a.s1part[k]        = scr[j]->s1part;
+        a.classes[k]       = scr[j]->classes;
+        a.result[k]        = scr[j]->result;
+    }
+    dim3 by(1, (unsigned int)nb, 1);
+    KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc0, st));
+    if (sort.n > 0)
+    {
+        uint64_t threads = ((uint64_t)sort.cap_entries + sort.chunk - 1) / sort.chunk;
+        by.x             = msm_div_up(threads, 128);
+        k_msm_accumulate<XY><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, sort.chunk);
         KZP_CUDA_CHECK(cudaGetLastError());
     }
-    k_msm_scan<<<1, 1024, 0, st>>>(s.counts, s.offsets, s.cursor);
+    KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc1, st));
+    by.x = kMsmHeavyBlocks;
+    k_msm_heavy<XY><<<by, 256, 256 * sizeof(XY), st>>>(sort.counts, sort.offsets, sort.heavy_ids, a, sort.chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
-    if (b.n > 0)
-    {
-        k_msm_scatter<<<msm_div_up(b.n, 256), 256, 0, st>>>(scalars, b.scalar_idx, b.n, s.cursor, s.sorted);
-        KZP_CUDA_CHECK(cudaGetLastError());
-        uint64_t threads = ((uint64_t)b.n * kMsmWindows + s.chunk - 1) / s.chunk;
-        KZP_CUDA_CHECK(cudaEventRecord(s.ev_acc0, st));
-        k_msm_accumulate<XY><<<msm_div_up(threads, 128), 128, 0, st>>>(s.offsets, s.sorted, b.table, s.records, s.chunk);
-        KZP_CUDA_CHECK(cudaGetLastError());
-        KZP_CUDA_CHECK(cudaEventRecord(s.ev_acc1, st));
-    }
-    KZP_CUDA_CHECK(cudaMemsetAsync(s.heavy, 0, 4, st));
-    k_msm_bucket_finalize<XY><<<msm_div_up(kMsmBuckets, 128), 128, 0, st>>>(s.offsets, s.records, s.buckets, s.chunk, s.heavy, s.heavy + 1);
+    by.x = kMsmBuckets / kMsmFoldBlock;
+    k_msm_finalize_fold<XY><<<by, kMsmFoldBlock, kMsmFoldBlock * sizeof(XY), st>>>(sort.offsets, sort.heavy_slot, a,
+                                                                                   sort.chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
-    k_msm_bucket_finalize_heavy<XY><<<128, 256, 256 * sizeof(XY), st>>>(s.offsets, s.records, s.buckets, s.chunk, s.heavy, s.heavy + 1);
+    by.x = 32 * kMsmFoldLevels;
+    k_msm_fold2<XY><<<by, 256, 256 * sizeof(XY), st>>>(a);
     KZP_CUDA_CHECK(cudaGetLastError());
-    k_msm_reduce1<XY><<<kMsmBuckets / 256, 256, 512 * sizeof(XY), st>>>(s.buckets, s.partial);
-    KZP_CUDA_CHECK(cudaGetLastError());
-    k_msm_reduce2<XY><<<1, 128, 3 * (kMsmBuckets / 256) * sizeof(XY), st>>>(s.partial, s.result);
+    by.x = 1;
+    k_msm_final<XY><<<by, 192, 192 * sizeof(XY), st>>>(a);
     KZP_CUDA_CHECK(cudaGetLastError());
 }
 
 template <class XY>
-void msm_last_accumulate(const MsmScratch<XY>& s, float* ms, uint64_t* entries)
+void msm_last_accumulate(const MsmSort& sort, const MsmScratch<XY>& s, float* ms, uint64_t* entries)
 {
     float t = 0;
     if (s.ev_acc0 && cudaEventElapsedTime(&t, s.ev_acc0, s.ev_acc1) != cudaSuccess)
@@ -678,7 +638,7 @@ void msm_last_accumulate(const MsmScratch<XY>& s, float* ms, uint64_t* entries)
         t = 0;
     }
     uint32_t total = 0;
-    KZP_CUDA_CHECK(cudaMemcpy(&total, s.offsets + kMsmBuckets + 1, 4, cudaMemcpyDeviceToHost));
+    KZP_CUDA_CHECK(cudaMemcpy(&total, sort.offsets + kMsmBuckets + 1, 4, cudaMemcpyDeviceToHost));
     if (ms)
         *ms = t;
     if (entries)

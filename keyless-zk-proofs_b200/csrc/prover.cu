@@ -1,10 +1,12 @@
 // Host-side driver of one GPU-resident Groth16 prover (thin C++: parse, upload once, launch, assemble).
 // Stage order follows Prover::prove in the reference (rust-rapidsnark/rapidsnark/src/groth16.cpp:43-360);
 // what the reference runs as std::async futures on CPU threads runs here on two CUDA streams.
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <random>
 #include <thread>
+#include <vector>
 
 #include "binfile.hpp"
 #include "device.hpp"
@@ -87,20 +89,101 @@ void append_decimal(std::string& s, const F& mont)
 
 } // namespace
 
-// Sums the shards' partial MSM results, blinds with (r, s) and prints the proof. Host-only arithmetic (a few
-// thousand field multiplications); mirrors groth16.cpp:296-357 + Proof::toJson (:379-410).
-std::string assemble_proof(const HostVk& vk, const ShardPartials* ps, int count, const uint8_t* r32,
-                           const uint8_t* s32, MsmArtefacts* art_out)
+// r/s-dependent terms of the proof that do not depend on the MSM results (groth16.cpp:296-316, 328-347): computed
+// on the host while the GPU works.
+struct BlindTerms
 {
-    HG1Affine alpha1, beta1, delta1;
-    HG2Affine beta2, delta2;
+    uint8_t r[32], s[32];
+    HG1     r_delta1, s_delta1, rs_delta1;
+    HG2     s_delta2;
+};
+
+static void compute_blind_terms(const HostVk& vk, const uint8_t* r32, const uint8_t* s32, BlindTerms& bt)
+{
+    HG1Affine delta1;
+    HG2Affine delta2;
+    memcpy(&delta1, vk.delta1, 64);
+    memcpy(&delta2, vk.delta2, 128);
+    if (r32 && s32)
+    {
+        memcpy(bt.r, r32, 32);
+        memcpy(bt.s, s32, 32);
+    }
+    else
+    {
+        sample_blinding(bt.r);
+        sample_blinding(bt.s);
+    }
+    // rs = r*s mod r_modulus, canonical (groth16.cpp:346-347)
+    uint8_t rs[32];
+    {
+        HFr fr, fs, t;
+        memcpy(&fr, bt.r, 32);
+        memcpy(&fs, bt.s, 32);
+        while (HFr::geq_p(fr))
+            HFr::sub_p(fr);
+        while (HFr::geq_p(fs))
+            HFr::sub_p(fs);
+        HFr::to_mont(fr, fr);
+        HFr::mul(t, fr, fs); // (r R)(s) R^-1 = r s
+        memcpy(rs, &t, 32);
+    }
+    HG1 d1;
+    HG2 d2;
+    HG1::from_affine(d1, delta1);
+    HG2::from_affine(d2, delta2);
+    scalar_mul(bt.r_delta1, d1, bt.r);
+    scalar_mul(bt.s_delta1, d1, bt.s);
+    scalar_mul(bt.rs_delta1, d1, rs);
+    scalar_mul(bt.s_delta2, d2, bt.s);
+}
+
+// Sums the shards' partial MSM results, blinds and prints the proof. Host-only arithmetic (a few thousand field
+// multiplications); mirrors groth16.cpp:318-357 + Proof::toJson (:379-410).
+static void artefacts_from_sums(const ShardPartials& sums, MsmArtefacts& art)
+{
+    HG1 A, B1, C, H;
+    HG2 B2;
+    memcpy(&A, sums.bytes + 0, 128);
+    memcpy(&B1, sums.bytes + 128, 128);
+    memcpy(&C, sums.bytes + 256, 128);
+    memcpy(&H, sums.bytes + 384, 128);
+    memcpy(&B2, sums.bytes + 512, 256);
+    auto put1 = [&](uint8_t* out, const HG1& p) {
+        HG1Affine a;
+        HG1::to_affine(a, p);
+        HFq t;
+        HFq::from_mont(t, a.x);
+        memcpy(out, &t, 32);
+        HFq::from_mont(t, a.y);
+        memcpy(out + 32, &t, 32);
+    };
+    put1(art.bytes + 0, A);
+    put1(art.bytes + 64, B1);
+    HG2Affine b2;
+    HG2::to_affine(b2, B2);
+    HFq t;
+    HFq::from_mont(t, b2.x.a);
+    memcpy(art.bytes + 128, &t, 32);
+    HFq::from_mont(t, b2.x.b);
+    memcpy(art.bytes + 160, &t, 32);
+    HFq::from_mont(t, b2.y.a);
+    memcpy(art.bytes + 192, &t, 32);
+    HFq::from_mont(t, b2.y.b);
+    memcpy(art.bytes + 224, &t, 32);
+    put1(art.bytes + 256, C);
+    put1(art.bytes + 320, H);
+}
+
+// sums_out (optional) receives the five summed MSM results (XYZZ) for the parity artefacts.
+static std::string assemble_with_terms(const HostVk& vk, const ShardPartials* ps, int count, const BlindTerms& bt,
+                                       ShardPartials* sums_out)
+{
+    HG1Affine alpha1, beta1;
+    HG2Affine beta2;
     memcpy(&alpha1, vk.alpha1, 64);
     memcpy(&beta1, vk.beta1, 64);
-    memcpy(&delta1, vk.delta1, 64);
     memcpy(&beta2, vk.beta2, 128);
-    memcpy(&delta2, vk.delta2, 128);
-    MsmArtefacts art_local;
-    MsmArtefacts& art = art_out ? *art_out : art_local;
     HG1 A, B1, C, H;
     HG2 B2;
     HG1::set_inf(A);
@@ -123,94 +206,43 @@ std::string assemble_proof(const HostVk& vk, const ShardPartials* ps, int count,
         memcpy(&t2, ps[k].bytes + 512, 256);
         HG2::add(B2, t2);
     }
-    // parity artefacts (affine, canonical)
-    {
-        auto put1 = [&](uint8_t* out, const HG1& p) {
-            HG1Affine a;
-            HG1::to_affine(a, p);
-            HFq t;
-            HFq::from_mont(t, a.x);
-            memcpy(out, &t, 32);
-            HFq::from_mont(t, a.y);
-            memcpy(out + 32, &t, 32);
-        };
-        put1(art.bytes + 0, A);
-        put1(art.bytes + 64, B1);
-        HG2Affine b2;
-        HG2::to_affine(b2, B2);
-        HFq t;
-        HFq::from_mont(t, b2.x.a);
-        memcpy(art.bytes + 128, &t, 32);
-        HFq::from_mont(t, b2.x.b);
-        memcpy(art.bytes + 160, &t, 32);
-        HFq::from_mont(t, b2.y.a);
-        memcpy(art.bytes + 192, &t, 32);
-        HFq::from_mont(t, b2.y.b);
-        memcpy(art.bytes + 224, &t, 32);
-        put1(art.bytes + 256, C);
-        put1(art.bytes + 320, H);
-    }
-
-    uint8_t r[32], s[32];
-    if (r32 && s32)
-    {
-        memcpy(r, r32, 32);
-        memcpy(s, s32, 32);
-    }
-    else
-    {
-        sample_blinding(r);
-        sample_blinding(s);
-    }
-    // rs = r*s mod r_modulus, canonical (groth16.cpp:346-347)
-    uint8_t rs[32];
-    {
-        HFr fr, fs, t;
-        memcpy(&fr, r, 32);
-        memcpy(&fs, s, 32);
-        while (HFr::geq_p(fr))
-            HFr::sub_p(fr);
-        while (HFr::geq_p(fs))
-            HFr::sub_p(fs);
-        HFr::to_mont(fr, fr);
-        HFr::mul(t, fr, fs); // (r R)(s) R^-1 = r s
-        memcpy(rs, &t, 32);
-    }
-    HG1 d1, al, be1, p1;
-    HG2 d2, be2, p2;
-    HG1::from_affine(d1, delta1);
+    HG1 al, be1;
+    HG2 be2;
     HG1::from_affine(al, alpha1);
     HG1::from_affine(be1, beta1);
-    HG2::from_affine(d2, delta2);
     HG2::from_affine(be2, beta2);
 
     // pi_a = A + alpha1 + r*delta1            (groth16.cpp:328-330)
     HG1 pi_a = A;
     HG1::add(pi_a, al);
-    scalar_mul(p1, d1, r);
-    HG1::add(pi_a, p1);
+    HG1::add(pi_a, bt.r_delta1);
     // pi_b = B2 + beta2 + s*delta2            (:332-334)
     HG2 pi_b = B2;
     HG2::add(pi_b, be2);
-    scalar_mul(p2, d2, s);
-    HG2::add(pi_b, p2);
+    HG2::add(pi_b, bt.s_delta2);
     // pib1 = B1 + beta1 + s*delta1            (:336-338)
     HG1 pib1 = B1;
     HG1::add(pib1, be1);
-    scalar_mul(p1, d1, s);
-    HG1::add(pib1, p1);
+    HG1::add(pib1, bt.s_delta1);
     // pi_c = C + H + s*pi_a + r*pib1 - rs*delta1   (:340-352)
-    HG1 pi_c = C;
+    HG1 pi_c = C, p1;
     HG1::add(pi_c, H);
-    scalar_mul(p1, pi_a, s);
+    scalar_mul(p1, pi_a, bt.s);
     HG1::add(pi_c, p1);
-    scalar_mul(p1, pib1, r);
+    scalar_mul(p1, pib1, bt.r);
     HG1::add(pi_c, p1);
-    scalar_mul(p1, d1, rs);
     HG1 np1;
-    HG1::neg(np1, p1);
+    HG1::neg(np1, bt.rs_delta1);
     HG1::add(pi_c, np1);
 
+    if (sums_out)
+    {
+        memcpy(sums_out->bytes + 0, &A, 128);
+        memcpy(sums_out->bytes + 128, &B1, 128);
+        memcpy(sums_out->bytes + 256, &C, 128);
+        memcpy(sums_out->bytes + 384, &H, 128);
+        memcpy(sums_out->bytes + 512, &B2, 256);
+    }
     HG1Affine a_aff, c_aff;
     HG2Affine b_aff;
     HG1::to_affine(a_aff, pi_a);
@@ -241,6 +273,18 @@ std::string assemble_proof(const HostVk& vk, const ShardPartials* ps, int count,
     return j;
 }
 
+std::string assemble_proof(const HostVk& vk, const ShardPartials* ps, int count, const uint8_t* r32,
+                           const uint8_t* s32, MsmArtefacts* art_out)
+{
+    BlindTerms bt;
+    compute_blind_terms(vk, r32, s32, bt);
+    ShardPartials sums;
+    std::string   j = assemble_with_terms(vk, ps, count, bt, art_out ? &sums : nullptr);
+    if (art_out)
+        artefacts_from_sums(sums, *art_out);
+    return j;
+}
+
 class DeviceProverImpl
 {
 public:
@@ -253,8 +297,14 @@ public:
     uint32_t log_domain = 0;
     uint64_t n_coefs    = 0;
 
-    cudaStream_t st_h = nullptr, st_w = nullptr, st_copy = nullptr;
-    cudaEvent_t  ev[16] = {};
+    // st_h: SpMV -> NTT chain -> H MSM.  st_w: witness digit sort + the three G1 witness MSMs (one batch).
+    // st_w2: the G2 witness MSM (joins st_w after the sort).  st_copy: witness upload.
+    cudaStream_t st_h = nullptr, st_w = nullptr, st_w2 = nullptr, st_copy = nullptr;
+    enum
+    {
+        EV_H2D0, EV_H2D1, EV_H0, EV_SPMV, EV_NTT, EV_HMSM, EV_W0, EV_WSORT, EV_WG1, EV_WG2_0, EV_WG2, EV_COUNT
+    };
+    cudaEvent_t ev[EV_COUNT] = {};
 
     CoefCsr   csr;
     NttDomain ntt;
@@ -264,6 +314,7 @@ public:
     uint8_t*  pinned_w = nullptr;
     uint8_t*  pinned_out = nullptr; // 5 result points
 
+    MsmSort            sort_w, sort_h;
     MsmBases<G1Xyzz>   bases_a, bases_b1, bases_c, bases_h;
     MsmBases<G2Xyzz>   bases_b2;
     MsmScratch<G1Xyzz> sc_a, sc_b1, sc_c, sc_h;
@@ -272,9 +323,12 @@ public:
     HostVk vk;
 
     ShardPartials parts;
+    ShardPartials sums;       // the five MSM results of the last assemble(), summed over shards
+    bool          art_valid = false;
     MsmArtefacts  art;
     ProveTimings  tm;
     bool          witness_resident = false;
+    bool          gpu_in_flight    = false;
 
     void set_device() const { KZP_CUDA_CHECK(cudaSetDevice(device)); }
 
@@ -321,14 +375,22 @@ public:
         KZP_CUDA_CHECK(cudaMemcpy(csr.coef, coef.data(), coef.size(), cudaMemcpyHostToDevice));
     }
 
+    // Base columns [first, last) of a zkey point section whose point k belongs to scalar index k + lead
+    // (lead = nPublic + 1 for section 8, which holds private wires only; 0 otherwise). Columns without a point
+    // are infinity (all-zero), so that every MSM over the witness shares one digit sort.
     template <class XY>
-    void make_bases(MsmBases<XY>& b, MsmScratch<XY>& sc, const uint8_t* sec, uint64_t count,
-                    uint32_t scalar_base)
+    void make_bases(MsmBases<XY>& b, const uint8_t* sec, uint64_t sec_count, uint32_t lead, uint64_t first,
+                    uint64_t last)
     {
-        uint64_t first = (uint64_t)rank * count / (uint64_t)world;
-        uint64_t last  = (uint64_t)(rank + 1) * count / (uint64_t)world;
-        msm_bases_create<XY>(b, sec, first, last - first, scalar_base + (uint32_t)first, st_h);
-        msm_scratch_create<XY>(sc, b.n);
+        const size_t         psz = sizeof(typename XY::Affine);
+        std::vector<uint8_t> cols((size_t)(last - first) * psz, 0);
+        for (uint64_t col = first; col < last; col++)
+        {
+            if (col < lead || col - lead >= sec_count)
+                continue;
+            memcpy(&cols[(size_t)(col - first) * psz], sec + (col - lead) * psz, psz);
+        }
+        msm_bases_create<XY>(b, cols.data(), last - first, false, st_h);
     }
 
     DeviceProverImpl(const std::string& path, int dev, int rank_, int world_)
@@ -355,6 +417,7 @@ public:
         set_device();
         KZP_CUDA_CHECK(cudaStreamCreateWithFlags(&st_h, cudaStreamNonBlocking));
         KZP_CUDA_CHECK(cudaStreamCreateWithFlags(&st_w, cudaStreamNonBlocking));
+        KZP_CUDA_CHECK(cudaStreamCreateWithFlags(&st_w2, cudaStreamNonBlocking));
         KZP_CUDA_CHECK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
         for (auto& e : ev)
             KZP_CUDA_CHECK(cudaEventCreate(&e));
@@ -376,11 +439,21 @@ public:
         KZP_CUDA_CHECK(cudaMallocHost(&pinned_w, (size_t)n_vars * 32));
         KZP_CUDA_CHECK(cudaMallocHost(&pinned_out, sizeof(ShardPartials)));
 
-        make_bases(bases_a, sc_a, zh.points_a, n_vars, 0);
-        make_bases(bases_b1, sc_b1, zh.points_b1, n_vars, 0);
-        make_bases(bases_b2, sc_b2, zh.points_b2, n_vars, 0);
-        make_bases(bases_c, sc_c, zh.points_c, n_vars - n_public - 1, n_public + 1);
-        make_bases(bases_h, sc_h, zh.points_h, domain, 0);
+        // this shard's base ranges: wires [w0, w1) of sections 5-8, points [h0, h1) of section 9
+        uint64_t w0 = (uint64_t)rank * n_vars / (uint64_t)world, w1 = (uint64_t)(rank + 1) * n_vars / (uint64_t)world;
+        uint64_t h0 = (uint64_t)rank * domain / (uint64_t)world, h1 = (uint64_t)(rank + 1) * domain / (uint64_t)world;
+        make_bases(bases_a, zh.points_a, n_vars, 0, w0, w1);
+        make_bases(bases_b1, zh.points_b1, n_vars, 0, w0, w1);
+        make_bases(bases_b2, zh.points_b2, n_vars, 0, w0, w1);
+        make_bases(bases_c, zh.points_c, n_vars - n_public - 1, n_public + 1, w0, w1);
+        make_bases(bases_h, zh.points_h, domain, 0, h0, h1);
+        msm_sort_create(sort_w, (uint32_t)(w1 - w0), nullptr, (uint32_t)w0, 32);
+        msm_sort_create(sort_h, (uint32_t)(h1 - h0), nullptr, (uint32_t)h0, 0);
+        msm_scratch_create(sc_a, sort_w);
+        msm_scratch_create(sc_b1, sort_w);
+        msm_scratch_create(sc_c, sort_w);
+        msm_scratch_create(sc_b2, sort_w);
+        msm_scratch_create(sc_h, sort_h);
         KZP_CUDA_CHECK(cudaDeviceSynchronize());
     }
 
@@ -398,6 +471,8 @@ public:
         msm_scratch_destroy(sc_b2);
         msm_scratch_destroy(sc_c);
         msm_scratch_destroy(sc_h);
+        msm_sort_destroy(sort_w);
+        msm_sort_destroy(sort_h);
         ntt_domain_destroy(ntt);
         cudaFree(csr.row_ptr);
         cudaFree(csr.wire);
@@ -415,47 +490,79 @@ public:
             cudaEventDestroy(e);
         cudaStreamDestroy(st_h);
         cudaStreamDestroy(st_w);
+        cudaStreamDestroy(st_w2);
         cudaStreamDestroy(st_copy);
     }
 
+    // Host -> pinned staging -> device, pipelined: kUploadThreads workers copy slices into the pinned buffer (the
+    // source is normally a fresh file mapping, so this is also where its pages are faulted in) while the calling
+    // thread hands every finished slice to the copy engine.
     void upload(const uint8_t* values, uint64_t n)
     {
         if (n < n_vars)
             throw FormatError("witness has fewer values than the zkey has variables");
         set_device();
-        // stage through pinned memory in slices so the host copy of slice k+1 overlaps the DMA of slice k
-        const size_t total = (size_t)n_vars * 32;
-        const size_t slice = 4u << 20;
-        KZP_CUDA_CHECK(cudaEventRecord(ev[0], st_copy));
-        for (size_t off = 0; off < total; off += slice)
+        const size_t total    = (size_t)n_vars * 32;
+        const size_t slice    = 2u << 20;
+        const size_t n_slices = (total + slice - 1) / slice;
+        const int    kUploadThreads = 4;
+        std::vector<std::atomic<int>> ready(n_slices);
+        for (auto& r : ready)
+            r.store(0, std::memory_order_relaxed);
+        std::atomic<size_t>      next{0};
+        std::vector<std::thread> workers;
+        auto                     work = [&] {
+            for (;;)
+            {
+                size_t k = next.fetch_add(1);
+                if (k >= n_slices)
+                    return;
+                size_t off = k * slice, len = std::min(slice, total - off);
+                memcpy(pinned_w + off, values + off, len);
+                ready[k].store(1, std::memory_order_release);
+            }
+        };
+        int n_workers = (int)std::min<size_t>(kUploadThreads, n_slices);
+        for (int t = 1; t < n_workers; t++)
+            workers.emplace_back(work);
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H2D0], st_copy));
+        cudaError_t err = cudaSuccess;
+        if (n_workers <= 1)
+            work();
+        for (size_t k = 0; k < n_slices; k++)
         {
-            size_t len = std::min(slice, total - off);
-            memcpy(pinned_w + off, values + off, len);
-            KZP_CUDA_CHECK(cudaMemcpyAsync((uint8_t*)d_w + off, pinned_w + off, len,
-                                           cudaMemcpyHostToDevice, st_copy));
+            while (!ready[k].load(std::memory_order_acquire))
+                std::this_thread::yield();
+            size_t off = k * slice, len = std::min(slice, total - off);
+            if (err == cudaSuccess)
+                err = cudaMemcpyAsync((uint8_t*)d_w + off, pinned_w + off, len, cudaMemcpyHostToDevice, st_copy);
         }
-        KZP_CUDA_CHECK(cudaEventRecord(ev[1], st_copy));
+        for (auto& w : workers)
+            w.join();
+        KZP_CUDA_CHECK(err);
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H2D1], st_copy));
         witness_resident = true;
     }
 
-    void run_gpu()
+    // Enqueues the whole GPU part of one proof (no host synchronisation).
+    void launch_gpu()
     {
         if (!witness_resident)
             throw FormatError("no witness uploaded");
         set_device();
         const uint32_t* w = reinterpret_cast<const uint32_t*>(d_w);
-        KZP_CUDA_CHECK(cudaStreamWaitEvent(st_h, ev[1], 0));
-        KZP_CUDA_CHECK(cudaStreamWaitEvent(st_w, ev[1], 0));
+        KZP_CUDA_CHECK(cudaStreamWaitEvent(st_h, ev[EV_H2D1], 0));
+        KZP_CUDA_CHECK(cudaStreamWaitEvent(st_w, ev[EV_H2D1], 0));
 
         // ---- stream H: SpMV -> 3 x (iNTT, coset, NTT) -> pointwise -> MSM H
-        KZP_CUDA_CHECK(cudaEventRecord(ev[2], st_h));
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H0], st_h));
         spmv_abc(csr, d_w, d_a, d_b, d_c, st_h);
         if (keep_ab)
         {
             KZP_CUDA_CHECK(cudaMemcpyAsync(d_keep_a, d_a, (size_t)domain * 32, cudaMemcpyDeviceToDevice, st_h));
             KZP_CUDA_CHECK(cudaMemcpyAsync(d_keep_b, d_b, (size_t)domain * 32, cudaMemcpyDeviceToDevice, st_h));
         }
-        KZP_CUDA_CHECK(cudaEventRecord(ev[3], st_h));
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_SPMV], st_h));
         Fr* vecs[3] = {d_a, d_b, d_c};
         for (Fr* x : vecs)
         {
@@ -463,28 +570,49 @@ public:
             ntt_forward_dit(ntt, x, st_h);
         }
         h_pointwise(d_a, d_b, d_c, d_h, domain, st_h);
-        KZP_CUDA_CHECK(cudaEventRecord(ev[4], st_h));
-        msm_run(bases_h, sc_h, reinterpret_cast<const uint32_t*>(d_h), st_h);
-        KZP_CUDA_CHECK(cudaEventRecord(ev[5], st_h));
-
-        // ---- stream W: the four witness MSMs
-        KZP_CUDA_CHECK(cudaEventRecord(ev[6], st_w));
-        msm_run(bases_a, sc_a, w, st_w);
-        KZP_CUDA_CHECK(cudaEventRecord(ev[7], st_w));
-        msm_run(bases_b1, sc_b1, w, st_w);
-        KZP_CUDA_CHECK(cudaEventRecord(ev[8], st_w));
-        msm_run(bases_b2, sc_b2, w, st_w);
-        KZP_CUDA_CHECK(cudaEventRecord(ev[9], st_w));
-        msm_run(bases_c, sc_c, w, st_w);
-        KZP_CUDA_CHECK(cudaEventRecord(ev[10], st_w));
-
-        // results -> pinned host
-        KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 0, sc_a.result, 128, cudaMemcpyDeviceToHost, st_w));
-        KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 128, sc_b1.result, 128, cudaMemcpyDeviceToHost, st_w));
-        KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 256, sc_c.result, 128, cudaMemcpyDeviceToHost, st_w));
-        KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 512, sc_b2.result, 256, cudaMemcpyDeviceToHost, st_w));
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_NTT], st_h));
+        {
+            const MsmBases<G1Xyzz>* b[1] = {&bases_h};
+            MsmScratch<G1Xyzz>*     s[1] = {&sc_h};
+            msm_sort_run(sort_h, reinterpret_cast<const uint32_t*>(d_h), st_h);
+            msm_reduce_batch<G1Xyzz>(sort_h, b, s, 1, st_h);
+        }
         KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 384, sc_h.result, 128, cudaMemcpyDeviceToHost, st_h));
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_HMSM], st_h));
+
+        // ---- stream W: one digit sort of the witness, then A, B1, C as one G1 batch; B2 on its own stream
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_W0], st_w));
+        msm_sort_run(sort_w, w, st_w);
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_WSORT], st_w));
+        KZP_CUDA_CHECK(cudaStreamWaitEvent(st_w2, ev[EV_WSORT], 0));
+        {
+            const MsmBases<G2Xyzz>* b[1] = {&bases_b2};
+            MsmScratch<G2Xyzz>*     s[1] = {&sc_b2};
+            KZP_CUDA_CHECK(cudaEventRecord(ev[EV_WG2_0], st_w2));
+            msm_reduce_batch<G2Xyzz>(sort_w, b, s, 1, st_w2);
+            KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 512, sc_b2.result, 256, cudaMemcpyDeviceToHost, st_w2));
+            KZP_CUDA_CHECK(cudaEventRecord(ev[EV_WG2], st_w2));
+        }
+        {
+            const MsmBases<G1Xyzz>* b[3] = {&bases_a, &bases_b1, &bases_c};
+            MsmScratch<G1Xyzz>*     s[3] = {&sc_a, &sc_b1, &sc_c};
+            msm_reduce_batch<G1Xyzz>(sort_w, b, s, 3, st_w);
+            KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 0, sc_a.result, 128, cudaMemcpyDeviceToHost, st_w));
+            KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 128, sc_b1.result, 128, cudaMemcpyDeviceToHost, st_w));
+            KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 256, sc_c.result, 128, cudaMemcpyDeviceToHost, st_w));
+            KZP_CUDA_CHECK(cudaEventRecord(ev[EV_WG1], st_w));
+        }
+        gpu_in_flight = true;
+    }
+
+    void wait_gpu()
+    {
+        if (!gpu_in_flight)
+            throw FormatError("no proof in flight");
+        set_device();
+        gpu_in_flight = false;
         KZP_CUDA_CHECK(cudaStreamSynchronize(st_w));
+        KZP_CUDA_CHECK(cudaStreamSynchronize(st_w2));
         KZP_CUDA_CHECK(cudaStreamSynchronize(st_h));
         memcpy(parts.bytes, pinned_out, sizeof(parts.bytes));
 
@@ -493,25 +621,59 @@ public:
             cudaEventElapsedTime(&ms, ev[a], ev[b]);
             return ms;
         };
-        tm.h2d_ms    = el(0, 1);
-        tm.spmv_ms   = el(2, 3);
-        tm.ntt_ms    = el(3, 4);
-        tm.msm_h_ms  = el(4, 5);
-        tm.msm_a_ms  = el(6, 7);
-        tm.msm_b1_ms = el(7, 8);
-        tm.msm_b2_ms = el(8, 9);
-        tm.msm_c_ms  = el(9, 10);
-        tm.gpu_ms    = std::max(el(2, 5), el(2, 10));
-        uint32_t per_msm   = 8;
-        tm.kernel_launches = 1 + 3 * 2 * log_domain + 1 + 5 * per_msm;
+        tm.h2d_ms       = el(EV_H2D0, EV_H2D1);
+        tm.spmv_ms      = el(EV_H0, EV_SPMV);
+        tm.ntt_ms       = el(EV_SPMV, EV_NTT);
+        tm.msm_h_ms     = el(EV_NTT, EV_HMSM);
+        tm.msm_wsort_ms = el(EV_W0, EV_WSORT);
+        tm.msm_wg1_ms   = el(EV_WSORT, EV_WG1);
+        tm.msm_wg2_ms   = el(EV_WG2_0, EV_WG2);
+        tm.gpu_ms       = std::max(std::max(el(EV_H0, EV_HMSM), el(EV_H0, EV_WG1)), el(EV_H0, EV_WG2));
+        tm.kernel_launches = 1 + ntt_launches(log_domain) * 6 + 1 + 2 * kMsmSortLaunches + 3 * kMsmReduceLaunches;
+    }
+
+    void run_gpu()
+    {
+        launch_gpu();
+        wait_gpu();
     }
 
     std::string assemble(const ShardPartials* ps, int count, const uint8_t* r32, const uint8_t* s32)
     {
-        double      t0 = now_ms();
-        std::string j  = assemble_proof(vk, ps, count, r32, s32, &art);
+        double     t0 = now_ms();
+        BlindTerms bt;
+        compute_blind_terms(vk, r32, s32, bt);
+        std::string j       = assemble_with_terms(vk, ps, count, bt, &sums);
+        art_valid           = false;
         tm.assemble_host_ms = (float)(now_ms() - t0);
         return j;
+    }
+
+    // upload + GPU + assembly with the r/s-only host work overlapped with the GPU
+    std::string prove(const uint8_t* values, uint64_t n, const uint8_t* r32, const uint8_t* s32)
+    {
+        double t0 = now_ms();
+        upload(values, n);
+        launch_gpu();
+        BlindTerms bt;
+        compute_blind_terms(vk, r32, s32, bt);
+        wait_gpu();
+        double      t1      = now_ms();
+        std::string j       = assemble_with_terms(vk, &parts, 1, bt, &sums);
+        art_valid           = false;
+        tm.assemble_host_ms = (float)(now_ms() - t1);
+        tm.total_host_ms    = (float)(now_ms() - t0);
+        return j;
+    }
+
+    const MsmArtefacts& artefacts()
+    {
+        if (!art_valid)
+        {
+            artefacts_from_sums(sums, art);
+            art_valid = true;
+        }
+        return art;
     }
 };
 
@@ -536,12 +698,7 @@ std::string DeviceProver::assemble(const ShardPartials* parts, int count, const 
 }
 std::string DeviceProver::prove(const uint8_t* values, uint64_t n, const uint8_t* r32, const uint8_t* s32)
 {
-    double t0 = now_ms();
-    impl_->upload(values, n);
-    impl_->run_gpu();
-    std::string j           = impl_->assemble(&impl_->parts, 1, r32, s32);
-    impl_->tm.total_host_ms = (float)(now_ms() - t0);
-    return j;
+    return impl_->prove(values, n, r32, s32);
 }
 const ProveTimings& DeviceProver::timings() const { return impl_->tm; }
 void DeviceProver::msm_profile(int which, float* ms, uint64_t* entries) const
@@ -549,15 +706,15 @@ void DeviceProver::msm_profile(int which, float* ms, uint64_t* entries) const
     impl_->set_device();
     switch (which)
     {
-    case 0: msm_last_accumulate(impl_->sc_a, ms, entries); break;
-    case 1: msm_last_accumulate(impl_->sc_b1, ms, entries); break;
-    case 2: msm_last_accumulate(impl_->sc_b2, ms, entries); break;
-    case 3: msm_last_accumulate(impl_->sc_c, ms, entries); break;
-    case 4: msm_last_accumulate(impl_->sc_h, ms, entries); break;
+    case 0: // A, B1 and C run as one batched launch over the shared witness sort
+    case 1:
+    case 3: msm_last_accumulate(impl_->sort_w, impl_->sc_a, ms, entries); break;
+    case 2: msm_last_accumulate(impl_->sort_w, impl_->sc_b2, ms, entries); break;
+    case 4: msm_last_accumulate(impl_->sort_h, impl_->sc_h, ms, entries); break;
     default: throw FormatError("msm index out of range");
     }
 }
-const MsmArtefacts& DeviceProver::msm_artefacts() const { return impl_->art; }
+const MsmArtefacts& DeviceProver::msm_artefacts() const { return impl_->artefacts(); }
 void DeviceProver::copy_h(uint8_t* out) const
 {
     impl_->set_device();

@@ -18,10 +18,10 @@ struct ProveTimings
     float spmv_ms     = 0;
     float ntt_ms      = 0; // 3 x (iNTT + coset + NTT) + pointwise
     float msm_h_ms    = 0;
-    float msm_a_ms    = 0;
-    float msm_b1_ms   = 0;
-    float msm_b2_ms   = 0;
-    float msm_c_ms    = 0;
+    float msm_wsort_ms = 0; // digit sort of the witness (shared by A, B1, B2, C)
+    float msm_wg1_ms   = 0; // A, B1, C: one batched G1 launch per stage
+    float msm_wg2_ms   = 0; // B2
+    float reserved_ms  = 0;
     float gpu_ms      = 0; // first kernel to last kernel (both streams)
     float assemble_host_ms = 0;
     float total_host_ms    = 0; // wall clock of prove_*()
