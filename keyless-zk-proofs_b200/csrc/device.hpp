@@ -80,9 +80,14 @@ constexpr int      kMsmWindowBits   = 16;
 constexpr int      kMsmWindows      = 16;
 constexpr uint32_t kMsmBuckets      = 1u << (kMsmWindowBits - 1); // bucket ids 1..kMsmBuckets
 constexpr int      kMsmMaxBatch     = 3;                           // MSMs per batched launch
-constexpr uint32_t kMsmHeavyRecords = 32;   // buckets with more partial sums than this are pre-reduced by whole blocks
-constexpr uint32_t kMsmHeavyBlocks  = 32;   // blocks that cooperate on one heavy bucket
+constexpr uint32_t kMsmHeavyRecords = 8;    // a bucket with more partial sums than max(this, 2 x average) is "heavy":
+                                            // pre-reduced by whole blocks instead of one finalise thread
+constexpr uint32_t kMsmHeavyBlocks  = 32;   // most slices (blocks) one heavy bucket is cut into
+constexpr uint32_t kMsmHeavySlice   = 512;  // target records per slice
+constexpr uint32_t kMsmHeavyGrid    = 128;  // blocks of the heavy kernel (work items are spread over them)
 constexpr uint32_t kMsmMaxHeavy     = 1024; // heavy buckets handled that way (the rest stay thread-serial)
+constexpr uint32_t kMsmEntryBaseBits = 27;  // sorted entry = base | window << 27 | sign << 31
+constexpr uint32_t kMsmEntryBaseMask = (1u << kMsmEntryBaseBits) - 1u;
 constexpr uint32_t kMsmFoldBlock    = 128;  // buckets per block of the finalise+fold kernel
 constexpr int      kMsmFoldLevels   = (kMsmWindowBits - 1 + 4) / 5; // base-32 digits of a bucket index
 
@@ -107,6 +112,7 @@ struct MsmBases
     typedef typename XY::Affine Affine;
     uint32_t  n          = 0;       // table columns (bases kept)
     uint32_t* scalar_idx = nullptr; // n, only when infinity bases were filtered out: scalar index of each kept base
+    uint8_t*  skip       = nullptr; // n, only when infinity columns were kept: 1 = column is infinity
     Affine*   table      = nullptr; // kMsmWindows x n affine points: table[j*n + i] = 2^(16 j) * P_i
 };
 

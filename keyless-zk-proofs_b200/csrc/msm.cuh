@@ -26,6 +26,7 @@ template <class XY>
 struct MsmBatchArgs
 {
     const typename XY::Affine* table[kMsmMaxBatch];
+    const uint8_t*             skip[kMsmMaxBatch]; // per base column: 1 = infinity (nullptr = no flags)
     XY*                        records[kMsmMaxBatch];
     XY*                        heavy_partial[kMsmMaxBatch];
     XY*                        heavy_sum[kMsmMaxBatch];
@@ -45,12 +46,13 @@ struct MsmBatchArgs
 template <class XY>
 __global__ void __launch_bounds__(128)
     k_msm_accumulate(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
-                     MsmBatchArgs<XY> args, uint32_t chunk)
+                     MsmBatchArgs<XY> args, uint32_t chunk, uint32_t n)
 {
     typedef typename XY::Affine Affine;
     typedef typename XY::Field  F;
-    const Affine* __restrict__ table   = args.table[blockIdx.y];
-    XY* __restrict__           records = args.records[blockIdx.y];
+    const Affine* __restrict__  table   = args.table[blockIdx.y];
+    const uint8_t* __restrict__ skip    = args.skip[blockIdx.y];
+    XY* __restrict__            records = args.records[blockIdx.y];
     uint32_t t     = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t total = offsets[kMsmBuckets + 1];
     uint64_t start64 = (uint64_t)t * chunk;
@@ -85,7 +87,10 @@ __global__ void __launch_bounds__(128)
             } while (pos >= next);
         }
         uint32_t e = sorted[pos];
-        Affine   p = table[e & 0x7fffffffu];
+        uint32_t i = e & kMsmEntryBaseMask;
+        if (skip && skip[i])
+            continue; // infinity column: costs one byte, not a point load
+        Affine p = table[(size_t)((e >> kMsmEntryBaseBits) & 15u) * n + i];
         if (e >> 31)
             F::neg(p.y, p.y);
         XY::madd(acc, p);
@@ -139,9 +144,11 @@ __device__ __forceinline__ XY load_cg(const XY* p)
 }
 
 // ---- heavy buckets -------------------------------------------------------------------------------------
-// A bucket whose range spans more than kMsmHeavyRecords accumulate threads (bucket 1 of a bit-heavy witness holds
-// ~half of all entries) is summed by kMsmHeavyBlocks blocks: each reduces a slice of its records to one point, the
-// last block to arrive (arrival counter) sums the slices. grid = (kMsmHeavyBlocks, batch).
+// A bucket whose range spans more accumulate threads than the sort's heavy threshold (bucket 1 of a bit-heavy
+// witness holds ~half of all entries; byte-valued wires fill buckets 2..255) is summed by whole blocks: its records
+// are cut into slices of ~kMsmHeavySlice, one block reduces one slice, and for multi-slice buckets the last block
+// to arrive (arrival counter) sums the slice results. Work items (bucket, slice) are spread over the grid.
+// grid = (kMsmHeavyGrid, batch).
 template <class XY>
 __global__ void __launch_bounds__(256)
     k_msm_heavy(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
@@ -149,6 +156,7 @@ __global__ void __launch_bounds__(256)
 {
     extern __shared__ uint4 smem_raw[];
     __shared__ uint32_t     s_last;
+    __shared__ uint32_t     pre[kMsmMaxHeavy + 1];
     XY*                     sm      = reinterpret_cast<XY*>(smem_raw);
     const XY* __restrict__  records = args.records[blockIdx.y];
     XY*                     partial = args.heavy_partial[blockIdx.y];
@@ -156,31 +164,70 @@ __global__ void __launch_bounds__(256)
     uint32_t*               done    = args.heavy_done[blockIdx.y];
     uint32_t                tid     = threadIdx.x;
     uint32_t                n       = min(counts[0], kMsmMaxHeavy);
-    for (uint32_t h = 0; h < n; h++)
+    if (n == 0)
+        return;
+    // slices per heavy bucket, then an exclusive prefix (n <= 1024: one thread scans)
+    for (uint32_t h = tid; h < n; h += blockDim.x)
     {
+        uint32_t b   = heavy_ids[h];
+        uint32_t lo  = offsets[b], hi = offsets[b + 1];
+        uint32_t cnt = (hi - 1) / chunk - lo / chunk + 1;
+        pre[h + 1]   = min(kMsmHeavyBlocks, (cnt + kMsmHeavySlice - 1) / kMsmHeavySlice);
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        pre[0] = 0;
+        for (uint32_t h = 0; h < n; h++)
+            pre[h + 1] += pre[h];
+    }
+    __syncthreads();
+    uint32_t items = pre[n];
+    for (uint32_t item = blockIdx.x; item < items; item += gridDim.x)
+    {
+        // h = largest index with pre[h] <= item
+        uint32_t l = 0, r = n - 1;
+        while (l < r)
+        {
+            uint32_t mid = (l + r + 1) >> 1;
+            if (pre[mid] <= item)
+                l = mid;
+            else
+                r = mid - 1;
+        }
+        uint32_t  h   = l;
+        uint32_t  j   = item - pre[h];
+        uint32_t  nsl = pre[h + 1] - pre[h];
         uint32_t  b   = heavy_ids[h];
         uint32_t  lo  = offsets[b], hi = offsets[b + 1];
         uint32_t  t0  = lo / chunk;
         uint32_t  cnt = (hi - 1) / chunk - t0 + 1;
         const XY* rec = records + (size_t)t0 + b;
-        uint32_t  per = (cnt + gridDim.x - 1) / gridDim.x;
-        uint32_t  s   = blockIdx.x * per;
+        uint32_t  per = (cnt + nsl - 1) / nsl;
+        uint32_t  s   = j * per;
         uint32_t  e   = min(s + per, cnt);
         XY        acc;
         XY::set_inf(acc);
         for (uint32_t k = s + tid; k < e; k += blockDim.x)
         {
-            XY r = rec[k];
-            cold_add(acc, r);
+            XY q = rec[k];
+            cold_add(acc, q);
         }
         sm[tid] = acc;
         block_tree_sum(sm, blockDim.x, tid);
+        if (nsl == 1)
+        {
+            if (tid == 0)
+                sums[h] = sm[0];
+            __syncthreads();
+            continue;
+        }
         if (tid == 0)
         {
-            partial[(size_t)h * kMsmHeavyBlocks + blockIdx.x] = sm[0];
+            partial[(size_t)h * kMsmHeavyBlocks + j] = sm[0];
             __threadfence();
             uint32_t ticket = atomicAdd(&done[h], 1u);
-            s_last          = (ticket == gridDim.x - 1) ? 1u : 0u;
+            s_last          = (ticket == nsl - 1) ? 1u : 0u;
         }
         __syncthreads();
         if (s_last)
@@ -188,7 +235,7 @@ __global__ void __launch_bounds__(256)
             __threadfence();
             if (tid < kMsmHeavyBlocks)
             {
-                if (tid < gridDim.x)
+                if (tid < nsl)
                     sm[tid] = load_cg(partial + (size_t)h * kMsmHeavyBlocks + tid);
                 else
                     XY::set_inf(sm[tid]);
@@ -495,11 +542,35 @@ void msm_bases_create(MsmBases<XY>& out, const uint8_t* points_host, uint64_t co
     }
     else
         out.n = (uint32_t)count;
-    if ((uint64_t)out.n * kMsmWindows >= 0x80000000ull)
-        throw CudaError("MSM too large for 31-bit entry ids");
+    if (out.n > kMsmEntryBaseMask)
+        throw CudaError("MSM too large for 27-bit base ids");
     if (out.n == 0)
         return;
     size_t n = out.n;
+    if (!filter_inf)
+    {
+        std::vector<uint8_t> flags(n, 0);
+        bool                 any = false;
+        for (uint64_t k = 0; k < count; k++)
+        {
+            const uint8_t* p  = points_host + k * psz;
+            bool           nz = false;
+            for (size_t q = 0; q < psz / 8 && !nz; q++)
+            {
+                uint64_t v;
+                memcpy(&v, p + 8 * q, 8);
+                nz = v != 0;
+            }
+            flags[k] = nz ? 0 : 1;
+            any |= !nz;
+        }
+        if (any)
+        {
+            KZP_CUDA_CHECK(cudaMalloc(&out.skip, n));
+            KZP_CUDA_CHECK(cudaMemcpyAsync(out.skip, flags.data(), n, cudaMemcpyHostToDevice, st));
+            KZP_CUDA_CHECK(cudaStreamSynchronize(st)); // flags is a local
+        }
+    }
     if (filter_inf)
     {
         KZP_CUDA_CHECK(cudaMalloc(&out.scalar_idx, n * 4));
@@ -526,6 +597,8 @@ void msm_bases_destroy(MsmBases<XY>& b)
 {
     cudaFree(b.scalar_idx);
     cudaFree(b.table);
+    cudaFree(b.skip);
+    b.skip       = nullptr;
     b.scalar_idx = nullptr;
     b.table      = nullptr;
     b.n          = 0;
@@ -594,6 +667,7 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
         if (bases[j]->n != sort.n)
             throw CudaError("MSM bases do not match the digit sort");
         a.table[k]         = bases[j]->table;
+        a.skip[k]          = bases[j]->skip;
         a.records[k]       = scr[j]->records;
         a.heavy_partial[k] = scr[j]->heavy_partial;
         a.heavy_sum[k]     = scr[j]->heavy_sum;
@@ -609,11 +683,11 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     {
         uint64_t threads = ((uint64_t)sort.cap_entries + sort.chunk - 1) / sort.chunk;
         by.x             = msm_div_up(threads, 128);
-        k_msm_accumulate<XY><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, sort.chunk);
+        k_msm_accumulate<XY><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, sort.chunk, sort.n);
         KZP_CUDA_CHECK(cudaGetLastError());
     }
     KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc1, st));
-    by.x = kMsmHeavyBlocks;
+    by.x = kMsmHeavyGrid;
     k_msm_heavy<XY><<<by, 256, 256 * sizeof(XY), st>>>(sort.counts, sort.offsets, sort.heavy_ids, a, sort.chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = kMsmBuckets / kMsmFoldBlock;

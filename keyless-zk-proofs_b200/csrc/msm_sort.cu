@@ -136,6 +136,8 @@ static __global__ void __launch_bounds__(1024)
     }
     __syncthreads();
     uint32_t base = warp_sums[wid] + inc - sum;
+    // heavy = more than max(kMsmHeavyRecords, 2 x the average number of records per bucket)
+    uint32_t thr = max(kMsmHeavyRecords, 2u * (carry_s / chunk / kMsmBuckets + 1u));
 #pragma unroll
     for (uint32_t k = 0; k < per; k++)
     {
@@ -147,7 +149,7 @@ static __global__ void __launch_bounds__(1024)
             offsets[b]  = lo;
             cursor[b]   = lo;
             uint32_t slot = 0;
-            if (hi > lo && (hi - 1) / chunk - lo / chunk + 1 > kMsmHeavyRecords)
+            if (hi > lo && (hi - 1) / chunk - lo / chunk + 1 > thr)
             {
                 uint32_t pos = atomicAdd(&counts[0], 1u);
                 if (pos < kMsmMaxHeavy)
@@ -166,7 +168,7 @@ static __global__ void __launch_bounds__(1024)
     }
 }
 
-// Pass 2: scatter entry = (window * n + base) | sign << 31 into its bucket's range.
+// Pass 2: scatter entry = base | window << 27 | sign << 31 into its bucket's range.
 static __global__ void __launch_bounds__(256)
     k_msm_scatter(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ scalar_idx, uint32_t scalar_offset,
                   uint32_t n, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted)
@@ -202,7 +204,7 @@ static __global__ void __launch_bounds__(256)
         {
             uint32_t bkt = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
             uint32_t pos = atomicAdd(&cursor[bkt], 1u);
-            sorted[pos]  = ((uint32_t)j * n + i) | (d < 0 ? 0x80000000u : 0u);
+            sorted[pos]  = i | ((uint32_t)j << kMsmEntryBaseBits) | (d < 0 ? 0x80000000u : 0u);
         }
     }
 }
@@ -218,8 +220,8 @@ uint32_t msm_default_chunk(uint64_t n)
 
 void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_t scalar_offset, uint32_t chunk)
 {
-    if ((uint64_t)n * kMsmWindows >= 0x80000000ull)
-        throw CudaError("MSM too large for 31-bit entry ids");
+    if (n > kMsmEntryBaseMask)
+        throw CudaError("MSM too large for 27-bit base ids");
     s.n             = n;
     s.scalar_idx    = scalar_idx;
     s.scalar_offset = scalar_offset;
