@@ -39,6 +39,7 @@ class MappedFile
 {
     uint8_t* addr_ = nullptr;
     size_t   size_ = 0;
+    int      fd_   = -1;
 
 public:
     explicit MappedFile(const std::string& path)
@@ -59,16 +60,22 @@ public:
             throw LoadError("empty file: " + path);
         }
         void* m = ::mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
-        ::close(fd);
         if (m == MAP_FAILED)
+        {
+            ::close(fd);
             throw LoadError("mmap failed: " + path);
+        }
         addr_ = static_cast<uint8_t*>(m);
+        fd_   = fd;
     }
     ~MappedFile()
     {
         if (addr_)
             ::munmap(addr_, size_);
+        if (fd_ >= 0)
+            ::close(fd_);
     }
+    int fd() const { return fd_; } // stays open for bulk pread() (cheaper than faulting the mapping in)
     MappedFile(const MappedFile&)            = delete;
     MappedFile& operator=(const MappedFile&) = delete;
     const uint8_t* data() const { return addr_; }

@@ -161,6 +161,29 @@ static char* dup_string(const std::string& s)
     return out;
 }
 
+// shared tail of the two prove entry points: `run` produces the proof JSON (throws on failure)
+template <class Run>
+static int prove_common(kzp_prover* p, Run&& run, char** json_out, int* error_out, int* prover_time_ms)
+{
+    auto fail = [&](int err) {
+        if (error_out)
+            *error_out = err;
+        return KZP_RESPONSE_ERROR;
+    };
+    std::string json;
+    auto        t0 = std::chrono::steady_clock::now();
+    int         rc = guarded([&] { json = run(); });
+    if (rc != KZP_OK)
+        return fail(KZP_PROVER_ERROR_INVALID_INPUT);
+    auto t1 = std::chrono::steady_clock::now();
+    if (prover_time_ms)
+        *prover_time_ms = (int)std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count();
+    *json_out = dup_string(json);
+    if (error_out)
+        *error_out = KZP_PROVER_ERROR_NONE;
+    return KZP_RESPONSE_SUCCESS;
+}
+
 int kzp_prover_prove_mem(kzp_prover* p, const uint8_t* witness, uint64_t n, const uint8_t* r32,
                          const uint8_t* s32, char** json_out, int* error_out, int* prover_time_ms)
 {
@@ -183,18 +206,8 @@ int kzp_prover_prove_mem(kzp_prover* p, const uint8_t* witness, uint64_t n, cons
         g_last_error = "null argument";
         return fail(KZP_PROVER_ERROR_INVALID_INPUT);
     }
-    std::string json;
-    auto        t0 = std::chrono::steady_clock::now();
-    int         rc = guarded([&] { json = p->prover->prove(witness, n, r32, s32); });
-    if (rc != KZP_OK)
-        return fail(KZP_PROVER_ERROR_INVALID_INPUT);
-    auto t1 = std::chrono::steady_clock::now();
-    if (prover_time_ms)
-        *prover_time_ms = (int)std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count();
-    *json_out = dup_string(json);
-    if (error_out)
-        *error_out = KZP_PROVER_ERROR_NONE;
-    return KZP_RESPONSE_SUCCESS;
+    return prove_common(p, [&] { return p->prover->prove(witness, n, r32, s32); }, json_out, error_out,
+                        prover_time_ms);
 }
 
 int kzp_prover_prove(kzp_prover* p, const char* wtns_path, const uint8_t* r32, const uint8_t* s32,
@@ -214,10 +227,16 @@ int kzp_prover_prove(kzp_prover* p, const char* wtns_path, const uint8_t* r32, c
         g_last_error = p ? p->why : "null prover";
         return fail(KZP_PROVER_ERROR_NOT_READY);
     }
+    if (!json_out)
+    {
+        g_last_error = "null argument";
+        return fail(KZP_PROVER_ERROR_INVALID_INPUT);
+    }
     int ret = KZP_RESPONSE_ERROR;
     int rc  = guarded([&] {
         // The reference throws out of prove() on an unreadable witness (fullprover.cpp:212, a bug noted in
-        // SURVEY.md §8(b)); here it is reported as INVALID_INPUT.
+        // SURVEY.md §8(b)); here it is reported as INVALID_INPUT. Only the headers are read through the mapping;
+        // the values go file -> pinned staging buffer by pread().
         MappedFile file(wtns_path ? wtns_path : "");
         BinView    bin(file.data(), file.size(), "wtns", 2);
         WtnsHeader wh = parse_wtns(bin);
@@ -227,8 +246,10 @@ int kzp_prover_prove(kzp_prover* p, const char* wtns_path, const uint8_t* r32, c
             ret          = fail(KZP_PROVER_ERROR_WITNESS_GENERATION_INVALID_CURVE);
             return;
         }
-        uint64_t n = wh.values_bytes / 32;
-        ret = kzp_prover_prove_mem(p, wh.values, n, r32, s32, json_out, error_out, prover_time_ms);
+        uint64_t n   = wh.values_bytes / 32;
+        uint64_t off = (uint64_t)(wh.values - file.data());
+        ret = prove_common(p, [&] { return p->prover->prove_fd(file.fd(), off, n, r32, s32); }, json_out, error_out,
+                           prover_time_ms);
     });
     if (rc != KZP_OK)
         return fail(KZP_PROVER_ERROR_INVALID_INPUT);
@@ -257,7 +278,7 @@ int kzp_prover_upload_witness_file(kzp_prover* p, const char* wtns_path)
         WtnsHeader wh = parse_wtns(bin);
         if (!wh.prime_is_bn254_r)
             throw FormatError("witness file uses a different curve than bn128");
-        p->prover->upload_witness(wh.values, wh.values_bytes / 32);
+        p->prover->upload_witness_fd(file.fd(), (uint64_t)(wh.values - file.data()), wh.values_bytes / 32);
     });
 }
 

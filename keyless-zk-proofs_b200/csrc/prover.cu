@@ -2,7 +2,14 @@
 // Stage order follows Prover::prove in the reference (rust-rapidsnark/rapidsnark/src/groth16.cpp:43-360);
 // what the reference runs as std::async futures on CPU threads runs here on two CUDA streams.
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <unistd.h>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <thread>
@@ -285,6 +292,84 @@ std::string assemble_proof(const HostVk& vk, const ShardPartials* ps, int count,
     return j;
 }
 
+// Persistent staging workers (spawning threads per proof costs more than the copy they do).
+class SlicePool
+{
+    std::vector<std::thread>           threads_;
+    std::mutex                         mu_;
+    std::condition_variable            cv_;
+    std::function<void(size_t)>        job_;
+    size_t                             n_slices_ = 0;
+    std::atomic<size_t>                next_{0};
+    uint64_t                           generation_ = 0;
+    int                                active_     = 0; // workers currently inside drain()
+    bool                               stop_       = false;
+
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_)
+                    return;
+                seen = generation_;
+                active_++;
+            }
+            drain();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                active_--;
+            }
+            cv_.notify_all();
+        }
+    }
+
+public:
+    explicit SlicePool(int n)
+    {
+        for (int i = 0; i < n; i++)
+            threads_.emplace_back([this] { loop(); });
+    }
+    ~SlicePool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_)
+            t.join();
+    }
+    // workers call job(k) for every k < n_slices exactly once; the job must stay valid until the caller has seen
+    // every slice complete (the job signals that itself)
+    void start(size_t n_slices, std::function<void(size_t)> job)
+    {
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return active_ == 0; }); // nobody is still looking at the previous job
+            job_      = std::move(job);
+            n_slices_ = n_slices;
+            next_.store(0);
+            generation_++;
+        }
+        cv_.notify_all();
+    }
+    void drain()
+    {
+        for (;;)
+        {
+            size_t k = next_.fetch_add(1);
+            if (k >= n_slices_)
+                return;
+            job_(k);
+        }
+    }
+    size_t size() const { return threads_.size(); }
+};
+
 class DeviceProverImpl
 {
 public:
@@ -321,6 +406,7 @@ public:
     MsmScratch<G2Xyzz> sc_b2;
 
     HostVk vk;
+    std::unique_ptr<SlicePool> pool; // witness staging workers
 
     ShardPartials parts;
     ShardPartials sums;       // the five MSM results of the last assemble(), summed over shards
@@ -415,9 +501,18 @@ public:
         if (device < 0 || device >= n_dev)
             throw CudaError("CUDA device " + std::to_string(device) + " not present");
         set_device();
-        KZP_CUDA_CHECK(cudaStreamCreateWithFlags(&st_h, cudaStreamNonBlocking));
-        KZP_CUDA_CHECK(cudaStreamCreateWithFlags(&st_w, cudaStreamNonBlocking));
-        KZP_CUDA_CHECK(cudaStreamCreateWithFlags(&st_w2, cudaStreamNonBlocking));
+        // The witness MSMs are short, latency-bound chains; the H chain is long and fills the machine. Giving the
+        // witness streams priority lets their small grids run as soon as they are ready while NTT / H-MSM blocks
+        // fill every SM slot they leave free (KZP_PRIO=0 disables, =-1 inverts: for experiments).
+        int prio_lo = 0, prio_hi = 0;
+        KZP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        const char* pe   = getenv("KZP_PRIO");
+        int         mode = pe ? atoi(pe) : 1;
+        int         ph   = mode == 1 ? prio_lo : (mode == -1 ? prio_hi : prio_lo);
+        int         pw   = mode == 1 ? prio_hi : (mode == -1 ? prio_lo : prio_lo);
+        KZP_CUDA_CHECK(cudaStreamCreateWithPriority(&st_h, cudaStreamNonBlocking, ph));
+        KZP_CUDA_CHECK(cudaStreamCreateWithPriority(&st_w, cudaStreamNonBlocking, pw));
+        KZP_CUDA_CHECK(cudaStreamCreateWithPriority(&st_w2, cudaStreamNonBlocking, pw));
         KZP_CUDA_CHECK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
         for (auto& e : ev)
             KZP_CUDA_CHECK(cudaEventCreate(&e));
@@ -438,6 +533,11 @@ public:
         KZP_CUDA_CHECK(cudaMalloc(&d_h, vec));
         KZP_CUDA_CHECK(cudaMallocHost(&pinned_w, (size_t)n_vars * 32));
         KZP_CUDA_CHECK(cudaMallocHost(&pinned_out, sizeof(ShardPartials)));
+        {
+            const char* te = getenv("KZP_UPLOAD_THREADS");
+            int         nt = te ? atoi(te) : (int)std::min(12u, std::max(1u, std::thread::hardware_concurrency() * 3 / 4));
+            pool.reset(new SlicePool(std::max(nt, 0)));
+        }
 
         // this shard's base ranges: wires [w0, w1) of sections 5-8, points [h0, h1) of section 9
         uint64_t w0 = (uint64_t)rank * n_vars / (uint64_t)world, w1 = (uint64_t)(rank + 1) * n_vars / (uint64_t)world;
@@ -459,6 +559,7 @@ public:
 
     ~DeviceProverImpl()
     {
+        pool.reset();
         cudaSetDevice(device);
         cudaDeviceSynchronize();
         msm_bases_destroy(bases_a);
@@ -494,54 +595,83 @@ public:
         cudaStreamDestroy(st_copy);
     }
 
-    // Host -> pinned staging -> device, pipelined: kUploadThreads workers copy slices into the pinned buffer (the
-    // source is normally a fresh file mapping, so this is also where its pages are faulted in) while the calling
+    // Host -> pinned staging -> device, pipelined: worker threads fill slices of the pinned buffer (memcpy from
+    // memory, or pread() straight from the witness file: no page faults on a fresh mapping) while the calling
     // thread hands every finished slice to the copy engine.
-    void upload(const uint8_t* values, uint64_t n)
+    //   KZP_UPLOAD_THREADS (default 8), KZP_UPLOAD_SLICE_KB (default 2048)
+    template <class Fill>
+    void upload_with(Fill&& fill)
     {
-        if (n < n_vars)
-            throw FormatError("witness has fewer values than the zkey has variables");
         set_device();
+        static const size_t slice = getenv("KZP_UPLOAD_SLICE_KB") ? (size_t)atoi(getenv("KZP_UPLOAD_SLICE_KB")) << 10 : (2u << 20);
         const size_t total    = (size_t)n_vars * 32;
-        const size_t slice    = 2u << 20;
         const size_t n_slices = (total + slice - 1) / slice;
-        const int    kUploadThreads = 4;
         std::vector<std::atomic<int>> ready(n_slices);
         for (auto& r : ready)
             r.store(0, std::memory_order_relaxed);
-        std::atomic<size_t>      next{0};
-        std::vector<std::thread> workers;
-        auto                     work = [&] {
-            for (;;)
-            {
-                size_t k = next.fetch_add(1);
-                if (k >= n_slices)
-                    return;
-                size_t off = k * slice, len = std::min(slice, total - off);
-                memcpy(pinned_w + off, values + off, len);
-                ready[k].store(1, std::memory_order_release);
-            }
+        std::atomic<int> failed{0};
+        auto             job = [&](size_t k) {
+            size_t off = k * slice, len = std::min(slice, total - off);
+            if (!fill(pinned_w + off, off, len))
+                failed.store(1);
+            ready[k].store(1, std::memory_order_release);
         };
-        int n_workers = (int)std::min<size_t>(kUploadThreads, n_slices);
-        for (int t = 1; t < n_workers; t++)
-            workers.emplace_back(work);
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H2D0], st_copy));
+        double dbg_t0 = now_ms();
+        if (pool && pool->size() > 0 && n_slices > 1)
+            pool->start(n_slices, job);
+        else
+            for (size_t k = 0; k < n_slices; k++)
+                job(k);
         cudaError_t err = cudaSuccess;
-        if (n_workers <= 1)
-            work();
         for (size_t k = 0; k < n_slices; k++)
         {
             while (!ready[k].load(std::memory_order_acquire))
                 std::this_thread::yield();
             size_t off = k * slice, len = std::min(slice, total - off);
-            if (err == cudaSuccess)
+            if (err == cudaSuccess && !failed.load())
                 err = cudaMemcpyAsync((uint8_t*)d_w + off, pinned_w + off, len, cudaMemcpyHostToDevice, st_copy);
         }
-        for (auto& w : workers)
-            w.join();
         KZP_CUDA_CHECK(err);
+        if (failed.load())
+            throw LoadError("reading the witness failed");
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H2D1], st_copy));
+        if (getenv("KZP_DEBUG_UPLOAD"))
+        {
+            double t1 = now_ms();
+            cudaStreamSynchronize(st_copy);
+            fprintf(stderr, "[kzp upload] staged+enqueued %.3f ms, DMA drained +%.3f ms, %zu slices, %zu workers\n",
+                    t1 - dbg_t0, now_ms() - t1, n_slices, pool ? pool->size() : 0);
+        }
         witness_resident = true;
+    }
+
+    void upload(const uint8_t* values, uint64_t n)
+    {
+        if (n < n_vars)
+            throw FormatError("witness has fewer values than the zkey has variables");
+        upload_with([&](uint8_t* dst, size_t off, size_t len) {
+            memcpy(dst, values + off, len);
+            return true;
+        });
+    }
+
+    void upload_fd(int fd, uint64_t file_offset, uint64_t n)
+    {
+        if (n < n_vars)
+            throw FormatError("witness has fewer values than the zkey has variables");
+        upload_with([&](uint8_t* dst, size_t off, size_t len) {
+            while (len > 0)
+            {
+                ssize_t got = ::pread(fd, dst, len, (off_t)(file_offset + off));
+                if (got <= 0)
+                    return false;
+                dst += got;
+                off += (size_t)got;
+                len -= (size_t)got;
+            }
+            return true;
+        });
     }
 
     // Enqueues the whole GPU part of one proof (no host synchronisation).
@@ -650,10 +780,11 @@ public:
     }
 
     // upload + GPU + assembly with the r/s-only host work overlapped with the GPU
-    std::string prove(const uint8_t* values, uint64_t n, const uint8_t* r32, const uint8_t* s32)
+    template <class Upload>
+    std::string prove_with(Upload&& do_upload, const uint8_t* r32, const uint8_t* s32)
     {
         double t0 = now_ms();
-        upload(values, n);
+        do_upload();
         launch_gpu();
         BlindTerms bt;
         compute_blind_terms(vk, r32, s32, bt);
@@ -698,8 +829,13 @@ std::string DeviceProver::assemble(const ShardPartials* parts, int count, const 
 }
 std::string DeviceProver::prove(const uint8_t* values, uint64_t n, const uint8_t* r32, const uint8_t* s32)
 {
-    return impl_->prove(values, n, r32, s32);
+    return impl_->prove_with([&] { impl_->upload(values, n); }, r32, s32);
 }
+std::string DeviceProver::prove_fd(int fd, uint64_t file_offset, uint64_t n, const uint8_t* r32, const uint8_t* s32)
+{
+    return impl_->prove_with([&] { impl_->upload_fd(fd, file_offset, n); }, r32, s32);
+}
+void DeviceProver::upload_witness_fd(int fd, uint64_t file_offset, uint64_t n) { impl_->upload_fd(fd, file_offset, n); }
 const ProveTimings& DeviceProver::timings() const { return impl_->tm; }
 void DeviceProver::msm_profile(int which, float* ms, uint64_t* entries) const
 {

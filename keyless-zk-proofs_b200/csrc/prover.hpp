@@ -74,6 +74,8 @@ public:
 
     // Upload a witness (n values x 32 B canonical LE) from host memory; n must be >= n_vars.
     void upload_witness(const uint8_t* values, uint64_t n);
+    // Same, reading the values with pread() from an open witness file at `file_offset`.
+    void upload_witness_fd(int fd, uint64_t file_offset, uint64_t n);
     // Run the GPU part on the resident witness; leaves partial MSM results on the host.
     void run_gpu();
     const ShardPartials& partials() const;
@@ -83,6 +85,7 @@ public:
 
     // convenience: upload + run + assemble for world == 1
     std::string prove(const uint8_t* values, uint64_t n, const uint8_t* r32, const uint8_t* s32);
+    std::string prove_fd(int fd, uint64_t file_offset, uint64_t n, const uint8_t* r32, const uint8_t* s32);
 
     const ProveTimings& timings() const;
     // bucket-accumulation kernel of MSM `which` (0 A, 1 B1, 2 B2, 3 C, 4 H) in the last proof: duration and entries
