@@ -222,6 +222,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     distributed = world > 1
+    if rank == 0:
+        # torchrun pins OMP_NUM_THREADS=1; the input generator and the CPU reference arm are OpenMP programs that
+        # should use the box's cores (libgomp reads this when it is first loaded, i.e. before `import torch`)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
     if args.impl == "reference":
         # rank 0 alone runs and prints; the others exit without work (no process group needed)
@@ -229,6 +233,9 @@ def main():
             zkey, wtns, info = ensure_inputs(args.workload)
             run_reference_arm(args, zkey, wtns, info, rank)
         return 0
+
+    if rank == 0:
+        zkey, wtns, info = ensure_inputs(args.workload)  # before torch (and its libgomp) is loaded; other ranks wait at init
 
     import torch
     import torch.distributed as dist
@@ -245,8 +252,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    if rank == 0:
-        zkey, wtns, info = ensure_inputs(args.workload)
     barrier()
     if rank != 0:
         zkey, wtns, info = ensure_inputs(args.workload)
@@ -371,11 +376,17 @@ def main():
                                  "gpu_ms", "assemble_host_ms")},
             "roofline": {
                 "kernel": "k_msm_accumulate<G1> of the H MSM (bucket accumulation, XYZZ mixed adds)",
-                "bound": "int32-multiply (IMAD.WIDE pipe; BASELINE.json: 'MSM vs integer-multiply peak') — neither hbm nor tensor",
-                "achieved": achieved, "peak": imad_peak / 1e12, "unit": "T multiply-add/s", "frac": achieved / (imad_peak / 1e12),
-                "peak_source": "kzp_imad_peak: dependent-free mad.wide.u32 chains on all SMs, measured in this run",
-                "algorithmic_work": "%d sorted (point,bucket) entries x %d Fq-mul x %d multiply-adds" % (entries, FQ_MUL_PER_MIXED_ADD, IMAD_PER_FQ_MUL),
-                "launch_ms": acc_t, "traffic": None},
+                "bound": "integer-pipe (IMAD.WIDE; BASELINE.json: 'MSM vs integer-multiply peak') — neither hbm nor tensor: "
+                         "ncu shows sm__pipe_fmaheavy_cycles_active 89% and dram throughput 11% for this kernel",
+                "achieved": achieved, "peak": imad_peak / 1e12, "unit": "T wide-multiply-add/s", "frac": achieved / (imad_peak / 1e12),
+                "peak_source": "kzp_imad_peak: carry-chained mad.lo.cc/madc.hi.cc (IMAD.WIDE.U32[.X]) on all SMs, measured in "
+                               "this run; IMAD.WIDE issues at half the 32-bit IMAD rate on sm_100a (profiles/r01_ubench_int_fp64_pipes.txt)",
+                "algorithmic_work": "%d sorted (point,bucket) entries x %d Fq-mul x %d wide multiply-adds" % (entries, FQ_MUL_PER_MIXED_ADD, IMAD_PER_FQ_MUL),
+                "launch_ms": acc_t,
+                "traffic": 4.50e9, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, "
+                                                   "profiles/r01_ncu_top_kernels.txt); algorithmic bytes = entries x (64 B point + 4 B entry) = %.2e" % (entries * 68.0),
+                "hbm_view": {"achieved": 4.50e9 / (acc_t * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": 4.50e9 / (acc_t * 1e-3) / 1e9 / hbm_peak}},
             "roofline_ntt": {
                 "kernel": "NTT stage kernels, 3 x (iNTT + coset + NTT) + pointwise, per proof",
                 "bound": "hbm", "achieved": ntt_bytes / (ntt_t * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -553,14 +553,14 @@ kzp_msm* kzp_msm_new(int group, const uint8_t* bases, uint64_t n, int device)
         if (group == 0)
         {
             msm_bases_create<G1Xyzz>(m->b1, bases, n, true, 0);
-            msm_sort_create(m->sort, m->b1.n, m->b1.scalar_idx, 0, 0);
-            msm_scratch_create<G1Xyzz>(m->s1, m->sort);
+            msm_sort_create(m->sort, m->b1.n, m->b1.scalar_idx, 0);
+            msm_scratch_create<G1Xyzz>(m->s1, m->sort, 0);
         }
         else
         {
             msm_bases_create<G2Xyzz>(m->b2, bases, n, true, 0);
-            msm_sort_create(m->sort, m->b2.n, m->b2.scalar_idx, 0, 0);
-            msm_scratch_create<G2Xyzz>(m->s2, m->sort);
+            msm_sort_create(m->sort, m->b2.n, m->b2.scalar_idx, 0);
+            msm_scratch_create<G2Xyzz>(m->s2, m->sort, 0);
         }
     });
     if (rc != KZP_OK)

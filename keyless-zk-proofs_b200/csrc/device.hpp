@@ -97,13 +97,10 @@ struct MsmSort
     uint32_t  scalar_offset = 0;       // scalar index of element 0 when scalar_idx == nullptr
     const uint32_t* scalar_idx = nullptr; // optional gather list (n entries, not owned)
     uint32_t  cap_entries   = 0;
-    uint32_t  chunk         = 32;      // sorted entries per accumulate thread
-    uint32_t* counts        = nullptr; // kMsmBuckets + 2; counts[0] doubles as the heavy-bucket counter
+    uint32_t* counts        = nullptr; // kMsmBuckets + 2
     uint32_t* offsets       = nullptr; // kMsmBuckets + 2 (offsets[b] = first entry of bucket b; [B+1] = total)
     uint32_t* cursor        = nullptr; // kMsmBuckets + 2
     uint32_t* sorted        = nullptr; // cap_entries
-    uint32_t* heavy_ids     = nullptr; // kMsmMaxHeavy
-    uint32_t* heavy_slot    = nullptr; // kMsmBuckets + 2: 0 = light bucket, k + 1 = k-th heavy bucket
 };
 
 template <class XY>
@@ -119,6 +116,10 @@ struct MsmBases
 template <class XY>
 struct MsmScratch
 {
+    uint32_t  chunk         = 32;      // sorted entries per accumulate thread (per MSM: G2 wants smaller chunks)
+    uint32_t* heavy_count   = nullptr; // 1: number of heavy buckets of the current sort at this chunk size
+    uint32_t* heavy_ids     = nullptr; // kMsmMaxHeavy
+    uint32_t* heavy_slot    = nullptr; // kMsmBuckets + 2: 0 = light bucket, k + 1 = k-th heavy bucket
     XY*       records       = nullptr; // cap_entries / chunk + kMsmBuckets + 2 partial sums, grouped by bucket
     XY*       heavy_partial = nullptr; // kMsmMaxHeavy x kMsmHeavyBlocks
     XY*       heavy_sum     = nullptr; // kMsmMaxHeavy
@@ -130,7 +131,7 @@ struct MsmScratch
     cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr; // bracket the bucket-accumulation kernel of the last run
 };
 
-void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_t scalar_offset, uint32_t chunk);
+void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_t scalar_offset);
 void msm_sort_destroy(MsmSort& s);
 // scalars: device array of 32-byte little-endian integers (canonical or not; reduced mod r on the fly).
 void msm_sort_run(MsmSort& s, const uint32_t* scalars, cudaStream_t st);
@@ -144,12 +145,13 @@ void msm_bases_create(MsmBases<XY>& out, const uint8_t* points_host, uint64_t co
                       cudaStream_t st);
 template <class XY>
 void msm_bases_destroy(MsmBases<XY>& b);
+// chunk = sorted entries per accumulate thread (0 = msm_default_chunk(sort.n))
 template <class XY>
-void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort);
+void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort, uint32_t chunk);
 template <class XY>
 void msm_scratch_destroy(MsmScratch<XY>& s);
-// Bucket accumulation + reduction of `nb` <= kMsmMaxBatch MSMs that share one digit sort (bases[k]->n == sort.n).
-// Leaves each XYZZ result in scr[k]->result (device).
+// Bucket accumulation + reduction of `nb` <= kMsmMaxBatch MSMs that share one digit sort (bases[k]->n == sort.n)
+// and one chunk size. Leaves each XYZZ result in scr[k]->result (device).
 template <class XY>
 void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, MsmScratch<XY>* const* scr, int nb,
                       cudaStream_t st);
@@ -159,7 +161,7 @@ template <class XY>
 void msm_last_accumulate(const MsmSort& sort, const MsmScratch<XY>& s, float* ms, uint64_t* entries);
 // kernels launched by one msm_sort_run / one msm_reduce_batch
 constexpr uint32_t kMsmSortLaunches   = 3;
-constexpr uint32_t kMsmReduceLaunches = 5;
+constexpr uint32_t kMsmReduceLaunches = 6;
 
 extern template struct MsmBases<G1Xyzz>;
 extern template struct MsmBases<G2Xyzz>;

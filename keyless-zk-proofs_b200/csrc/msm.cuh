@@ -28,6 +28,9 @@ struct MsmBatchArgs
     const typename XY::Affine* table[kMsmMaxBatch];
     const uint8_t*             skip[kMsmMaxBatch]; // per base column: 1 = infinity (nullptr = no flags)
     XY*                        records[kMsmMaxBatch];
+    uint32_t*                  heavy_count; // classification is shared by the batch (same sort, same chunk)
+    uint32_t*                  heavy_ids;
+    uint32_t*                  heavy_slot;
     XY*                        heavy_partial[kMsmMaxBatch];
     XY*                        heavy_sum[kMsmMaxBatch];
     uint32_t*                  heavy_done[kMsmMaxBatch];
@@ -143,6 +146,32 @@ __device__ __forceinline__ XY load_cg(const XY* p)
     return r;
 }
 
+// ---- bucket classification ------------------------------------------------------------------------------
+// A bucket whose range spans more accumulate threads than max(kMsmHeavyRecords, 2 x average) is "heavy": it gets a
+// slot in the heavy list and is pre-reduced by whole blocks (k_msm_heavy) instead of one finalise thread.
+static __global__ void __launch_bounds__(256)
+    k_msm_classify(const uint32_t* __restrict__ offsets, uint32_t chunk, uint32_t* __restrict__ heavy_count,
+                   uint32_t* __restrict__ heavy_ids, uint32_t* __restrict__ heavy_slot)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (b > kMsmBuckets)
+        return;
+    uint32_t total = offsets[kMsmBuckets + 1];
+    uint32_t thr   = max(kMsmHeavyRecords, 2u * (total / chunk / kMsmBuckets + 1u));
+    uint32_t lo = offsets[b], hi = offsets[b + 1];
+    uint32_t slot = 0;
+    if (hi > lo && (hi - 1) / chunk - lo / chunk + 1 > thr)
+    {
+        uint32_t pos = atomicAdd(heavy_count, 1u);
+        if (pos < kMsmMaxHeavy)
+        {
+            heavy_ids[pos] = b;
+            slot           = pos + 1;
+        }
+    }
+    heavy_slot[b] = slot;
+}
+
 // ---- heavy buckets -------------------------------------------------------------------------------------
 // A bucket whose range spans more accumulate threads than the sort's heavy threshold (bucket 1 of a bit-heavy
 // witness holds ~half of all entries; byte-valued wires fill buckets 2..255) is summed by whole blocks: its records
@@ -151,9 +180,9 @@ __device__ __forceinline__ XY load_cg(const XY* p)
 // grid = (kMsmHeavyGrid, batch).
 template <class XY>
 __global__ void __launch_bounds__(256)
-    k_msm_heavy(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                const uint32_t* __restrict__ heavy_ids, MsmBatchArgs<XY> args, uint32_t chunk)
+    k_msm_heavy(const uint32_t* __restrict__ offsets, MsmBatchArgs<XY> args, uint32_t chunk)
 {
+    const uint32_t* __restrict__ heavy_ids = args.heavy_ids;
     extern __shared__ uint4 smem_raw[];
     __shared__ uint32_t     s_last;
     __shared__ uint32_t     pre[kMsmMaxHeavy + 1];
@@ -163,7 +192,7 @@ __global__ void __launch_bounds__(256)
     XY*                     sums    = args.heavy_sum[blockIdx.y];
     uint32_t*               done    = args.heavy_done[blockIdx.y];
     uint32_t                tid     = threadIdx.x;
-    uint32_t                n       = min(counts[0], kMsmMaxHeavy);
+    uint32_t                n       = min(*args.heavy_count, kMsmMaxHeavy);
     if (n == 0)
         return;
     // slices per heavy bucket, then an exclusive prefix (n <= 1024: one thread scans)
@@ -257,9 +286,9 @@ __global__ void __launch_bounds__(256)
 // higher digits are constant over a block). grid = (kMsmBuckets / 128, batch).
 template <class XY>
 __global__ void __launch_bounds__(kMsmFoldBlock)
-    k_msm_finalize_fold(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ heavy_slot,
-                        MsmBatchArgs<XY> args, uint32_t chunk)
+    k_msm_finalize_fold(const uint32_t* __restrict__ offsets, MsmBatchArgs<XY> args, uint32_t chunk)
 {
+    const uint32_t* __restrict__ heavy_slot = args.heavy_slot;
     extern __shared__ uint4 smem_raw[];
     XY*                     sm      = reinterpret_cast<XY*>(smem_raw);
     const XY* __restrict__  records = args.records[blockIdx.y];
@@ -618,12 +647,16 @@ static void msm_set_smem_attrs()
 }
 
 template <class XY>
-void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort)
+void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort, uint32_t chunk)
 {
     msm_set_smem_attrs<XY>(); // function attributes are per device: set on the device that owns the scratch
     size_t nb   = kMsmBuckets + 2;
     size_t nblk = kMsmBuckets / kMsmFoldBlock;
-    KZP_CUDA_CHECK(cudaMalloc(&s.records, ((size_t)sort.cap_entries / sort.chunk + nb + 1) * sizeof(XY)));
+    s.chunk     = chunk ? chunk : msm_default_chunk(sort.n);
+    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_count, 4));
+    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_ids, kMsmMaxHeavy * 4));
+    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_slot, nb * 4));
+    KZP_CUDA_CHECK(cudaMalloc(&s.records, ((size_t)sort.cap_entries / s.chunk + nb + 1) * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_partial, (size_t)kMsmMaxHeavy * kMsmHeavyBlocks * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_sum, (size_t)kMsmMaxHeavy * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_done, (size_t)kMsmMaxHeavy * 4));
@@ -639,6 +672,9 @@ void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort)
 template <class XY>
 void msm_scratch_destroy(MsmScratch<XY>& s)
 {
+    cudaFree(s.heavy_count);
+    cudaFree(s.heavy_ids);
+    cudaFree(s.heavy_slot);
     cudaFree(s.records);
     cudaFree(s.heavy_partial);
     cudaFree(s.heavy_sum);
@@ -677,22 +713,32 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
         a.classes[k]       = scr[j]->classes;
         a.result[k]        = scr[j]->result;
     }
+    const uint32_t chunk = scr[0]->chunk;
+    for (int k = 1; k < nb; k++)
+        if (scr[k]->chunk != chunk)
+            throw CudaError("MSM batch members must share one chunk size");
+    a.heavy_count = scr[0]->heavy_count;
+    a.heavy_ids   = scr[0]->heavy_ids;
+    a.heavy_slot  = scr[0]->heavy_slot;
     dim3 by(1, (unsigned int)nb, 1);
+    KZP_CUDA_CHECK(cudaMemsetAsync(a.heavy_count, 0, 4, st));
+    k_msm_classify<<<msm_div_up(kMsmBuckets, 256), 256, 0, st>>>(sort.offsets, chunk, a.heavy_count, a.heavy_ids,
+                                                                  a.heavy_slot);
+    KZP_CUDA_CHECK(cudaGetLastError());
     KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc0, st));
     if (sort.n > 0)
     {
-        uint64_t threads = ((uint64_t)sort.cap_entries + sort.chunk - 1) / sort.chunk;
+        uint64_t threads = ((uint64_t)sort.cap_entries + chunk - 1) / chunk;
         by.x             = msm_div_up(threads, 128);
-        k_msm_accumulate<XY><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, sort.chunk, sort.n);
+        k_msm_accumulate<XY><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n);
         KZP_CUDA_CHECK(cudaGetLastError());
     }
     KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc1, st));
     by.x = kMsmHeavyGrid;
-    k_msm_heavy<XY><<<by, 256, 256 * sizeof(XY), st>>>(sort.counts, sort.offsets, sort.heavy_ids, a, sort.chunk);
+    k_msm_heavy<XY><<<by, 256, 256 * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = kMsmBuckets / kMsmFoldBlock;
-    k_msm_finalize_fold<XY><<<by, kMsmFoldBlock, kMsmFoldBlock * sizeof(XY), st>>>(sort.offsets, sort.heavy_slot, a,
-                                                                                   sort.chunk);
+    k_msm_finalize_fold<XY><<<by, kMsmFoldBlock, kMsmFoldBlock * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = 32 * kMsmFoldLevels;
     k_msm_fold2<XY><<<by, 256, 256 * sizeof(XY), st>>>(a);

@@ -86,11 +86,8 @@ static __global__ void __launch_bounds__(256)
 }
 
 // Exclusive scan of counts[1..B] -> offsets[b] (start of bucket b), offsets[B+1] = total; cursor = offsets.
-// Also classifies buckets: one whose range spans more than kMsmHeavyRecords accumulate threads is "heavy" and gets
-// a slot in the heavy list (counts[0] is the list length; it is zeroed together with the histogram).
 static __global__ void __launch_bounds__(1024)
-    k_msm_scan(uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
-               uint32_t* __restrict__ heavy_ids, uint32_t* __restrict__ heavy_slot, uint32_t chunk)
+    k_msm_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor)
 {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
@@ -136,29 +133,14 @@ static __global__ void __launch_bounds__(1024)
     }
     __syncthreads();
     uint32_t base = warp_sums[wid] + inc - sum;
-    // heavy = more than max(kMsmHeavyRecords, 2 x the average number of records per bucket)
-    uint32_t thr = max(kMsmHeavyRecords, 2u * (carry_s / chunk / kMsmBuckets + 1u));
 #pragma unroll
     for (uint32_t k = 0; k < per; k++)
     {
         uint32_t b = b0 + k;
         if (b <= kMsmBuckets)
         {
-            uint32_t lo = base + loc[k];
-            uint32_t hi = (k + 1 < per) ? base + loc[k + 1] : base + sum;
-            offsets[b]  = lo;
-            cursor[b]   = lo;
-            uint32_t slot = 0;
-            if (hi > lo && (hi - 1) / chunk - lo / chunk + 1 > thr)
-            {
-                uint32_t pos = atomicAdd(&counts[0], 1u);
-                if (pos < kMsmMaxHeavy)
-                {
-                    heavy_ids[pos] = b;
-                    slot           = pos + 1;
-                }
-            }
-            heavy_slot[b] = slot;
+            offsets[b] = base + loc[k];
+            cursor[b]  = base + loc[k];
         }
     }
     if (tid == 0)
@@ -218,14 +200,13 @@ uint32_t msm_default_chunk(uint64_t n)
     return c;
 }
 
-void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_t scalar_offset, uint32_t chunk)
+void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_t scalar_offset)
 {
     if (n > kMsmEntryBaseMask)
         throw CudaError("MSM too large for 27-bit base ids");
     s.n             = n;
     s.scalar_idx    = scalar_idx;
     s.scalar_offset = scalar_offset;
-    s.chunk         = chunk ? chunk : msm_default_chunk(n);
     uint64_t cap    = (uint64_t)n * kMsmWindows;
     s.cap_entries   = (uint32_t)cap;
     size_t nb       = kMsmBuckets + 2;
@@ -233,8 +214,6 @@ void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_
     KZP_CUDA_CHECK(cudaMalloc(&s.offsets, nb * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.cursor, nb * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.sorted, std::max<uint64_t>(cap, 1) * 4));
-    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_ids, kMsmMaxHeavy * 4));
-    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_slot, nb * 4));
 }
 
 void msm_sort_destroy(MsmSort& s)
@@ -243,8 +222,6 @@ void msm_sort_destroy(MsmSort& s)
     cudaFree(s.offsets);
     cudaFree(s.cursor);
     cudaFree(s.sorted);
-    cudaFree(s.heavy_ids);
-    cudaFree(s.heavy_slot);
     s = MsmSort();
 }
 
@@ -257,7 +234,7 @@ void msm_sort_run(MsmSort& s, const uint32_t* scalars, cudaStream_t st)
         k_msm_count<<<sort_div_up(s.n, 256), 256, 0, st>>>(scalars, s.scalar_idx, s.scalar_offset, s.n, s.counts);
         KZP_CUDA_CHECK(cudaGetLastError());
     }
-    k_msm_scan<<<1, 1024, 0, st>>>(s.counts, s.offsets, s.cursor, s.heavy_ids, s.heavy_slot, s.chunk);
+    k_msm_scan<<<1, 1024, 0, st>>>(s.counts, s.offsets, s.cursor);
     KZP_CUDA_CHECK(cudaGetLastError());
     if (s.n > 0)
     {

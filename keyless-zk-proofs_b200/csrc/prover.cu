@@ -547,13 +547,15 @@ public:
         make_bases(bases_b2, zh.points_b2, n_vars, 0, w0, w1);
         make_bases(bases_c, zh.points_c, n_vars - n_public - 1, n_public + 1, w0, w1);
         make_bases(bases_h, zh.points_h, domain, 0, h0, h1);
-        msm_sort_create(sort_w, (uint32_t)(w1 - w0), nullptr, (uint32_t)w0, 32);
-        msm_sort_create(sort_h, (uint32_t)(h1 - h0), nullptr, (uint32_t)h0, 0);
-        msm_scratch_create(sc_a, sort_w);
-        msm_scratch_create(sc_b1, sort_w);
-        msm_scratch_create(sc_c, sort_w);
-        msm_scratch_create(sc_b2, sort_w);
-        msm_scratch_create(sc_h, sort_h);
+        msm_sort_create(sort_w, (uint32_t)(w1 - w0), nullptr, (uint32_t)w0);
+        msm_sort_create(sort_h, (uint32_t)(h1 - h0), nullptr, (uint32_t)h0);
+        // chunk = sorted entries per accumulate thread. A witness has few non-trivial digits (mostly bits and
+        // bytes): small chunks keep enough threads in flight; G2 additions are 3x as long, so smaller still.
+        msm_scratch_create(sc_a, sort_w, 32);
+        msm_scratch_create(sc_b1, sort_w, 32);
+        msm_scratch_create(sc_c, sort_w, 32);
+        msm_scratch_create(sc_b2, sort_w, 8);
+        msm_scratch_create(sc_h, sort_h, 0);
         KZP_CUDA_CHECK(cudaDeviceSynchronize());
     }
 
@@ -713,6 +715,14 @@ public:
         // ---- stream W: one digit sort of the witness, then A, B1, C as one G1 batch; B2 on its own stream
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_W0], st_w));
         msm_sort_run(sort_w, w, st_w);
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_WSORT], st_w));
+        {
+            // KZP_WDELAY=1: hold the witness bucket work back until the NTT chain is done, so that it overlaps the
+            // (atomics-bound) H digit sort instead of sharing the integer pipe with the NTT
+            static const int wdelay = getenv("KZP_WDELAY") ? atoi(getenv("KZP_WDELAY")) : 0;
+            if (wdelay == 1)
+                KZP_CUDA_CHECK(cudaStreamWaitEvent(st_w, ev[EV_NTT], 0));
+        }
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_WSORT], st_w));
         KZP_CUDA_CHECK(cudaStreamWaitEvent(st_w2, ev[EV_WSORT], 0));
         {
