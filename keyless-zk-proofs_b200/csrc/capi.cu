@@ -450,8 +450,8 @@ int kzp_fr_coset_chain(uint8_t* data, uint64_t n, int device)
             DevBuf buf(n * 32);
             Fr*    x = (Fr*)buf.p;
             KZP_CUDA_CHECK(cudaMemcpy(x, data, n * 32, cudaMemcpyHostToDevice));
-            ntt_inverse_dif(d, x, d.coset_br, 0);
-            ntt_forward_dit(d, x, 0);
+            Fr* xs[1] = {x};
+            ntt_coset_chain(d, xs, 1, 0);
             KZP_CUDA_CHECK(cudaDeviceSynchronize());
             KZP_CUDA_CHECK(cudaMemcpy(data, x, n * 32, cudaMemcpyDeviceToHost));
         }
@@ -480,18 +480,13 @@ int kzp_fr_ntt_bench(uint32_t log_n, int iters, int device, float* ms_per_chain)
             cudaEvent_t e0, e1;
             KZP_CUDA_CHECK(cudaEventCreate(&e0));
             KZP_CUDA_CHECK(cudaEventCreate(&e1));
+            Fr* xs[1] = {x};
             for (int w = 0; w < 2; w++)
-            {
-                ntt_inverse_dif(d, x, d.coset_br, 0);
-                ntt_forward_dit(d, x, 0);
-            }
+                ntt_coset_chain(d, xs, 1, 0);
             KZP_CUDA_CHECK(cudaDeviceSynchronize());
             KZP_CUDA_CHECK(cudaEventRecord(e0, 0));
             for (int it = 0; it < iters; it++)
-            {
-                ntt_inverse_dif(d, x, d.coset_br, 0);
-                ntt_forward_dit(d, x, 0);
-            }
+                ntt_coset_chain(d, xs, 1, 0);
             KZP_CUDA_CHECK(cudaEventRecord(e1, 0));
             KZP_CUDA_CHECK(cudaEventSynchronize(e1));
             float ms = 0;

@@ -51,6 +51,9 @@ void ntt_domain_destroy(NttDomain& d);
 void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st);
 void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st);
 uint32_t ntt_launches(uint32_t log_n); // kernels per transform
+// ifft -> coset shift -> fft (groth16.cpp:172-262) on `count` <= 3 vectors, all of them through each launch together;
+// returns the number of kernels launched
+uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st);
 // natural <-> bit-reversed permutation (only used by the component-level entry points that expose
 // the reference's natural-in/natural-out FFT::fft / FFT::ifft contract, fft.cpp:192-246)
 void ntt_bitrev_permute(Fr* x, uint32_t log_n, cudaStream_t st);

@@ -173,6 +173,15 @@ static void ntt_level_attrs()
     // per device; cheap enough to repeat
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttMidSmem));
+}
+
+static NttBatch ntt_batch1(Fr* x)
+{
+    NttBatch b;
+    for (int i = 0; i < kNttMaxBatch; i++)
+        b.x[i] = x;
+    return b;
 }
 
 // Sizes with k >= 11 run as 7-stage shared-memory levels (ntt_tiled.cuh) plus at most 6 plain stages; smaller ones
@@ -207,7 +216,7 @@ void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st)
         while (hi >= (uint32_t)kNttTileBits)
         {
             uint32_t lo = hi - kNttTileBits;
-            k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(x, d.tw_inv, log_n, lo, 0, lo == 0 ? post : nullptr);
+            k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_inv, log_n, lo, 0, lo == 0 ? post : nullptr);
             KZP_CUDA_CHECK(cudaGetLastError());
             hi = lo;
         }
@@ -242,10 +251,52 @@ void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st)
     uint32_t     plo   = 0;
     for (uint32_t lo = r; lo + kNttTileBits <= log_n; lo += kNttTileBits)
     {
-        k_ntt_level<true><<<lgrid, kNttThreads, kNttLevelSmem, st>>>(x, d.tw_fwd, log_n, lo, plo, nullptr);
+        k_ntt_level<true><<<lgrid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_fwd, log_n, lo, plo, nullptr);
         KZP_CUDA_CHECK(cudaGetLastError());
         plo = lo;
     }
+}
+
+// The prover's H chain on `count` <= 3 vectors at once: ifft, multiply by w_2n^i, fft (groth16.cpp:172-262), all
+// vectors through each launch together. When log_n is a multiple of 7 the middle two levels run fused (k_ntt_mid).
+uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st)
+{
+    uint32_t log_n = d.log_n;
+    if (count < 1 || count > kNttMaxBatch)
+        throw CudaError("NTT batch size out of range");
+    if (!ntt_use_levels(log_n) || log_n % kNttTileBits != 0)
+    {
+        for (int i = 0; i < count; i++)
+        {
+            ntt_inverse_dif(d, xs[i], d.coset_br, st);
+            ntt_forward_dit(d, xs[i], st);
+        }
+        return 2 * ntt_launches(log_n) * (uint32_t)count;
+    }
+    ntt_level_attrs();
+    NttBatch b;
+    for (int i = 0; i < kNttMaxBatch; i++)
+        b.x[i] = xs[i < count ? i : 0];
+    dim3     grid(1u << (log_n - kNttTileBits - 4), (unsigned int)count, 1);
+    uint32_t launches = 0;
+    for (uint32_t lo = log_n - kNttTileBits; lo > 0; lo -= kNttTileBits)
+    {
+        k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, nullptr);
+        KZP_CUDA_CHECK(cudaGetLastError());
+        launches++;
+    }
+    k_ntt_mid<<<grid, kNttThreads, kNttMidSmem, st>>>(b, d.tw_inv, d.tw_fwd, log_n, d.coset_br);
+    KZP_CUDA_CHECK(cudaGetLastError());
+    launches++;
+    uint32_t plo = 0;
+    for (uint32_t lo = kNttTileBits; lo + kNttTileBits <= log_n; lo += kNttTileBits)
+    {
+        k_ntt_level<true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr);
+        KZP_CUDA_CHECK(cudaGetLastError());
+        plo = lo;
+        launches++;
+    }
+    return launches;
 }
 
 // ---- twiddle tables (host generated once per domain; fft.cpp:40-136 computes the same roots:

@@ -12,6 +12,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -730,7 +731,10 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     {
         uint64_t threads = ((uint64_t)sort.cap_entries + chunk - 1) / chunk;
         by.x             = msm_div_up(threads, 128);
-        k_msm_accumulate<XY><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n);
+        static const int acc_smem = getenv("KZP_ACC_SMEM") ? atoi(getenv("KZP_ACC_SMEM")) : 0; // experiment: cap occupancy
+        if (acc_smem > 48 * 1024)
+            KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_accumulate<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize, acc_smem));
+        k_msm_accumulate<XY><<<by, 128, (size_t)(nb == 1 && sizeof(XY) == 128 ? acc_smem : 0), st>>>(sort.offsets, sort.sorted, a, chunk, sort.n);
         KZP_CUDA_CHECK(cudaGetLastError());
     }
     KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc1, st));

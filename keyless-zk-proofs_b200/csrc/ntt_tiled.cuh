@@ -26,6 +26,13 @@ namespace kzp
 constexpr int kNttTileBits = 7;
 constexpr int kNttTileCols = 16;
 constexpr int kNttThreads  = 256;
+constexpr int kNttMaxBatch = 3;
+
+// vectors transformed by one launch (blockIdx.y selects): the prover runs a, b and c through every level together
+struct NttBatch
+{
+    Fr* x[kNttMaxBatch];
+};
 
 __device__ __forceinline__ uint32_t ntt_phys(uint32_t t, uint32_t c) { return 16u * t + ((c + t) & 15u); }
 
@@ -126,9 +133,10 @@ __device__ __forceinline__ void ntt_round(Fr (&v)[8], const Fr* twT, uint32_t t_
 // post (DIF only, may be null): element at position pos is multiplied by post[pos] on the way out.
 template <bool DIT>
 __global__ void __launch_bounds__(kNttThreads, 2)
-    k_ntt_level(Fr* __restrict__ x, const Fr* __restrict__ tw, uint32_t k, uint32_t lo, uint32_t plo,
+    k_ntt_level(NttBatch batch, const Fr* __restrict__ tw, uint32_t k, uint32_t lo, uint32_t plo,
                 const Fr* __restrict__ post)
 {
+    Fr* __restrict__        x = batch.x[blockIdx.y];
     extern __shared__ uint4 ntt_smem[];
     uint4*                  sm  = ntt_smem;                                   // 2 planes x 2048 uint4
     Fr*                     twT = reinterpret_cast<Fr*>(ntt_smem + 2 * 2048); // 64 roots of order 128
@@ -254,6 +262,96 @@ __global__ void __launch_bounds__(kNttThreads, 2)
     }
 }
 
+
+// Fused middle of the prover's ifft -> coset shift -> fft chain when k is a multiple of 7: the inverse transform's
+// last level and the forward transform's first level both act on the same 128 contiguous elements (lo = 0), so one
+// CTA runs DIF rounds A, B, C, multiplies by post[pos] (= w_2n^bitrev(pos) / n: ifft scaling + coset shift), and
+// continues with DIT rounds C, B, A. Round C of both directions uses the same thread -> element map, so the hand-over
+// happens in registers. Saves one full read + write of the vector and four shared-memory passes per chain.
+__global__ void __launch_bounds__(kNttThreads, 2)
+    k_ntt_mid(NttBatch batch, const Fr* __restrict__ tw_inv, const Fr* __restrict__ tw_fwd, uint32_t k,
+              const Fr* __restrict__ post)
+{
+    Fr* __restrict__        x = batch.x[blockIdx.y];
+    extern __shared__ uint4 ntt_smem[];
+    uint4*                  sm   = ntt_smem;
+    Fr*                     twI  = reinterpret_cast<Fr*>(ntt_smem + 2 * 2048);
+    Fr*                     twF  = twI + 64;
+    const uint32_t          tid  = threadIdx.x;
+    if (tid < 64)
+        twI[tid] = tw_inv[(size_t)tid << (k - kNttTileBits)];
+    else if (tid < 128)
+        twF[tid - 64] = tw_fwd[(size_t)(tid - 64) << (k - kNttTileBits)];
+    const uint32_t base = blockIdx.x * (kNttTileCols << kNttTileBits); // 2048 contiguous elements
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+    {
+        uint32_t e = tid + 256u * q;
+        Fr       val = x[base + e];
+        ntt_sm_store(sm, e & 127u, e >> 7, val);
+    }
+    __syncthreads();
+    const uint32_t c = tid & 15u;
+    const uint32_t g = tid >> 4;
+    Fr             v[8];
+    // DIF rounds A and B through shared memory
+#pragma unroll 1
+    for (int round = 0; round < 2; round++)
+    {
+        uint32_t t_rest = round == 0 ? g : (g >> 1) * 16u + (g & 1u);
+        uint32_t sh     = round == 0 ? 4u : 1u;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            ntt_sm_load(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
+        ntt_round<false>(v, twI, t_rest & ((1u << sh) - 1u), sh, 3);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            ntt_sm_store(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
+        __syncthreads();
+    }
+    // round C of both directions in registers, with the pointwise multiplier in between
+    {
+        uint32_t t_rest = g * 8u;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            ntt_sm_load(sm, t_rest + (uint32_t)q, c, v[q]);
+        ntt_round<false>(v, twI, 0, 0, 1);
+        const Fr* pp = post + base + c * 128u + t_rest;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            Fr::mul(v[q], v[q], pp[q]);
+        ntt_round<true>(v, twF, 0, 0, 1);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            ntt_sm_store(sm, t_rest + (uint32_t)q, c, v[q]);
+        __syncthreads();
+    }
+    // DIT rounds B and A
+#pragma unroll 1
+    for (int round = 1; round >= 0; round--)
+    {
+        uint32_t t_rest = round == 0 ? g : (g >> 1) * 16u + (g & 1u);
+        uint32_t sh     = round == 0 ? 4u : 1u;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            ntt_sm_load(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
+        ntt_round<true>(v, twF, t_rest & ((1u << sh) - 1u), sh, 3);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            ntt_sm_store(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+    {
+        uint32_t e = tid + 256u * q;
+        Fr       val;
+        ntt_sm_load(sm, e & 127u, e >> 7, val);
+        x[base + e] = val;
+    }
+}
+
+constexpr size_t kNttMidSmem = 2 * 2048 * sizeof(uint4) + 128 * sizeof(Fr);
 constexpr size_t kNttLevelSmem = 2 * 2048 * sizeof(uint4) + 64 * sizeof(Fr);
 
 } // namespace kzp

@@ -190,6 +190,24 @@ __global__ void __launch_bounds__(128) p_point(XY* out, const typename XY::Affin
     if (XY::Field::is_zero(acc.x)) out[0] = acc;
 }
 
+template <class XY, int OP>
+__global__ void __launch_bounds__(32) p_point_lat(XY* out, const typename XY::Affine* in, int iters)
+{
+    XY acc, q;
+    XY::set_inf(acc);
+    XY::set_inf(q);
+    XY::madd(acc, in[threadIdx.x & 7]);
+    XY::madd(q, in[8 + (threadIdx.x & 7)]);
+    XY t = q;
+    XY::dbl(q, t);
+    for (int it = 0; it < iters; it++)
+    {
+        if (OP == 0) XY::add(acc, q);
+        else { XY t2 = acc; XY::dbl(acc, t2); }
+    }
+    if (XY::Field::is_zero(acc.x)) out[0] = acc;
+}
+
 template <class K>
 static float time_it(K&& launch)
 {
@@ -285,6 +303,41 @@ int main()
             t = time_it([&] { p_point<G1Xyzz, 1><<<grid, 128>>>((G1Xyzz*)sink, d, 512); });
             printf("blocks/SM %d (128 thr)  G1 dbl   %7.2f G dbl/s\n", bps, (double)grid * 128 * 512 / t / 1e6);
         }
+    }
+    // lone-warp latency (what bounds the MSM tail kernels): one warp per SM
+    {
+        G1Affine* d;
+        CK(cudaMalloc(&d, 16 * sizeof(G1Affine)));
+        G1Affine h[16];
+        G1Xyzz   g, acc;
+        G1Affine ga;
+        ga.x = Fq::one();
+        Fq two = Fq::one();
+        Fq::add(two, two, two);
+        ga.y = two;
+        G1Xyzz::from_affine(g, ga);
+        acc = g;
+        for (int i = 0; i < 16; i++)
+        {
+            G1Xyzz t = acc;
+            G1Xyzz::dbl(acc, t);
+            G1Xyzz::add(acc, g);
+            G1Xyzz::to_affine(h[i], acc);
+        }
+        CK(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
+        for (int w = 1; w <= 4; w *= 2)
+        {
+            float t = time_it([&] { p_field<Fq, 1, 0><<<sms, 32 * w>>>((Fq*)sink, 2048); });
+            printf("lone %d warp(s)/SM: Fq mul chain        %7.1f ns per mul\n", w, t * 1e6 / 2048);
+            t = time_it([&] { p_field<Fq, 2, 0><<<sms, 32 * w>>>((Fq*)sink, 2048); });
+            printf("lone %d warp(s)/SM: Fq mul 2 chains     %7.1f ns per mul\n", w, t * 1e6 / 4096);
+            t = time_it([&] { p_field<Fq, 4, 0><<<sms, 32 * w>>>((Fq*)sink, 2048); });
+            printf("lone %d warp(s)/SM: Fq mul 4 chains     %7.1f ns per mul\n", w, t * 1e6 / 8192);
+        }
+        float t = time_it([&] { p_point_lat<G1Xyzz, 0><<<sms, 32>>>((G1Xyzz*)sink, d, 256); });
+        printf("lone warp: G1 add %7.2f us, ", t * 1e3 / 256);
+        t = time_it([&] { p_point_lat<G1Xyzz, 1><<<sms, 32>>>((G1Xyzz*)sink, d, 256); });
+        printf("G1 dbl %7.2f us\n", t * 1e3 / 256);
     }
     CK(cudaDeviceSynchronize());
     printf("done\n");
