@@ -79,6 +79,11 @@ int kzp_prover_prove_mem(kzp_prover* p, const uint8_t* witness, uint64_t n, cons
 int kzp_prover_upload_witness(kzp_prover* p, const uint8_t* witness, uint64_t n);
 int kzp_prover_upload_witness_file(kzp_prover* p, const char* wtns_path);
 int kzp_prover_run_gpu(kzp_prover* p);                         /* all kernels, result = this shard's partials */
+/* One whole proof on the witness already resident in HBM (kzp_prover_upload_witness*): same code path as
+ * kzp_prover_prove minus the upload, i.e. the host-side proof assembly overlaps the GPU work. Result like
+ * kzp_prover_prove. */
+int kzp_prover_prove_resident(kzp_prover* p, const uint8_t* r32, const uint8_t* s32, char** json_out, int* error_out,
+                              int* prover_time_ms);
 #define KZP_PARTIALS_BYTES 768                                 /* A,B1,C,H as XYZZ (4x128) + B2 XYZZ (256) */
 int kzp_prover_get_partials(kzp_prover* p, uint8_t* out768);
 /* sum `count` shards' partials (count*768 bytes), blind and print */

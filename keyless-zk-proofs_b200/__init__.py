@@ -102,6 +102,7 @@ def lib() -> ctypes.CDLL:
         "kzp_prover_free": (None, [vp]),
         "kzp_prover_prove": (c.c_int, [vp, c.c_char_p, u8p, u8p, c.POINTER(vp), i32p, i32p]),
         "kzp_prover_prove_mem": (c.c_int, [vp, u8p, c.c_uint64, u8p, u8p, c.POINTER(vp), i32p, i32p]),
+        "kzp_prover_prove_resident": (c.c_int, [vp, u8p, u8p, c.POINTER(vp), i32p, i32p]),
         "kzp_prover_upload_witness": (c.c_int, [vp, u8p, c.c_uint64]),
         "kzp_prover_upload_witness_file": (c.c_int, [vp, c.c_char_p]),
         "kzp_prover_run_gpu": (c.c_int, [vp]),
@@ -233,6 +234,14 @@ class FullProver:
         out, err, ms = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int()
         rc = lib().kzp_prover_prove_mem(self._h, witness, len(witness) // 32, r, s, ctypes.byref(out),
                                         ctypes.byref(err), ctypes.byref(ms))
+        if rc != 0:
+            self._raise_prover_error(err.value)
+        return _take_string(out), {"prover_time": ms.value}
+
+    def prove_resident(self, r: Optional[bytes] = None, s: Optional[bytes] = None):
+        """One proof on the witness already uploaded with upload_witness*(): GPU work + overlapped host assembly."""
+        out, err, ms = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int()
+        rc = lib().kzp_prover_prove_resident(self._h, r, s, ctypes.byref(out), ctypes.byref(err), ctypes.byref(ms))
         if rc != 0:
             self._raise_prover_error(err.value)
         return _take_string(out), {"prover_time": ms.value}

@@ -210,6 +210,31 @@ int kzp_prover_prove_mem(kzp_prover* p, const uint8_t* witness, uint64_t n, cons
                         prover_time_ms);
 }
 
+int kzp_prover_prove_resident(kzp_prover* p, const uint8_t* r32, const uint8_t* s32, char** json_out, int* error_out,
+                              int* prover_time_ms)
+{
+    if (json_out)
+        *json_out = nullptr;
+    if (prover_time_ms)
+        *prover_time_ms = 0;
+    auto fail = [&](int err) {
+        if (error_out)
+            *error_out = err;
+        return KZP_RESPONSE_ERROR;
+    };
+    if (!p || p->state != KZP_STATE_OK || !p->prover)
+    {
+        g_last_error = p ? p->why : "null prover";
+        return fail(KZP_PROVER_ERROR_NOT_READY);
+    }
+    if (!json_out)
+    {
+        g_last_error = "null argument";
+        return fail(KZP_PROVER_ERROR_INVALID_INPUT);
+    }
+    return prove_common(p, [&] { return p->prover->prove_resident(r32, s32); }, json_out, error_out, prover_time_ms);
+}
+
 int kzp_prover_prove(kzp_prover* p, const char* wtns_path, const uint8_t* r32, const uint8_t* s32,
                      char** json_out, int* error_out, int* prover_time_ms)
 {

@@ -182,15 +182,109 @@ static void artefacts_from_sums(const ShardPartials& sums, MsmArtefacts& art)
     put1(art.bytes + 320, H);
 }
 
-// sums_out (optional) receives the five summed MSM results (XYZZ) for the parity artefacts.
-static std::string assemble_with_terms(const HostVk& vk, const ShardPartials* ps, int count, const BlindTerms& bt,
-                                       ShardPartials* sums_out)
+// Proof assembly in two steps so that everything that does not need the H MSM result runs while the GPU is still
+// busy with it (the witness MSMs finish first): early = pi_a, pi_b and pi_c without its H term; final = + H.
+// pi_c = C + H + s*pi_a + r*pib1 - rs*delta1 (groth16.cpp:340-352) is a sum in an abelian group, so adding H last
+// gives the same affine point.
+struct EarlyProof
+{
+    HG1         A, B1, C;
+    HG2         B2;
+    HG1         pi_c_partial; // C + s*pi_a + r*pib1 - rs*delta1
+    std::string head;         // JSON up to and including "pi_c":[
+};
+
+static void assemble_early(const HostVk& vk, const BlindTerms& bt, const HG1& A, const HG1& B1, const HG1& C,
+                           const HG2& B2, EarlyProof& ep)
 {
     HG1Affine alpha1, beta1;
     HG2Affine beta2;
     memcpy(&alpha1, vk.alpha1, 64);
     memcpy(&beta1, vk.beta1, 64);
     memcpy(&beta2, vk.beta2, 128);
+    ep.A  = A;
+    ep.B1 = B1;
+    ep.C  = C;
+    ep.B2 = B2;
+    HG1 al, be1;
+    HG2 be2;
+    HG1::from_affine(al, alpha1);
+    HG1::from_affine(be1, beta1);
+    HG2::from_affine(be2, beta2);
+
+    // pi_a = A + alpha1 + r*delta1            (groth16.cpp:328-330)
+    HG1 pi_a = A;
+    HG1::add(pi_a, al);
+    HG1::add(pi_a, bt.r_delta1);
+    // pi_b = B2 + beta2 + s*delta2            (:332-334)
+    HG2 pi_b = B2;
+    HG2::add(pi_b, be2);
+    HG2::add(pi_b, bt.s_delta2);
+    // pib1 = B1 + beta1 + s*delta1            (:336-338)
+    HG1 pib1 = B1;
+    HG1::add(pib1, be1);
+    HG1::add(pib1, bt.s_delta1);
+    // pi_c - H = C + s*pi_a + r*pib1 - rs*delta1   (:340-352)
+    HG1 pc = C, p1;
+    scalar_mul(p1, pi_a, bt.s);
+    HG1::add(pc, p1);
+    scalar_mul(p1, pib1, bt.r);
+    HG1::add(pc, p1);
+    HG1 np1;
+    HG1::neg(np1, bt.rs_delta1);
+    HG1::add(pc, np1);
+    ep.pi_c_partial = pc;
+
+    HG1Affine a_aff;
+    HG2Affine b_aff;
+    HG1::to_affine(a_aff, pi_a);
+    HG2::to_affine(b_aff, pi_b);
+    // compact JSON, keys in sorted order, exactly what nlohmann::json::dump() prints for
+    // Proof::toJson (groth16.cpp:379-410, fullprover.cpp:246)
+    std::string& j = ep.head;
+    j.clear();
+    j.reserve(900);
+    j += "{\"pi_a\":[";
+    append_decimal(j, a_aff.x);
+    j += ',';
+    append_decimal(j, a_aff.y);
+    j += ",\"1\"],\"pi_b\":[[";
+    append_decimal(j, b_aff.x.a);
+    j += ',';
+    append_decimal(j, b_aff.x.b);
+    j += "],[";
+    append_decimal(j, b_aff.y.a);
+    j += ',';
+    append_decimal(j, b_aff.y.b);
+    j += "],[\"1\",\"0\"]],\"pi_c\":[";
+}
+
+// sums_out (optional) receives the five summed MSM results (XYZZ) for the parity artefacts.
+static std::string assemble_final(const EarlyProof& ep, const HG1& H, ShardPartials* sums_out)
+{
+    HG1 pi_c = ep.pi_c_partial;
+    HG1::add(pi_c, H);
+    if (sums_out)
+    {
+        memcpy(sums_out->bytes + 0, &ep.A, 128);
+        memcpy(sums_out->bytes + 128, &ep.B1, 128);
+        memcpy(sums_out->bytes + 256, &ep.C, 128);
+        memcpy(sums_out->bytes + 384, &H, 128);
+        memcpy(sums_out->bytes + 512, &ep.B2, 256);
+    }
+    HG1Affine c_aff;
+    HG1::to_affine(c_aff, pi_c);
+    std::string j = ep.head;
+    append_decimal(j, c_aff.x);
+    j += ',';
+    append_decimal(j, c_aff.y);
+    j += ",\"1\"],\"protocol\":\"groth16\"}";
+    return j;
+}
+
+static std::string assemble_with_terms(const HostVk& vk, const ShardPartials* ps, int count, const BlindTerms& bt,
+                                       ShardPartials* sums_out)
+{
     HG1 A, B1, C, H;
     HG2 B2;
     HG1::set_inf(A);
@@ -213,71 +307,9 @@ static std::string assemble_with_terms(const HostVk& vk, const ShardPartials* ps
         memcpy(&t2, ps[k].bytes + 512, 256);
         HG2::add(B2, t2);
     }
-    HG1 al, be1;
-    HG2 be2;
-    HG1::from_affine(al, alpha1);
-    HG1::from_affine(be1, beta1);
-    HG2::from_affine(be2, beta2);
-
-    // pi_a = A + alpha1 + r*delta1            (groth16.cpp:328-330)
-    HG1 pi_a = A;
-    HG1::add(pi_a, al);
-    HG1::add(pi_a, bt.r_delta1);
-    // pi_b = B2 + beta2 + s*delta2            (:332-334)
-    HG2 pi_b = B2;
-    HG2::add(pi_b, be2);
-    HG2::add(pi_b, bt.s_delta2);
-    // pib1 = B1 + beta1 + s*delta1            (:336-338)
-    HG1 pib1 = B1;
-    HG1::add(pib1, be1);
-    HG1::add(pib1, bt.s_delta1);
-    // pi_c = C + H + s*pi_a + r*pib1 - rs*delta1   (:340-352)
-    HG1 pi_c = C, p1;
-    HG1::add(pi_c, H);
-    scalar_mul(p1, pi_a, bt.s);
-    HG1::add(pi_c, p1);
-    scalar_mul(p1, pib1, bt.r);
-    HG1::add(pi_c, p1);
-    HG1 np1;
-    HG1::neg(np1, bt.rs_delta1);
-    HG1::add(pi_c, np1);
-
-    if (sums_out)
-    {
-        memcpy(sums_out->bytes + 0, &A, 128);
-        memcpy(sums_out->bytes + 128, &B1, 128);
-        memcpy(sums_out->bytes + 256, &C, 128);
-        memcpy(sums_out->bytes + 384, &H, 128);
-        memcpy(sums_out->bytes + 512, &B2, 256);
-    }
-    HG1Affine a_aff, c_aff;
-    HG2Affine b_aff;
-    HG1::to_affine(a_aff, pi_a);
-    HG2::to_affine(b_aff, pi_b);
-    HG1::to_affine(c_aff, pi_c);
-
-    // compact JSON, keys in sorted order, exactly what nlohmann::json::dump() prints for
-    // Proof::toJson (groth16.cpp:379-410, fullprover.cpp:246)
-    std::string j;
-    j.reserve(900);
-    j += "{\"pi_a\":[";
-    append_decimal(j, a_aff.x);
-    j += ',';
-    append_decimal(j, a_aff.y);
-    j += ",\"1\"],\"pi_b\":[[";
-    append_decimal(j, b_aff.x.a);
-    j += ',';
-    append_decimal(j, b_aff.x.b);
-    j += "],[";
-    append_decimal(j, b_aff.y.a);
-    j += ',';
-    append_decimal(j, b_aff.y.b);
-    j += "],[\"1\",\"0\"]],\"pi_c\":[";
-    append_decimal(j, c_aff.x);
-    j += ',';
-    append_decimal(j, c_aff.y);
-    j += ",\"1\"],\"protocol\":\"groth16\"}";
-    return j;
+    EarlyProof ep;
+    assemble_early(vk, bt, A, B1, C, B2, ep);
+    return assemble_final(ep, H, sums_out);
 }
 
 std::string assemble_proof(const HostVk& vk, const ShardPartials* ps, int count, const uint8_t* r32,
@@ -743,6 +775,16 @@ public:
         gpu_in_flight = true;
     }
 
+    // witness-side MSM results (A, B1, C, B2) are on the host after this; the H stream may still be running
+    void wait_witness_msms()
+    {
+        if (!gpu_in_flight)
+            throw FormatError("no proof in flight");
+        set_device();
+        KZP_CUDA_CHECK(cudaStreamSynchronize(st_w));
+        KZP_CUDA_CHECK(cudaStreamSynchronize(st_w2));
+    }
+
     void wait_gpu()
     {
         if (!gpu_in_flight)
@@ -787,7 +829,9 @@ public:
         return j;
     }
 
-    // upload + GPU + assembly with the r/s-only host work overlapped with the GPU
+    // upload + GPU + assembly. Host work is ordered by what it depends on: the r/s-only terms right after the
+    // launch, everything that needs A, B1, C, B2 (two 254-bit scalar multiplications, two affine conversions,
+    // six decimal strings) as soon as the witness streams are done, and only "+ H, to affine, print" after the H MSM.
     template <class Upload>
     std::string prove_with(Upload&& do_upload, const uint8_t* r32, const uint8_t* s32)
     {
@@ -796,9 +840,22 @@ public:
         launch_gpu();
         BlindTerms bt;
         compute_blind_terms(vk, r32, s32, bt);
+        wait_witness_msms();
+        EarlyProof ep;
+        {
+            HG1 A, B1, C;
+            HG2 B2;
+            memcpy(&A, pinned_out + 0, 128);
+            memcpy(&B1, pinned_out + 128, 128);
+            memcpy(&C, pinned_out + 256, 128);
+            memcpy(&B2, pinned_out + 512, 256);
+            assemble_early(vk, bt, A, B1, C, B2, ep);
+        }
         wait_gpu();
-        double      t1      = now_ms();
-        std::string j       = assemble_with_terms(vk, &parts, 1, bt, &sums);
+        double t1 = now_ms();
+        HG1    H;
+        memcpy(&H, parts.bytes + 384, 128);
+        std::string j       = assemble_final(ep, H, &sums);
         art_valid           = false;
         tm.assemble_host_ms = (float)(now_ms() - t1);
         tm.total_host_ms    = (float)(now_ms() - t0);
@@ -829,6 +886,10 @@ uint64_t DeviceProver::n_coefs() const { return impl_->n_coefs; }
 int      DeviceProver::device() const { return impl_->device; }
 void     DeviceProver::upload_witness(const uint8_t* values, uint64_t n) { impl_->upload(values, n); }
 void     DeviceProver::run_gpu() { impl_->run_gpu(); }
+std::string DeviceProver::prove_resident(const uint8_t* r32, const uint8_t* s32)
+{
+    return impl_->prove_with([] {}, r32, s32);
+}
 const ShardPartials& DeviceProver::partials() const { return impl_->parts; }
 std::string DeviceProver::assemble(const ShardPartials* parts, int count, const uint8_t* r32,
                                    const uint8_t* s32)

@@ -83,6 +83,10 @@ public:
     // groth16.cpp:296-316) and print the proof JSON (groth16.cpp:379-410 + nlohmann dump()).
     std::string assemble(const ShardPartials* parts, int count, const uint8_t* r32, const uint8_t* s32);
 
+    // one proof on the witness that is already resident (upload_witness*): GPU part + assembly, with the host work
+    // overlapped with the GPU exactly as in prove()/prove_fd()
+    std::string prove_resident(const uint8_t* r32, const uint8_t* s32);
+
     // convenience: upload + run + assemble for world == 1
     std::string prove(const uint8_t* values, uint64_t n, const uint8_t* r32, const uint8_t* s32);
     std::string prove_fd(int fd, uint64_t file_offset, uint64_t n, const uint8_t* r32, const uint8_t* s32);

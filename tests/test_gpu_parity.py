@@ -356,6 +356,10 @@ def test_proof_matches_golden(gpu, kzp, oracle, name, zkey, wtns):
         w = oracle.read_wtns(os.path.join(d, wtns))
         js, _ = p.prove_mem(b"".join(oracle.le32(v) for v in w), bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"]))
         assert js == exp["proof"]
+        # prove_resident: the witness uploaded by the previous call is still in HBM
+        js, _ = p.prove_resident(bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"]))
+        assert js == exp["proof"]
+        assert p.msm_results().hex() == exp["msm"]
         # fresh blinding: different bytes, still verifies under the circuit's VK (prover_handler.rs:329-336)
         js2, _ = p.prove(os.path.join(d, wtns))
         assert js2 != exp["proof"]
