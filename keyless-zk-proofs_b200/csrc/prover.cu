@@ -14,6 +14,9 @@
 #include <random>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "binfile.hpp"
 #include "device.hpp"
@@ -41,6 +44,30 @@ double now_ms()
     return std::chrono::duration<double, std::milli>(
                std::chrono::steady_clock::now().time_since_epoch())
         .count();
+}
+
+// Copy into the pinned staging buffer with non-temporal stores: the lines go to DRAM instead of staying dirty in the
+// writing core's cache, where the copy engine's reads would have to snoop them out (measured on the B200 host: a
+// freshly memcpy'd 43 MB pinned buffer DMAs at ~17 GB/s, a written-back one at 54 GB/s).
+void stream_copy(uint8_t* dst, const uint8_t* src, size_t len)
+{
+#if defined(__x86_64__)
+    if ((((uintptr_t)dst) & 15u) == 0)
+    {
+        size_t n16 = len / 16;
+        for (size_t i = 0; i < n16; i++)
+        {
+            __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + i);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + i, v);
+        }
+        _mm_sfence();
+        size_t done = n16 * 16;
+        if (done < len)
+            memcpy(dst + done, src + done, len - done);
+        return;
+    }
+#endif
+    memcpy(dst, src, len);
 }
 
 template <class XY>
@@ -568,7 +595,7 @@ public:
         KZP_CUDA_CHECK(cudaMallocHost(&pinned_out, sizeof(ShardPartials)));
         {
             const char* te = getenv("KZP_UPLOAD_THREADS");
-            int         nt = te ? atoi(te) : (int)std::min(12u, std::max(1u, std::thread::hardware_concurrency() * 3 / 4));
+            int         nt = te ? atoi(te) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
             pool.reset(new SlicePool(std::max(nt, 0)));
         }
 
@@ -633,12 +660,13 @@ public:
     // Host -> pinned staging -> device, pipelined: worker threads fill slices of the pinned buffer (memcpy from
     // memory, or pread() straight from the witness file: no page faults on a fresh mapping) while the calling
     // thread hands every finished slice to the copy engine.
-    //   KZP_UPLOAD_THREADS (default 8), KZP_UPLOAD_SLICE_KB (default 2048)
+    //   KZP_UPLOAD_THREADS (default min(8, cores/2)), KZP_UPLOAD_SLICE_KB (default 1024), KZP_UPLOAD_NT (default 1).
+    // Measured on the B200 host (16 cores), 43 MB witness: 2.9 ms with cached stores, 1.15-1.25 ms with streaming stores.
     template <class Fill>
     void upload_with(Fill&& fill)
     {
         set_device();
-        static const size_t slice = getenv("KZP_UPLOAD_SLICE_KB") ? (size_t)atoi(getenv("KZP_UPLOAD_SLICE_KB")) << 10 : (2u << 20);
+        static const size_t slice = getenv("KZP_UPLOAD_SLICE_KB") ? (size_t)atoi(getenv("KZP_UPLOAD_SLICE_KB")) << 10 : (1u << 20);
         const size_t total    = (size_t)n_vars * 32;
         const size_t n_slices = (total + slice - 1) / slice;
         std::vector<std::atomic<int>> ready(n_slices);
@@ -685,8 +713,12 @@ public:
     {
         if (n < n_vars)
             throw FormatError("witness has fewer values than the zkey has variables");
+        static const int nt = getenv("KZP_UPLOAD_NT") ? atoi(getenv("KZP_UPLOAD_NT")) : 1;
         upload_with([&](uint8_t* dst, size_t off, size_t len) {
-            memcpy(dst, values + off, len);
+            if (nt)
+                stream_copy(dst, values + off, len);
+            else
+                memcpy(dst, values + off, len);
             return true;
         });
     }
@@ -695,12 +727,20 @@ public:
     {
         if (n < n_vars)
             throw FormatError("witness has fewer values than the zkey has variables");
+        // KZP_UPLOAD_NT=1 (default): pread() into a cache-resident bounce buffer, then stream_copy() to the pinned
+        // buffer; 0: pread() straight into the pinned buffer (leaves the lines dirty in the reading core's cache)
+        static const int nt = getenv("KZP_UPLOAD_NT") ? atoi(getenv("KZP_UPLOAD_NT")) : 1;
         upload_with([&](uint8_t* dst, size_t off, size_t len) {
+            constexpr size_t            kBounce = 128u << 10;
+            static thread_local uint8_t bounce[kBounce] __attribute__((aligned(64)));
             while (len > 0)
             {
-                ssize_t got = ::pread(fd, dst, len, (off_t)(file_offset + off));
+                size_t  want = nt ? std::min(len, kBounce) : len;
+                ssize_t got  = ::pread(fd, nt ? bounce : dst, want, (off_t)(file_offset + off));
                 if (got <= 0)
                     return false;
+                if (nt)
+                    stream_copy(dst, bounce, (size_t)got);
                 dst += got;
                 off += (size_t)got;
                 len -= (size_t)got;
