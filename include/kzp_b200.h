@@ -106,6 +106,30 @@ int kzp_prover_keep_ab(kzp_prover* p, int on);
 int kzp_prover_get_ab(kzp_prover* p, uint8_t* out, uint64_t out_bytes);      /* 2 x domain x 32, Montgomery */
 int kzp_prover_get_msm_results(kzp_prover* p, uint8_t* out384);              /* A,B1,B2,C,H affine canonical */
 
+/* ---- (1b) prover pool: GPU-per-request scheduling --------------------------------
+ * The reference service owns ONE FullProver behind Arc<tokio::Mutex<Option<_>>> and proves on the async worker
+ * (prover-service/src/prover_state.rs:21,38-47,101; prover_handler.rs:266-283): proofs are serialised. A pool holds
+ * one resident prover per listed device (list a device twice for two provers on that GPU: one proof's witness
+ * staging and host assembly then overlap the other's kernels) and hands each request the least recently used free
+ * prover, FIFO. Every call is thread-safe and blocks until a prover is free; call it from spawn_blocking. */
+typedef struct kzp_pool kzp_pool;
+/* devices == NULL: $KZP_POOL_DEVICES ("0,1,2,...") or every visible device. Keys load concurrently. Always returns
+ * a handle; *state_out is KZP_STATE_OK only when every prover is ready. */
+kzp_pool* kzp_pool_new(const char* zkey_path, const int* devices, int n_devices, int* state_out);
+void      kzp_pool_free(kzp_pool* pool); /* waits for proofs in flight */
+int       kzp_pool_size(const kzp_pool* pool);
+int       kzp_pool_device(const kzp_pool* pool, int slot);
+/* kzp_prover_prove / kzp_prover_prove_mem on the next free prover; *slot_out (optional) says which one ran it */
+int kzp_pool_prove(kzp_pool* pool, const char* wtns_path, const uint8_t* r32, const uint8_t* s32, char** json_out,
+                   int* error_out, int* prover_time_ms, int* slot_out);
+int kzp_pool_prove_mem(kzp_pool* pool, const uint8_t* witness, uint64_t n, const uint8_t* r32, const uint8_t* s32,
+                       char** json_out, int* error_out, int* prover_time_ms, int* slot_out);
+/* proofs served per slot (returns the number of slots written) and the deepest queue seen */
+int kzp_pool_stats(kzp_pool* pool, uint64_t* proofs_per_slot, int cap, uint64_t* max_waiting);
+/* host-only exercise of the checkout queue (no GPU needed; used by the CPU test suite) */
+int kzp_pool_sched_selftest(int slots, int threads, int jobs_per_thread, int hold_us, uint64_t* per_slot_out,
+                            int* max_concurrent_per_slot, uint64_t* max_waiting);
+
 /* ---- (2) components ------------------------------------------------------------------------------ */
 /* FFT<Fr>::fft / ifft contract: n = 2^k Montgomery elements, natural order in and out, in place. */
 int kzp_fr_ntt(uint8_t* data, uint64_t n, int inverse, int device);

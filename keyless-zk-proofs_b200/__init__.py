@@ -116,6 +116,15 @@ def lib() -> ctypes.CDLL:
         "kzp_prover_keep_ab": (c.c_int, [vp, c.c_int]),
         "kzp_prover_get_ab": (c.c_int, [vp, u8p, c.c_uint64]),
         "kzp_prover_get_msm_results": (c.c_int, [vp, u8p]),
+        "kzp_pool_new": (vp, [c.c_char_p, c.POINTER(c.c_int), c.c_int, i32p]),
+        "kzp_pool_free": (None, [vp]),
+        "kzp_pool_size": (c.c_int, [vp]),
+        "kzp_pool_device": (c.c_int, [vp, c.c_int]),
+        "kzp_pool_prove": (c.c_int, [vp, c.c_char_p, u8p, u8p, c.POINTER(vp), i32p, i32p, i32p]),
+        "kzp_pool_prove_mem": (c.c_int, [vp, u8p, c.c_uint64, u8p, u8p, c.POINTER(vp), i32p, i32p, i32p]),
+        "kzp_pool_stats": (c.c_int, [vp, c.POINTER(c.c_uint64), c.c_int, c.POINTER(c.c_uint64)]),
+        "kzp_pool_sched_selftest": (c.c_int, [c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_uint64), i32p,
+                                              c.POINTER(c.c_uint64)]),
         "kzp_fr_ntt": (c.c_int, [u8p, c.c_uint64, c.c_int, c.c_int]),
         "kzp_fr_coset_chain": (c.c_int, [u8p, c.c_uint64, c.c_int]),
         "kzp_fr_ntt_bench": (c.c_int, [c.c_uint32, c.c_int, c.c_int, c.POINTER(c.c_float)]),
@@ -296,6 +305,78 @@ class FullProver:
         buf = ctypes.create_string_buffer(384)
         _check(lib().kzp_prover_get_msm_results(self._h, buf))
         return buf.raw
+
+
+class ProverPool:
+    """GPU-per-request prover pool (include/kzp_b200.h §1b): the replacement for prover-service's single
+    Arc<Mutex<Option<FullProver>>> (prover-service/src/prover_state.rs:21,38-47). ``prove`` may be called from any
+    number of threads; each call blocks until a prover is free (ctypes releases the GIL during the call)."""
+
+    def __init__(self, zkey_path: str, devices: Optional[Sequence[int]] = None):
+        state = ctypes.c_int(-1)
+        if devices is None:
+            arr, n = None, 0
+        else:
+            arr, n = (ctypes.c_int * len(devices))(*devices), len(devices)
+        self._h = lib().kzp_pool_new(os.fsencode(zkey_path), arr, n, ctypes.byref(state))
+        if not self._h:
+            raise MemoryError("kzp_pool_new returned NULL")
+        if state.value != 0:
+            why = last_error()
+            lib().kzp_pool_free(self._h)
+            self._h = None
+            if state.value == 2:
+                raise UnsupportedZKeyCurve(why)
+            raise ZKeyFileLoadError(why)
+        self.size = lib().kzp_pool_size(self._h)
+        self.devices = [lib().kzp_pool_device(self._h, i) for i in range(self.size)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().kzp_pool_free(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _finish(self, rc, out, err, ms, slot):
+        if rc != 0:
+            FullProver._raise_prover_error(err.value)
+        return _take_string(out), {"prover_time": ms.value, "slot": slot.value}
+
+    def prove(self, wtns_path: str, r: Optional[bytes] = None, s: Optional[bytes] = None):
+        out, err, ms, slot = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        rc = lib().kzp_pool_prove(self._h, os.fsencode(wtns_path), r, s, ctypes.byref(out), ctypes.byref(err),
+                                  ctypes.byref(ms), ctypes.byref(slot))
+        return self._finish(rc, out, err, ms, slot)
+
+    def prove_mem(self, witness: bytes, r: Optional[bytes] = None, s: Optional[bytes] = None):
+        out, err, ms, slot = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        rc = lib().kzp_pool_prove_mem(self._h, witness, len(witness) // 32, r, s, ctypes.byref(out),
+                                      ctypes.byref(err), ctypes.byref(ms), ctypes.byref(slot))
+        return self._finish(rc, out, err, ms, slot)
+
+    def stats(self):
+        arr, mw = (ctypes.c_uint64 * max(1, self.size))(), ctypes.c_uint64()
+        n = lib().kzp_pool_stats(self._h, arr, self.size, ctypes.byref(mw))
+        return {"proofs_per_slot": list(arr[:n]), "max_waiting": mw.value}
+
+
+def pool_sched_selftest(slots: int, threads: int, jobs_per_thread: int, hold_us: int = 200):
+    """Host-only run of the pool's checkout queue: (jobs per slot, max simultaneous holders of one slot, deepest queue)."""
+    arr, worst, mw = (ctypes.c_uint64 * slots)(), ctypes.c_int(), ctypes.c_uint64()
+    _check(lib().kzp_pool_sched_selftest(slots, threads, jobs_per_thread, hold_us, arr, ctypes.byref(worst),
+                                         ctypes.byref(mw)))
+    return list(arr), worst.value, mw.value
 
 
 # ---- component wrappers ------------------------------------------------------------------------------------

@@ -1,0 +1,211 @@
+// kzp_pool_*: a set of resident provers with GPU-per-request checkout (include/kzp_b200.h, pool.hpp).
+// Replaces, on the service side, the single mutex-guarded FullProver of prover-service/src/prover_state.rs:21-47;
+// INTEGRATION.md shows the Rust patch that binds it.
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/kzp_b200.h"
+#include "pool.hpp"
+
+using namespace kzp;
+
+struct kzp_pool
+{
+    std::vector<kzp_prover*> provers;
+    std::vector<int>         devices;
+    SlotScheduler*           sched = nullptr;
+    int                      state = KZP_STATE_OK;
+};
+
+static std::vector<int> pool_devices(const int* devices, int n)
+{
+    std::vector<int> out;
+    if (devices && n > 0)
+    {
+        out.assign(devices, devices + n);
+        return out;
+    }
+    // $KZP_POOL_DEVICES = "0,1,2,3" (a device may be listed more than once: several provers on one GPU)
+    if (const char* env = getenv("KZP_POOL_DEVICES"))
+    {
+        const char* p = env;
+        while (*p)
+        {
+            char* end = nullptr;
+            long  v   = strtol(p, &end, 10);
+            if (end == p)
+                break;
+            out.push_back((int)v);
+            p = (*end == ',') ? end + 1 : end;
+        }
+        if (!out.empty())
+            return out;
+    }
+    int cnt = kzp_device_count();
+    for (int i = 0; i < cnt; i++)
+        out.push_back(i);
+    return out;
+}
+
+kzp_pool* kzp_pool_new(const char* zkey_path, const int* devices, int n_devices, int* state_out)
+{
+    kzp_pool* pool = new (std::nothrow) kzp_pool();
+    if (!pool)
+        return nullptr;
+    try
+    {
+        pool->devices = pool_devices(devices, n_devices);
+        size_t n      = pool->devices.size();
+        pool->provers.assign(n, nullptr);
+        std::vector<int>         states(n, KZP_STATE_ZKEY_FILE_LOAD_ERROR);
+        std::vector<std::thread> th;
+        // keys are parsed and uploaded concurrently, one loader thread per prover
+        for (size_t i = 0; i < n; i++)
+            th.emplace_back([&, i] { pool->provers[i] = kzp_prover_new(zkey_path, pool->devices[i], &states[i]); });
+        for (auto& t : th)
+            t.join();
+        pool->state = n == 0 ? KZP_STATE_ZKEY_FILE_LOAD_ERROR : KZP_STATE_OK;
+        for (size_t i = 0; i < n; i++)
+            if (!pool->provers[i] || states[i] != KZP_STATE_OK)
+                pool->state = pool->provers[i] ? states[i] : KZP_STATE_ZKEY_FILE_LOAD_ERROR;
+        pool->sched = new SlotScheduler((int)n);
+    }
+    catch (...)
+    {
+        pool->state = KZP_STATE_ZKEY_FILE_LOAD_ERROR;
+    }
+    if (state_out)
+        *state_out = pool->state;
+    return pool;
+}
+
+void kzp_pool_free(kzp_pool* pool)
+{
+    if (!pool)
+        return;
+    if (pool->sched)
+    {
+        pool->sched->close();
+        // proofs in flight hold their slot until they return; wait for them before tearing the provers down
+        while (pool->sched->busy() > 0)
+            std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    }
+    for (kzp_prover* p : pool->provers)
+        kzp_prover_free(p);
+    delete pool->sched;
+    delete pool;
+}
+
+int kzp_pool_size(const kzp_pool* pool) { return pool ? (int)pool->provers.size() : 0; }
+
+int kzp_pool_device(const kzp_pool* pool, int slot)
+{
+    if (!pool || slot < 0 || slot >= (int)pool->devices.size())
+        return -1;
+    return pool->devices[slot];
+}
+
+template <class Run>
+static int pool_run(kzp_pool* pool, char** json_out, int* error_out, int* prover_time_ms, int* slot_out, Run&& run)
+{
+    if (json_out)
+        *json_out = nullptr;
+    if (prover_time_ms)
+        *prover_time_ms = 0;
+    if (slot_out)
+        *slot_out = -1;
+    if (!pool || pool->state != KZP_STATE_OK || !pool->sched)
+    {
+        if (error_out)
+            *error_out = KZP_PROVER_ERROR_NOT_READY;
+        return KZP_RESPONSE_ERROR;
+    }
+    int slot = pool->sched->acquire();
+    if (slot < 0)
+    {
+        if (error_out)
+            *error_out = KZP_PROVER_ERROR_NOT_READY;
+        return KZP_RESPONSE_ERROR;
+    }
+    if (slot_out)
+        *slot_out = slot;
+    int rc = run(pool->provers[slot]);
+    pool->sched->release(slot);
+    return rc;
+}
+
+int kzp_pool_prove(kzp_pool* pool, const char* wtns_path, const uint8_t* r32, const uint8_t* s32, char** json_out,
+                   int* error_out, int* prover_time_ms, int* slot_out)
+{
+    return pool_run(pool, json_out, error_out, prover_time_ms, slot_out, [&](kzp_prover* p) {
+        return kzp_prover_prove(p, wtns_path, r32, s32, json_out, error_out, prover_time_ms);
+    });
+}
+
+int kzp_pool_prove_mem(kzp_pool* pool, const uint8_t* witness, uint64_t n, const uint8_t* r32, const uint8_t* s32,
+                       char** json_out, int* error_out, int* prover_time_ms, int* slot_out)
+{
+    return pool_run(pool, json_out, error_out, prover_time_ms, slot_out, [&](kzp_prover* p) {
+        return kzp_prover_prove_mem(p, witness, n, r32, s32, json_out, error_out, prover_time_ms);
+    });
+}
+
+int kzp_pool_stats(kzp_pool* pool, uint64_t* proofs_per_slot, int cap, uint64_t* max_waiting)
+{
+    if (!pool || !pool->sched)
+        return 0;
+    int n = pool->sched->slots();
+    for (int i = 0; i < n && i < cap; i++)
+        proofs_per_slot[i] = pool->sched->jobs(i);
+    if (max_waiting)
+        *max_waiting = pool->sched->max_waiting();
+    return n < cap ? n : cap;
+}
+
+// Host-only exercise of the scheduler (no GPU): `threads` callers each run `jobs_per_thread` jobs that hold a slot
+// for hold_us microseconds. Reports per-slot job counts, the largest number of simultaneous holders seen on any one
+// slot (must be 1) and the deepest queue (callers waiting or being served) seen.
+int kzp_pool_sched_selftest(int slots, int threads, int jobs_per_thread, int hold_us, uint64_t* per_slot_out,
+                            int* max_concurrent_per_slot, uint64_t* max_waiting)
+{
+    if (slots <= 0 || threads <= 0 || jobs_per_thread < 0 || !per_slot_out)
+        return KZP_ERR_FORMAT;
+    SlotScheduler                 sched(slots);
+    std::vector<std::atomic<int>> holders(slots);
+    for (auto& h : holders)
+        h = 0;
+    std::atomic<int>         worst(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++)
+        th.emplace_back([&] {
+            for (int j = 0; j < jobs_per_thread; j++)
+            {
+                int slot = sched.acquire();
+                if (slot < 0)
+                    return;
+                int now = ++holders[slot];
+                int w   = worst.load();
+                while (now > w && !worst.compare_exchange_weak(w, now))
+                {
+                }
+                if (hold_us > 0)
+                    std::this_thread::sleep_for(std::chrono::microseconds(hold_us));
+                --holders[slot];
+                sched.release(slot);
+            }
+        });
+    for (auto& t : th)
+        t.join();
+    for (int i = 0; i < slots; i++)
+        per_slot_out[i] = sched.jobs(i);
+    if (max_concurrent_per_slot)
+        *max_concurrent_per_slot = worst.load();
+    if (max_waiting)
+        *max_waiting = sched.max_waiting();
+    return KZP_OK;
+}

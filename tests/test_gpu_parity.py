@@ -501,3 +501,74 @@ def test_keyless_shape_full_size(gpu, kzp, oracle, ref, port, workdir):
                              oracle.g2_from_zkey_bytes(hdr[340:468]), oracle.g2_from_zkey_bytes(hdr[532:660]),
                              [oracle.g1_from_zkey_bytes(sec[3][0][i * 64:(i + 1) * 64]) for i in range(2)])
     assert oracle.groth16_verify(vk, [info["public_input"]], pa, pb, pc)
+
+
+# ---------------------------------------------------------------- prover pool
+def test_pool_concurrent_proofs_match_golden(gpu, kzp, oracle):
+    """Two provers on one GPU behind the checkout queue, eight client threads: every proof equals the reference's
+    recorded bytes (fixed r, s), every prover served work, and the fresh-randomness path verifies."""
+    import threading
+
+    d = os.path.join(GOLDEN, "syn256")
+    exp = json.load(open(os.path.join(d, "expected.json")))
+    r, s = bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"])
+    wt = os.path.join(d, "syn256.wtns")
+    w = b"".join(oracle.le32(v) for v in oracle.read_wtns(wt))
+    with kzp.ProverPool(os.path.join(d, "syn256.zkey"), devices=[0, 0]) as pool:
+        assert pool.size == 2 and pool.devices == [0, 0]
+        bad, slots = [], []
+
+        def client(i):
+            for j in range(6):
+                js, m = pool.prove(wt, r, s) if (i + j) % 2 else pool.prove_mem(w, r, s)
+                slots.append(m["slot"])
+                if js != exp["proof"]:
+                    bad.append((i, j))
+
+        th = [threading.Thread(target=client, args=(i,)) for i in range(8)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not bad
+        st = pool.stats()
+        assert sum(st["proofs_per_slot"]) == 48 and min(st["proofs_per_slot"]) > 0 and set(slots) == {0, 1}
+        js, _ = pool.prove(wt)
+        zk = oracle.read_zkey(os.path.join(d, "syn256.zkey"))
+        assert oracle.groth16_verify(oracle.vk_from_zkey(zk), exp["public"], *oracle.proof_from_json(js))
+        with pytest.raises(kzp.InvalidInput):
+            pool.prove(os.path.join(d, "missing.wtns"))
+
+
+# ---------------------------------------------------------------- full-size MSM against a closed form
+@pytest.mark.slow
+@pytest.mark.parametrize("group,log_n", [(0, 22), (1, 20)])
+def test_msm_large_closed_form(gpu, kzp, group, log_n):
+    """BASELINE configs[4] sizes: bases P_i = (s0+i)G, so sum k_i P_i = (sum k_i (s0+i) mod r) G — one fixed-base
+    multiplication on the host (tools/setupgen.c, itself pinned to the oracle in test_oracle_golden) checks a
+    multi-million-point MSM bit for bit, for uniform scalars and for scalars with every digit at the signed-window
+    edges (0x7fff / 0x8000 / 0xffff patterns that exercise the carry chain)."""
+    import ctypes
+
+    import numpy as np
+
+    import bench
+
+    gen = bench.ensure_setupgen()
+    gen.kzp_gen_consecutive_points.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p]
+    gen.kzp_msm_closed_form.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_char_p]
+    n, psz = 1 << log_n, 64 if group == 0 else 128
+    s0 = ((0xABCDEF << 100) + 17).to_bytes(32, "little")
+    bases = ctypes.create_string_buffer(n * psz)
+    assert gen.kzp_gen_consecutive_points(group, n, s0, bases) == 0
+    m = kzp.Msm(group, bases)
+    rng = np.random.default_rng(9)
+    uni = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    uni[:, 3] = rng.integers(0, 0x30644E72E131A029, size=n, dtype=np.uint64)
+    edge = np.empty((n, 4), dtype=np.uint64)
+    pats = np.array([0x7FFF7FFF7FFF7FFF, 0x8000800080008000, 0xFFFFFFFFFFFFFFFF, 0x00007FFF80008001], dtype=np.uint64)
+    edge[:, :3] = pats[rng.integers(0, 4, size=(n, 3))]
+    edge[:, 3] = pats[rng.integers(0, 4, size=n)] & np.uint64(0x0FFFFFFFFFFFFFFF)
+    for sc in (uni, edge):
+        want = ctypes.create_string_buffer(psz)
+        assert gen.kzp_msm_closed_form(group, n, s0, sc.ctypes.data, want) == 0
+        assert m.run(sc.tobytes()) == want.raw
+    m.close()

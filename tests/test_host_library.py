@@ -227,3 +227,24 @@ int main(int argc, char** argv) {
     out = subprocess.check_output([exe, "/nonexistent/k.zkey"], text=True).split()
     # state ZKEY_FILE_LOAD_ERROR(1), response ERROR(1), error PROVER_NOT_READY(1)
     assert out[:3] == ["1", "1", "1"]
+
+
+def test_pool_checkout_queue(kzp):
+    """The prover pool's checkout (csrc/pool.hpp, host-only): a slot never has two holders, every job is served,
+    work spreads over the slots, and callers beyond the slot count queue up."""
+    per_slot, worst, deepest = kzp.pool_sched_selftest(4, 16, 40, 100)
+    assert worst == 1
+    assert sum(per_slot) == 16 * 40
+    assert min(per_slot) >= 0.8 * (16 * 40 / 4)  # least-recently-released first: even spread
+    assert 4 < deepest <= 16
+    per_slot, worst, _ = kzp.pool_sched_selftest(1, 8, 25, 20)
+    assert per_slot == [200] and worst == 1
+
+
+def test_pool_without_gpu_reports_load_error(kzp):
+    if kzp.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    with pytest.raises(kzp.ZKeyFileLoadError):
+        kzp.ProverPool(os.path.join(GOLDEN, "toy", "toy_1.zkey"))
+    with pytest.raises(kzp.ZKeyFileLoadError):
+        kzp.ProverPool(os.path.join(GOLDEN, "toy", "toy_1.zkey"), devices=[0, 0])

@@ -215,3 +215,29 @@ def test_port_matches_reference_medium(oracle, port, ref, workdir):
     zk = oracle.read_zkey(z)
     pa, pb, pc = oracle.proof_from_json(rj)
     assert oracle.groth16_verify(oracle.vk_from_zkey(zk), [info["public_input"]], pa, pb, pc)
+
+
+def test_microbench_generator_matches_oracle(oracle):
+    """tools/setupgen.c's micro-benchmark inputs (bases (s0+i)G and the closed-form MSM answer) against the
+    Python oracle's scalar multiplication — this is what pins the full-size MSM checks of the GPU suite."""
+    import ctypes
+
+    import bench
+
+    lib = bench.ensure_setupgen()
+    lib.kzp_gen_consecutive_points.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p]
+    lib.kzp_msm_closed_form.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
+    o, rnd = oracle, random.Random(3)
+    cases = [(0, o.G1_GEN, o.g1_mul, o.g1_to_zkey_bytes, o.g1_to_canonical_bytes, 64),
+             (1, o.G2_GEN, o.g2_mul, o.g2_to_zkey_bytes, o.g2_to_canonical_bytes, 128)]
+    for group, gen, mul, to_zkey, to_canon, sz in cases:
+        n, s0 = 4200, rnd.randrange(1 << 250)
+        out = ctypes.create_string_buffer(n * sz)
+        assert lib.kzp_gen_consecutive_points(group, n, o.le32(s0), out) == 0
+        for i in (0, 1, 4095, 4096, 4097, n - 1):  # 4096 = the generator's block size
+            assert out.raw[i * sz:(i + 1) * sz] == to_zkey(mul(gen, s0 + i)), (group, i)
+        ks = [rnd.randrange(o.R_MOD) for _ in range(n)]
+        res = ctypes.create_string_buffer(sz)
+        assert lib.kzp_msm_closed_form(group, n, o.le32(s0), b"".join(o.le32(k) for k in ks), res) == 0
+        tot = sum(k * (s0 + i) for i, k in enumerate(ks)) % o.R_MOD
+        assert res.raw == to_canon(mul(gen, tot)), group

@@ -835,3 +835,97 @@ int kzp_setupgen(uint32_t n_constraints, uint32_t n_vars, uint64_t seed, const c
     return 0;
 }
 
+
+/* ------------------------------------------------------------------ micro-benchmark inputs
+ * Bases P_i = (s0 + i) * G for i < n ("k*G distinct"), written in zkey byte layout (affine Montgomery), and the
+ * closed-form answer of an MSM over them: sum_i k_i P_i = (sum_i k_i (s0 + i) mod r) * G, which pins a 2^24-point MSM
+ * with ONE fixed-base multiplication instead of a CPU MSM. */
+static fb1_t* g_fb1 = NULL;
+static fb2_t* g_fb2 = NULL;
+static void   fb_tables(int group)
+{
+#pragma omp critical(kzp_fb_tables)
+    {
+        if (group == 0 && !g_fb1) g_fb1 = fb1_new();
+        if (group == 1 && !g_fb2) g_fb2 = fb2_new();
+    }
+}
+
+/* group 0 = G1 (64 B/point), 1 = G2 (128 B/point); s0: canonical 32-byte scalar, s0 + n < r assumed */
+int kzp_gen_consecutive_points(int group, uint64_t n, const uint8_t* s0_32, uint8_t* out)
+{
+    if (group < 0 || group > 1) return -1;
+    fb_tables(group);
+    const size_t blk = 4096;
+    fe s0; memcpy(&s0, s0_32, 32);
+#pragma omp parallel
+    {
+        void* tmp = malloc((group == 0 ? sizeof(g1_pt) : sizeof(g2_pt)) * blk);
+#pragma omp for schedule(dynamic, 1)
+        for (size_t b0 = 0; b0 < n; b0 += blk)
+        {
+            size_t cnt = n - b0 < blk ? n - b0 : blk;
+            fe k = s0; /* k = s0 + b0 (plain integers, no reduction needed below r) */
+            unsigned __int128 c = (unsigned __int128)k.v[0] + b0; k.v[0] = (uint64_t)c; c >>= 64;
+            for (int j = 1; j < 4; j++) { c += k.v[j]; k.v[j] = (uint64_t)c; c >>= 64; }
+            if (group == 0)
+            {
+                g1_pt* t = (g1_pt*)tmp; g1_aff g; g1_gen(&g);
+                fb1_mul(g_fb1, &t[0], &k);
+                for (size_t i = 1; i < cnt; i++) { t[i] = t[i - 1]; g1_madd(&t[i], &g); }
+                g1_batch_to_aff((g1_aff*)(out + b0 * 64), t, cnt);
+            }
+            else
+            {
+                g2_pt* t = (g2_pt*)tmp; g2_aff g; g2_gen(&g);
+                fb2_mul(g_fb2, &t[0], &k);
+                for (size_t i = 1; i < cnt; i++) { t[i] = t[i - 1]; g2_madd(&t[i], &g); }
+                g2_batch_to_aff((g2_aff*)(out + b0 * 128), t, cnt);
+            }
+        }
+        free(tmp);
+    }
+    return 0;
+}
+
+/* out: affine CANONICAL coordinates (64 / 128 bytes, zeros for infinity) of (sum_i k_i (s0 + i) mod r) * G;
+ * scalars: n x 32-byte canonical integers < r */
+int kzp_msm_closed_form(int group, uint64_t n, const uint8_t* s0_32, const uint8_t* scalars, uint8_t* out)
+{
+    if (group < 0 || group > 1) return -1;
+    fb_tables(group);
+    fe s0m; { fe s0; memcpy(&s0, s0_32, 32); f_to_mont(&s0m, &s0, &FR); }
+    int nt = omp_get_max_threads();
+    fe* part = (fe*)calloc((size_t)nt, sizeof(fe));
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < nt; b++)
+    {
+        size_t lo = n * (size_t)b / nt, hi = n * (size_t)(b + 1) / nt;
+        fe acc = {{0, 0, 0, 0}}, idx, one = FR.one;
+        f_from_u64(&idx, lo, &FR); fr_add(&idx, &idx, &s0m);
+        for (size_t i = lo; i < hi; i++)
+        {
+            fe k, km, t; memcpy(&k, scalars + i * 32, 32);
+            f_to_mont(&km, &k, &FR); fr_mul(&t, &km, &idx); fr_add(&acc, &acc, &t); fr_add(&idx, &idx, &one);
+        }
+        part[b] = acc;
+    }
+    fe tot = {{0, 0, 0, 0}};
+    for (int b = 0; b < nt; b++) fr_add(&tot, &tot, &part[b]);
+    free(part);
+    fe k; f_from_mont(&k, &tot, &FR);
+    if (group == 0)
+    {
+        g1_pt p; g1_aff a; fb1_mul(g_fb1, &p, &k); g1_to_aff(&a, &p);
+        fe x, y; f_from_mont(&x, &a.x, &FQ); f_from_mont(&y, &a.y, &FQ);
+        memcpy(out, &x, 32); memcpy(out + 32, &y, 32);
+    }
+    else
+    {
+        g2_pt p; g2_aff a; fb2_mul(g_fb2, &p, &k); g2_to_aff(&a, &p);
+        fe c[4]; f_from_mont(&c[0], &a.x.a, &FQ); f_from_mont(&c[1], &a.x.b, &FQ);
+        f_from_mont(&c[2], &a.y.a, &FQ); f_from_mont(&c[3], &a.y.b, &FQ);
+        memcpy(out, c, 128);
+    }
+    return 0;
+}
