@@ -245,6 +245,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

@@ -14,6 +14,7 @@ from typing import Optional, Sequence, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkzp_b200.so")
+CLI_PATH = os.path.join(_HERE, "kzp_prove")  # csrc/cli_main.cpp: zkey + wtns -> proof.json + public.json
 
 PARTIALS_BYTES = 768
 

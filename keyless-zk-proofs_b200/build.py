@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libkzp_b200.so")
+CLI = os.path.join(HERE, "kzp_prove")  # command-line prover over the C ABI (csrc/cli_main.cpp)
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["kernels.cu", "msm_sort.cu", "msm_g1.cu", "msm_g2.cu", "prover.cu", "capi.cu", "pool.cu", "fullprover_abi.cu"]
@@ -44,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     stamp = os.path.join(BUILD, "stamp.sha256")
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+    if not force and os.path.exists(LIB) and os.path.exists(CLI) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
     if not os.path.exists(NVCC):
         if os.path.exists(LIB):
@@ -68,6 +69,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", os.path.join(CSRC, "cli_main.cpp"), "-o", CLI,
+           "-L", HERE, "-lkzp_b200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("CLI build failed:\n%s\n%s" % (r.stdout, r.stderr))
     with open(stamp, "w") as f:
         f.write(digest)
     return LIB

@@ -248,3 +248,20 @@ def test_pool_without_gpu_reports_load_error(kzp):
         kzp.ProverPool(os.path.join(GOLDEN, "toy", "toy_1.zkey"))
     with pytest.raises(kzp.ZKeyFileLoadError):
         kzp.ProverPool(os.path.join(GOLDEN, "toy", "toy_1.zkey"), devices=[0, 0])
+
+
+def test_cli_exit_codes_without_proving(kzp, workdir):
+    """kzp_prove (csrc/cli_main.cpp): usage and unusable-zkey paths need no GPU; without a device the prover refuses
+    to run (exit 2) instead of falling back to anything."""
+    assert os.path.exists(kzp.CLI_PATH), "run keyless-zk-proofs_b200/build.py"
+    r = subprocess.run([kzp.CLI_PATH], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage" in r.stderr
+    out = [os.path.join(workdir, "cli_proof.json"), os.path.join(workdir, "cli_public.json")]
+    r = subprocess.run([kzp.CLI_PATH, os.path.join(workdir, "nope.zkey"), "x.wtns"] + out, capture_output=True, text=True)
+    assert r.returncode == 2 and "zkey not usable" in r.stderr
+    if kzp.device_count() == 0:
+        toy = os.path.join(GOLDEN, "toy")
+        r = subprocess.run([kzp.CLI_PATH, os.path.join(toy, "toy_1.zkey"), os.path.join(toy, "toy.wtns")] + out,
+                           capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
+        assert not os.path.exists(out[0])
