@@ -164,6 +164,16 @@ int kzp_host_parse_zkey(const char* path, uint32_t* n_vars, uint32_t* n_public, 
  * this is the step rank 0 performs after the all-gather in sharded mode). msm_out384 may be NULL. */
 int kzp_host_assemble(const char* zkey_path, const uint8_t* partials, int count, const uint8_t* r32,
                       const uint8_t* s32, char** json_out, uint8_t* msm_out384);
+/* Host-only pairing product check: *result_out = 1 iff prod_i e(P_i, Q_i) == 1. g1: n x 64-byte
+ * affine Montgomery points (zkey layout, zeros = infinity), g2: n x 128 bytes. Points off the curve -> KZP_ERR_FORMAT. */
+int kzp_host_pairing_check(const uint8_t* g1, const uint8_t* g2, int n, int* result_out);
+/* Groth16 verification of a proof JSON (the string the prove calls return) under the verifying key stored in the
+ * zkey (section 2 + IC section 3) — what prover-service does after every proof through ark-groth16
+ * (prover-service/src/request_handler/prover_handler.rs:329-336). public32: n_public x 32-byte LE canonical signals.
+ * Returns 0 and *valid_out = 1 / 0; non-zero for malformed inputs (kzp_verify_last_error()). No GPU involved. */
+int kzp_host_verify(const char* zkey_path, const char* proof_json, const uint8_t* public32, uint32_t n_public,
+                    int* valid_out);
+const char* kzp_verify_last_error(void);
 int kzp_host_fq_decimal(const uint8_t* mont32, char* out, size_t cap);
 int kzp_host_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out);
 

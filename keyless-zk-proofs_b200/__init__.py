@@ -139,6 +139,9 @@ def lib() -> ctypes.CDLL:
         "kzp_host_parse_zkey": (c.c_int, [c.c_char_p, c.POINTER(c.c_uint32), c.POINTER(c.c_uint32),
                                           c.POINTER(c.c_uint32), c.POINTER(c.c_uint64), i32p]),
         "kzp_host_assemble": (c.c_int, [c.c_char_p, u8p, c.c_int, u8p, u8p, c.POINTER(vp), u8p]),
+        "kzp_host_pairing_check": (c.c_int, [u8p, u8p, c.c_int, i32p]),
+        "kzp_host_verify": (c.c_int, [c.c_char_p, c.c_char_p, u8p, c.c_uint32, i32p]),
+        "kzp_verify_last_error": (c.c_char_p, []),
         "kzp_host_fq_decimal": (c.c_int, [u8p, c.c_char_p, c.c_size_t]),
         "kzp_host_field_op": (c.c_int, [c.c_int, c.c_int, u8p, u8p, u8p]),
     }
@@ -456,6 +459,26 @@ def host_assemble(zkey_path: str, partials: Sequence[bytes], r: Optional[bytes] 
     _check(lib().kzp_host_assemble(os.fsencode(zkey_path), b"".join(partials), len(partials), r, s,
                                    ctypes.byref(out), art))
     return _take_string(out), art.raw
+
+
+def host_pairing_check(g1: bytes, g2: bytes) -> bool:
+    """prod_i e(P_i, Q_i) == 1 on the host (csrc/pairing.hpp); points in zkey byte layout."""
+    res = ctypes.c_int()
+    rc = lib().kzp_host_pairing_check(g1, g2, len(g1) // 64, ctypes.byref(res))
+    if rc != 0:
+        raise KzpError("kzp_host_pairing_check: " + lib().kzp_verify_last_error().decode())
+    return bool(res.value)
+
+
+def host_verify(zkey_path: str, proof_json: str, public: Sequence[int]) -> bool:
+    """Groth16 verification under the VK inside the zkey — the check prover-service performs after every proof
+    (prover_handler.rs:329-336), done natively on the host next to the prover."""
+    res = ctypes.c_int()
+    pub = b"".join(int(v).to_bytes(32, "little") for v in public)
+    rc = lib().kzp_host_verify(os.fsencode(zkey_path), proof_json.encode(), pub, len(public), ctypes.byref(res))
+    if rc != 0:
+        raise KzpError("kzp_host_verify: " + lib().kzp_verify_last_error().decode())
+    return bool(res.value)
 
 
 def imad_peak(iters: int = 4096, device: int = -1):

@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libkzp_b200.so")
 CLI = os.path.join(HERE, "kzp_prove")  # command-line prover over the C ABI (csrc/cli_main.cpp)
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["kernels.cu", "msm_sort.cu", "msm_g1.cu", "msm_g2.cu", "prover.cu", "capi.cu", "pool.cu", "fullprover_abi.cu"]
+SOURCES = ["kernels.cu", "msm_sort.cu", "msm_g1.cu", "msm_g2.cu", "prover.cu", "capi.cu", "pool.cu", "verify.cu", "fullprover_abi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -265,3 +265,56 @@ def test_cli_exit_codes_without_proving(kzp, workdir):
                            capture_output=True, text=True)
         assert r.returncode == 2 and "no CPU fallback" in r.stderr
         assert not os.path.exists(out[0])
+
+
+# ---------------------------------------------------------------- native verifier (csrc/pairing.hpp, host only)
+def test_pairing_check_bilinearity(kzp, oracle):
+    """prod e(P_i, Q_i) == 1 on the host: bilinear in both arguments, non-degenerate, infinity-neutral; inputs off the
+    curve are refused. Points come from the Python oracle's scalar multiplication."""
+    o, rnd = oracle, random.Random(21)
+    g1, g2 = o.g1_to_zkey_bytes, o.g2_to_zkey_bytes
+    G1, G2 = o.G1_GEN, o.G2_GEN
+    for _ in range(2):
+        a, b = rnd.randrange(1, o.R_MOD), rnd.randrange(1, o.R_MOD)
+        aP, bQ = o.g1_mul(G1, a), o.g2_mul(G2, b)
+        abP = o.g1_mul(G1, a * b % o.R_MOD)
+        assert kzp.host_pairing_check(g1(aP) + g1(o.g1_neg(abP)), g2(bQ) + g2(G2))          # e(aP,bQ) = e(abP,Q)
+        assert kzp.host_pairing_check(g1(aP) + g1(o.g1_neg(G1)), g2(bQ) + g2(o.g2_mul(G2, a * b % o.R_MOD)))
+        assert not kzp.host_pairing_check(g1(aP) + g1(o.g1_neg(o.g1_mul(abP, 2))), g2(bQ) + g2(G2))
+    assert not kzp.host_pairing_check(g1(G1), g2(G2))                                           # non-degenerate
+    assert kzp.host_pairing_check(g1(G1) + g1(o.g1_neg(G1)), g2(G2) + g2(G2))
+    assert kzp.host_pairing_check(bytes(64) + g1(G1), g2(G2) + bytes(128))                       # infinity pairs
+    assert kzp.host_pairing_check(b"", b"")
+    bad = bytearray(g1(G1))
+    bad[0] ^= 1
+    with pytest.raises(kzp.KzpError):
+        kzp.host_pairing_check(bytes(bad), g2(G2))
+
+
+@pytest.mark.parametrize("name,zkey", [("toy", "toy_1.zkey"), ("syn256", "syn256.zkey")])
+def test_host_verify_agrees_with_oracle(kzp, oracle, name, zkey):
+    """kzp_host_verify on the reference's recorded proofs: accepts them with the right public input, rejects a wrong
+    public input, a swapped pi_a/pi_c and a tampered coordinate — the same verdicts as the oracle's verifier."""
+    d = os.path.join(GOLDEN, name)
+    exp = json.load(open(os.path.join(d, "expected.json")))
+    z = os.path.join(d, zkey)
+    vk = oracle.vk_from_zkey(oracle.read_zkey(z))
+    proof = exp["proof"]
+    cases = [(proof, exp["public"]), (proof, [exp["public"][0] + 1])]
+    js = json.loads(proof)
+    swapped = dict(js, pi_a=js["pi_c"], pi_c=js["pi_a"])
+    cases.append((json.dumps(swapped, separators=(",", ":")), exp["public"]))
+    neg = dict(js, pi_a=[js["pi_a"][0], str(oracle.Q_MOD - int(js["pi_a"][1])), "1"])  # -A: on the curve, wrong proof
+    cases.append((json.dumps(neg, separators=(",", ":")), exp["public"]))
+    for pj, pub in cases:
+        want = oracle.groth16_verify(vk, pub, *oracle.proof_from_json(pj))
+        assert kzp.host_verify(z, pj, pub) == want
+    assert kzp.host_verify(z, proof, exp["public"])
+    off = dict(js, pi_c=[js["pi_c"][0], str((int(js["pi_c"][1]) + 1) % oracle.Q_MOD), "1"])     # off the curve
+    assert not kzp.host_verify(z, json.dumps(off), exp["public"])
+    with pytest.raises(kzp.KzpError):
+        kzp.host_verify(z, proof, exp["public"] + [1])
+    with pytest.raises(kzp.KzpError):
+        kzp.host_verify(z, "{}", exp["public"])
+    with pytest.raises(kzp.KzpError):
+        kzp.host_verify(z, proof.replace(js["pi_a"][0], str(oracle.Q_MOD)), exp["public"])

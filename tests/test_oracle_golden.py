@@ -241,3 +241,20 @@ def test_microbench_generator_matches_oracle(oracle):
         assert lib.kzp_msm_closed_form(group, n, o.le32(s0), b"".join(o.le32(k) for k in ks), res) == 0
         tot = sum(k * (s0 + i) for i, k in enumerate(ks)) % o.R_MOD
         assert res.raw == to_canon(mul(gen, tot)), group
+
+
+def test_pairing_constants(oracle):
+    """The two integers csrc/pairing.hpp embeds: the ate loop count T = t - 1 = 6x^2 (congruent to p mod r) and the
+    final-exponentiation power (p^6 + 1) / r."""
+    import re
+
+    src = open(os.path.join(os.path.dirname(GOLDEN), "..", "keyless-zk-proofs_b200", "csrc", "pairing.hpp")).read()
+    p, r, x = oracle.Q_MOD, oracle.R_MOD, 4965661367192848881
+    assert p == 36 * x**4 + 36 * x**3 + 24 * x**2 + 6 * x + 1 and r == 36 * x**4 + 36 * x**3 + 18 * x**2 + 6 * x + 1
+    lo, hi = re.search(r"kAteLoop\[2\] = \{0x([0-9a-f]+)ull, 0x([0-9a-f]+)ull\}", src).groups()
+    T = int(hi, 16) << 64 | int(lo, 16)
+    assert T == 6 * x * x and (T - p) % r == 0 and T.bit_length() == 127
+    body = src[src.index("kFinalExpHex[] ="):]
+    body = body[:body.index(";")]
+    e = int("".join(re.findall(r'"([0-9a-f]+)"', body)), 16)
+    assert (p**6 + 1) % r == 0 and e == (p**6 + 1) // r
