@@ -382,15 +382,18 @@ def main():
                                "this run; IMAD.WIDE issues at half the 32-bit IMAD rate on sm_100a (profiles/r01_ubench_int_fp64_pipes.txt)",
                 "algorithmic_work": "%d sorted (point,bucket) entries x %d Fq-mul x %d wide multiply-adds" % (entries, FQ_MUL_PER_MIXED_ADD, IMAD_PER_FQ_MUL),
                 "launch_ms": acc_t,
-                "traffic": 4.50e9, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, "
-                                                   "profiles/r01_ncu_top_kernels.txt); algorithmic bytes = entries x (64 B point + 4 B entry) = %.2e" % (entries * 68.0),
-                "hbm_view": {"achieved": 4.50e9 / (acc_t * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": 4.50e9 / (acc_t * 1e-3) / 1e9 / hbm_peak}},
+                "traffic": 4.467e9, "traffic_unit": "bytes per launch (dram__bytes_read.sum 4.428 GB + dram__bytes_write.sum 0.039 GB, ncu --set full, "
+                                                   "profiles/r01_ncu_full_s8.txt); algorithmic bytes = entries x (64 B point + 4 B entry) = %.2e; the 2x is the "
+                                                   "128-byte DRAM->L2 fill behind every random 64-byte point gather (DESIGN.md section 4)" % (entries * 68.0),
+                "hbm_view": {"achieved": 4.467e9 / (acc_t * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": 4.467e9 / (acc_t * 1e-3) / 1e9 / hbm_peak}},
             "roofline_ntt": {
                 "kernel": "NTT stage kernels, 3 x (iNTT + coset + NTT) + pointwise, per proof",
                 "bound": "hbm", "achieved": ntt_bytes / (ntt_t * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ntt_bytes / (ntt_t * 1e-3) / 1e9 / hbm_peak,
-                "algorithmic_bytes": ntt_bytes, "launch_ms": ntt_t, "traffic": None,
+                "algorithmic_bytes": ntt_bytes, "launch_ms": ntt_t, "traffic": 2.149e9,
+                "traffic_unit": "bytes per proof, summed over the 5 NTT launches (ncu --set full, profiles/r01_ncu_full_s8.txt): "
+                                "a 2^21 transform is 3 radix-128 passes (2.5 with the fused middle), each reading and writing a, b, c once",
                 "note": "algorithmic bytes = 6 transforms x 2 x n x 32 B (SURVEY.md §8(d)); the binding roof for a 254-bit NTT "
                         "on B200 is the integer pipe"},
             "load_seconds": load_s,

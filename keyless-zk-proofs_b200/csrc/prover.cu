@@ -561,15 +561,6 @@ public:
         if (device < 0 || device >= n_dev)
             throw CudaError("CUDA device " + std::to_string(device) + " not present");
         set_device();
-        if (const char* g = getenv("KZP_L2_FETCH")) // experiment: L2 fetch granularity hint (32 / 64 / 128 bytes)
-        {
-            size_t before = 0, after = 0;
-            cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
-            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
-            cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
-            fprintf(stderr, "[kzp] L2 fetch granularity %zu -> %zu\n", before, after);
-            cudaGetLastError();
-        }
         // Stream priorities (KZP_PRIO=1: witness streams high, -1: H stream high, 0: equal). Measured on B200: equal
         // priorities are best (12.7 ms vs 13.0 ms); the NTT CTAs use the whole register file, so nothing co-resides
         // with them whatever the priority.

@@ -244,8 +244,8 @@ def test_microbench_generator_matches_oracle(oracle):
 
 
 def test_pairing_constants(oracle):
-    """The two integers csrc/pairing.hpp embeds: the ate loop count T = t - 1 = 6x^2 (congruent to p mod r) and the
-    final-exponentiation power (p^6 + 1) / r."""
+    """The integers csrc/pairing.hpp embeds or relies on: the ate loop count T = t - 1 = 6x^2 (congruent to p mod r),
+    the BN parameter x, and the base-p decomposition of the hard part of the final exponentiation."""
     import re
 
     src = open(os.path.join(os.path.dirname(GOLDEN), "..", "keyless-zk-proofs_b200", "csrc", "pairing.hpp")).read()
@@ -254,7 +254,8 @@ def test_pairing_constants(oracle):
     lo, hi = re.search(r"kAteLoop\[2\] = \{0x([0-9a-f]+)ull, 0x([0-9a-f]+)ull\}", src).groups()
     T = int(hi, 16) << 64 | int(lo, 16)
     assert T == 6 * x * x and (T - p) % r == 0 and T.bit_length() == 127
-    body = src[src.index("kFinalExpHex[] ="):]
-    body = body[:body.index(";")]
-    e = int("".join(re.findall(r'"([0-9a-f]+)"', body)), 16)
-    assert (p**6 + 1) % r == 0 and e == (p**6 + 1) // r
+    assert int(re.search(r"kBnX = 0x([0-9a-f]+)ull", src).group(1), 16) == x
+    # hard part of the final exponentiation in base p (Devegili-Scott-Dahab), as used by final_exponentiation()
+    l3, l2, l1, l0 = 1, 6 * x * x + 1, -36 * x**3 - 18 * x * x - 12 * x + 1, -36 * x**3 - 30 * x * x - 18 * x - 2
+    assert (p**4 - p**2 + 1) % r == 0 and l0 + l1 * p + l2 * p**2 + l3 * p**3 == (p**4 - p**2 + 1) // r
+    assert (p - 1) % 6 == 0
