@@ -104,6 +104,9 @@ struct MsmSort
     uint32_t* offsets       = nullptr; // kMsmBuckets + 2 (offsets[b] = first entry of bucket b; [B+1] = total)
     uint32_t* cursor        = nullptr; // kMsmBuckets + 2
     uint32_t* sorted        = nullptr; // cap_entries
+    uint32_t* cta_hist      = nullptr; // sort_ctas x (kMsmBuckets + 1): per-CTA bucket histograms
+    uint32_t  sort_ctas     = 0;       // CTAs of the histogram pass (one per SM at most)
+    uint32_t  per_cta       = 0;       // scalars per CTA (multiple of the block size)
 };
 
 template <class XY>
@@ -163,7 +166,7 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
 template <class XY>
 void msm_last_accumulate(const MsmSort& sort, const MsmScratch<XY>& s, float* ms, uint64_t* entries);
 // kernels launched by one msm_sort_run / one msm_reduce_batch
-constexpr uint32_t kMsmSortLaunches   = 3;
+constexpr uint32_t kMsmSortLaunches   = 4; // hist, column sums, bucket scan, scatter
 constexpr uint32_t kMsmReduceLaunches = 6;
 
 extern template struct MsmBases<G1Xyzz>;

@@ -1,5 +1,8 @@
 // Digit sort of a scalar vector for the Pippenger MSMs (sm_100a): signed base-2^16 digits -> histogram -> exclusive
-// scan -> scatter of (window, base) entries into per-bucket ranges. Group independent, so the four MSMs over the
+// scan -> scatter of (window, base) entries into per-bucket ranges. The histogram pass uses no global atomics: one
+// CTA per SM owns a contiguous slice of the scalars and keeps all 2^15 bucket counters in its shared memory (128 KiB
+// of the 227 KiB); the per-CTA histograms are summed per bucket afterwards (H MSM, 33.5 M entries: 0.39 ms with
+// global atomics -> 0.03 + 0.03 ms). Group independent, so the four MSMs over the
 // witness (A, B1, C in G1 and B2 in G2; groth16.cpp:88-112) sort once. Replaces the per-chunk digit extraction of
 // ParallelMultiexp::processChunk / getChunk (rust-rapidsnark/rapidsnark/src/multiexp.cpp:26-71).
 #include <algorithm>
@@ -52,57 +55,91 @@ __device__ __forceinline__ bool scalar_is_small(const Fr& s)
     return (s.v[1] | s.v[2] | s.v[3] | s.v[4] | s.v[5] | s.v[6] | s.v[7]) == 0 && s.v[0] <= 0x8000u;
 }
 
-// Pass 1: histogram of bucket ids. Small scalars (one digit; the bulk of a circom witness: bits, bytes)
-// are warp-aggregated so that a million equal digits do not serialise on one counter.
-static __global__ void __launch_bounds__(256)
-    k_msm_count(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ scalar_idx, uint32_t scalar_offset,
-                uint32_t n, uint32_t* __restrict__ counts)
+constexpr int    kSortThreads = 1024;
+constexpr size_t kSortSmem    = (size_t)(kMsmBuckets + 1) * sizeof(uint32_t);
+
+// Pass 1: per-CTA histogram of bucket ids in shared memory. Small scalars (one digit; the bulk of a circom witness:
+// bits, bytes) are warp-aggregated so that a million equal digits do not serialise on one counter.
+static __global__ void __launch_bounds__(kSortThreads, 1)
+    k_msm_hist(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ scalar_idx, uint32_t scalar_offset,
+               uint32_t n, uint32_t per_cta, uint32_t* __restrict__ cta_hist)
 {
-    uint32_t i     = blockIdx.x * blockDim.x + threadIdx.x;
-    bool     valid = i < n;
-    Fr       s     = Fr::zero();
-    if (valid)
-        load_scalar(scalars, scalar_idx ? scalar_idx[i] : scalar_offset + i, s);
-    bool     small = valid && scalar_is_small(s);
-    uint32_t lane  = threadIdx.x & 31;
-    uint32_t key   = (small && s.v[0] != 0) ? s.v[0] : (0xffff0000u | lane);
-    uint32_t peers = __match_any_sync(0xffffffffu, key);
-    if (small)
+    extern __shared__ uint32_t sm_cnt[];
+    for (uint32_t b = threadIdx.x; b <= kMsmBuckets; b += kSortThreads)
+        sm_cnt[b] = 0;
+    __syncthreads();
+    const uint32_t lo   = blockIdx.x * per_cta;
+    const uint32_t hi   = min(n, lo + per_cta);
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = lo; base < hi; base += kSortThreads) // trip count is uniform over the CTA
     {
-        if (s.v[0] != 0 && lane == (uint32_t)(__ffs(peers) - 1))
-            atomicAdd(&counts[s.v[0]], (uint32_t)__popc(peers));
-        return;
-    }
-    if (!valid)
-        return;
-    uint32_t carry = 0;
+        uint32_t i     = base + threadIdx.x;
+        bool     valid = i < hi;
+        Fr       s     = Fr::zero();
+        if (valid)
+            load_scalar(scalars, scalar_idx ? scalar_idx[i] : scalar_offset + i, s);
+        bool     small = valid && scalar_is_small(s);
+        uint32_t key   = (small && s.v[0] != 0) ? s.v[0] : (0xffff0000u | lane);
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (small)
+        {
+            if (s.v[0] != 0 && lane == (uint32_t)(__ffs(peers) - 1))
+                atomicAdd(&sm_cnt[s.v[0]], (uint32_t)__popc(peers));
+        }
+        else if (valid)
+        {
+            uint32_t carry = 0;
 #pragma unroll
-    for (int j = 0; j < kMsmWindows; j++)
-    {
-        int32_t d = next_digit(s, j, carry);
-        if (d != 0)
-            atomicAdd(&counts[d < 0 ? -d : d], 1u);
+            for (int j = 0; j < kMsmWindows; j++)
+            {
+                int32_t d = next_digit(s, j, carry);
+                if (d != 0)
+                    atomicAdd(&sm_cnt[d < 0 ? -d : d], 1u);
+            }
+        }
     }
+    __syncthreads();
+    uint32_t* out = cta_hist + (size_t)blockIdx.x * (kMsmBuckets + 1);
+    for (uint32_t b = threadIdx.x; b <= kMsmBuckets; b += kSortThreads)
+        out[b] = sm_cnt[b];
 }
 
-// Exclusive scan of counts[1..B] -> offsets[b] (start of bucket b), offsets[B+1] = total; cursor = offsets.
+// Per bucket: the total over the CTA histograms.
+static __global__ void __launch_bounds__(256)
+    k_msm_colsum(const uint32_t* __restrict__ cta_hist, uint32_t ctas, uint32_t* __restrict__ counts)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > kMsmBuckets)
+        return;
+    uint32_t run = 0;
+#pragma unroll 4
+    for (uint32_t c = 0; c < ctas; c++)
+        run += cta_hist[(size_t)c * (kMsmBuckets + 1) + b];
+    counts[b] = run;
+}
+
+// Exclusive scan of counts[0..B] -> offsets[b] (start of bucket b; counts[0] == 0), offsets[B+1] = total; cursor =
+// offsets. One CTA; every thread owns 32 consecutive buckets starting at a 128-byte boundary, read with 128-bit loads.
 static __global__ void __launch_bounds__(1024)
     k_msm_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor)
 {
+    static_assert(kMsmBuckets % 1024 == 0 && (kMsmBuckets / 1024) % 4 == 0, "bucket count must split into uint4 runs");
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
-    constexpr uint32_t  per = (kMsmBuckets + 1023) / 1024;
+    constexpr uint32_t  per = kMsmBuckets / 1024;
     uint32_t            tid = threadIdx.x;
-    uint32_t            b0  = 1 + tid * per;
+    uint32_t            b0  = tid * per;
     uint32_t            loc[per];
     uint32_t            sum = 0;
+    const uint4*        src = reinterpret_cast<const uint4*>(counts + b0);
 #pragma unroll
-    for (uint32_t k = 0; k < per; k++)
+    for (uint32_t k = 0; k < per / 4; k++)
     {
-        uint32_t b = b0 + k;
-        uint32_t c = (b <= kMsmBuckets) ? counts[b] : 0;
-        loc[k]     = sum;
-        sum += c;
+        uint4 c        = src[k];
+        loc[4 * k]     = sum; sum += c.x;
+        loc[4 * k + 1] = sum; sum += c.y;
+        loc[4 * k + 2] = sum; sum += c.z;
+        loc[4 * k + 3] = sum; sum += c.w;
     }
     uint32_t lane = tid & 31, wid = tid >> 5;
     uint32_t inc  = sum;
@@ -133,24 +170,30 @@ static __global__ void __launch_bounds__(1024)
     }
     __syncthreads();
     uint32_t base = warp_sums[wid] + inc - sum;
+    uint4*   o4   = reinterpret_cast<uint4*>(offsets + b0);
+    uint4*   c4   = reinterpret_cast<uint4*>(cursor + b0);
 #pragma unroll
-    for (uint32_t k = 0; k < per; k++)
+    for (uint32_t k = 0; k < per / 4; k++)
     {
-        uint32_t b = b0 + k;
-        if (b <= kMsmBuckets)
-        {
-            offsets[b] = base + loc[k];
-            cursor[b]  = base + loc[k];
-        }
+        uint4 v = make_uint4(base + loc[4 * k], base + loc[4 * k + 1], base + loc[4 * k + 2], base + loc[4 * k + 3]);
+        o4[k]   = v;
+        c4[k]   = v;
     }
     if (tid == 0)
     {
-        offsets[0]               = 0;
-        offsets[kMsmBuckets + 1] = carry_s;
+        // the last bucket (index B) and the grand total
+        uint32_t before_last     = carry_s;
+        offsets[kMsmBuckets]     = before_last;
+        cursor[kMsmBuckets]      = before_last;
+        offsets[kMsmBuckets + 1] = before_last + counts[kMsmBuckets];
     }
 }
 
-// Pass 2: scatter entry = base | window << 27 | sign << 31 into its bucket's range.
+// Pass 2: scatter entry = base | window << 27 | sign << 31 into its bucket's range. Positions come from global
+// cursors on purpose: all CTAs then fill every bucket range front to back, so the write frontier is one sector per
+// bucket (1 MB, L2 resident) and finished sectors leave L2 fully written. Handing out positions from per-CTA
+// shared-memory cursors instead (tried: 0.71 ms vs 0.47 ms) gives 148 x 2^15 frontiers = 154 MB of partially written
+// sectors, more than the L2 holds.
 static __global__ void __launch_bounds__(256)
     k_msm_scatter(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ scalar_idx, uint32_t scalar_offset,
                   uint32_t n, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted)
@@ -214,6 +257,16 @@ void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_
     KZP_CUDA_CHECK(cudaMalloc(&s.offsets, nb * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.cursor, nb * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.sorted, std::max<uint64_t>(cap, 1) * 4));
+    // one CTA per SM, each owning a contiguous slice of the scalars (a multiple of the block size)
+    int dev = 0, sms = 1;
+    KZP_CUDA_CHECK(cudaGetDevice(&dev));
+    KZP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    uint32_t blocks = std::max<uint32_t>(1, sort_div_up(n, kSortThreads));
+    s.sort_ctas     = std::min<uint32_t>((uint32_t)sms, blocks);
+    s.per_cta       = sort_div_up(blocks, s.sort_ctas) * kSortThreads;
+    s.sort_ctas     = std::max<uint32_t>(1, sort_div_up(n, s.per_cta));
+    KZP_CUDA_CHECK(cudaMalloc(&s.cta_hist, (size_t)s.sort_ctas * (kMsmBuckets + 1) * 4));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
 }
 
 void msm_sort_destroy(MsmSort& s)
@@ -222,18 +275,17 @@ void msm_sort_destroy(MsmSort& s)
     cudaFree(s.offsets);
     cudaFree(s.cursor);
     cudaFree(s.sorted);
+    cudaFree(s.cta_hist);
     s = MsmSort();
 }
 
 void msm_sort_run(MsmSort& s, const uint32_t* scalars, cudaStream_t st)
 {
-    size_t nb = kMsmBuckets + 2;
-    KZP_CUDA_CHECK(cudaMemsetAsync(s.counts, 0, nb * 4, st));
-    if (s.n > 0)
-    {
-        k_msm_count<<<sort_div_up(s.n, 256), 256, 0, st>>>(scalars, s.scalar_idx, s.scalar_offset, s.n, s.counts);
-        KZP_CUDA_CHECK(cudaGetLastError());
-    }
+    k_msm_hist<<<s.sort_ctas, kSortThreads, kSortSmem, st>>>(scalars, s.scalar_idx, s.scalar_offset, s.n, s.per_cta,
+                                                             s.cta_hist);
+    KZP_CUDA_CHECK(cudaGetLastError());
+    k_msm_colsum<<<sort_div_up(kMsmBuckets + 1, 256), 256, 0, st>>>(s.cta_hist, s.sort_ctas, s.counts);
+    KZP_CUDA_CHECK(cudaGetLastError());
     k_msm_scan<<<1, 1024, 0, st>>>(s.counts, s.offsets, s.cursor);
     KZP_CUDA_CHECK(cudaGetLastError());
     if (s.n > 0)
