@@ -738,14 +738,23 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
         KZP_CUDA_CHECK(cudaGetLastError());
     }
     KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc1, st));
-    by.x = kMsmHeavyGrid;
-    k_msm_heavy<XY><<<by, 256, 256 * sizeof(XY), st>>>(sort.offsets, a, chunk);
+    // The cold kernels below are latency-bound chains of point additions; what they cost the proof is the register
+    // file they hold while the NTT / H-MSM CTAs of the other stream wait for room (a 256-thread G2 CTA holds all
+    // 64 K registers of its SM). G2 therefore runs them as many narrow CTAs: measured on the keyless proof,
+    // 256-thread x 128-CTA -> 64-thread x 256-CTA for k_msm_heavy and 256 -> 64 threads for k_msm_fold2 moves the
+    // whole proof from 12.72 ms to 12.33 ms (B2 finishes later, in the shadow of the H MSM).
+    constexpr bool is_g2   = sizeof(XY) == 256;
+    static const bool wide = getenv("KZP_COLD_WIDE") && atoi(getenv("KZP_COLD_WIDE")) != 0; // A/B switch: old shapes
+    const uint32_t heavy_t = (is_g2 && !wide) ? 64 : 256, heavy_g = (is_g2 && !wide) ? 2 * kMsmHeavyGrid : kMsmHeavyGrid;
+    const uint32_t fold2_t = (is_g2 && !wide) ? 64 : 256;
+    by.x = heavy_g;
+    k_msm_heavy<XY><<<by, heavy_t, heavy_t * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = kMsmBuckets / kMsmFoldBlock;
     k_msm_finalize_fold<XY><<<by, kMsmFoldBlock, kMsmFoldBlock * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = 32 * kMsmFoldLevels;
-    k_msm_fold2<XY><<<by, 256, 256 * sizeof(XY), st>>>(a);
+    k_msm_fold2<XY><<<by, fold2_t, fold2_t * sizeof(XY), st>>>(a);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = 1;
     k_msm_final<XY><<<by, 192, 192 * sizeof(XY), st>>>(a);
