@@ -212,7 +212,7 @@ void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st)
     if (ntt_use_levels(log_n))
     {
         ntt_level_attrs();
-        unsigned int grid = 1u << (log_n - kNttTileBits - 4);
+        unsigned int grid = 1u << (log_n - kNttTileBits - kNttColBits);
         while (hi >= (uint32_t)kNttTileBits)
         {
             uint32_t lo = hi - kNttTileBits;
@@ -247,7 +247,7 @@ void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st)
     if (!levels)
         return;
     ntt_level_attrs();
-    unsigned int lgrid = 1u << (log_n - kNttTileBits - 4);
+    unsigned int lgrid = 1u << (log_n - kNttTileBits - kNttColBits);
     uint32_t     plo   = 0;
     for (uint32_t lo = r; lo + kNttTileBits <= log_n; lo += kNttTileBits)
     {
@@ -277,7 +277,7 @@ uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStrea
     NttBatch b;
     for (int i = 0; i < kNttMaxBatch; i++)
         b.x[i] = xs[i < count ? i : 0];
-    dim3     grid(1u << (log_n - kNttTileBits - 4), (unsigned int)count, 1);
+    dim3     grid(1u << (log_n - kNttTileBits - kNttColBits), (unsigned int)count, 1);
     uint32_t launches = 0;
     for (uint32_t lo = log_n - kNttTileBits; lo > 0; lo -= kNttTileBits)
     {
