@@ -365,9 +365,9 @@ def main():
             "config": workload_config(args, info),
             "clocks": clocks,
             "e2e": {"value": n * args.steps / e2e_elapsed, "unit": "proofs/s", "latency_ms_p50": e2e_p50,
-                    "h2d_bytes_per_step": prover.n_vars * 32, "d2h_bytes_per_step": kzp.PARTIALS_BYTES,
-                    "api": "FullProver.prove(wtns_path) via kzp_prover_prove (C ABI): file mmap + pinned staging + H2D + "
-                           "kernels + D2H + proof JSON", "h2d_ms": e2e_stage["h2d_ms"]},
+                    "h2d_bytes_per_step": int(e2e_stage["h2d_mbytes"] * 1e6), "witness_bytes": prover.n_vars * 32, "d2h_bytes_per_step": kzp.PARTIALS_BYTES,
+                    "api": "FullProver.prove(wtns_path) via kzp_prover_prove (C ABI): witness file -> classify + pack into pinned "
+                           "memory -> H2D of the packed slices -> expansion kernel -> proof kernels -> D2H -> proof JSON", "h2d_ms": e2e_stage["h2d_ms"]},
             "gpu_launches": launches_per_proof * args.steps * n,
             "gpu_launches_per_proof": launches_per_proof,
             "stage_ms_median": {k: statistics.median(s[k] for s in stage) for k in

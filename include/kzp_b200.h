@@ -94,7 +94,7 @@ int kzp_prover_assemble(kzp_prover* p, const uint8_t* partials, int count, const
 int kzp_prover_info(kzp_prover* p, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_size,
                     uint64_t* n_coefs, int* device);
 /* last proof: floats {h2d, spmv, ntt, msm_h, msm_witness_sort, msm_witness_g1 (A,B1,C batched), msm_witness_g2 (B2),
- * reserved, gpu, assemble_host, total_host, kernel_launches}; returns the number of values written (<= cap) */
+ * h2d_megabytes (what the upload moved over PCIe), gpu, assemble_host, total_host, kernel_launches}; returns the number of values written (<= cap) */
 int kzp_prover_timings(kzp_prover* p, float* out, int cap);
 /* bucket-accumulation kernel (the dominant kernel) of MSM `which` (0 A, 1 B1, 2 B2, 3 C, 4 H) in the last proof:
  * its duration from CUDA events on its stream and the number of (point, bucket) entries it summed. A, B1 and C

@@ -175,7 +175,7 @@ def _take_string(ptr: ctypes.c_void_p) -> str:
     return s
 
 
-TIMING_KEYS = ("h2d_ms", "spmv_ms", "ntt_ms", "msm_h_ms", "msm_wsort_ms", "msm_wg1_ms", "msm_wg2_ms", "reserved_ms",
+TIMING_KEYS = ("h2d_ms", "spmv_ms", "ntt_ms", "msm_h_ms", "msm_wsort_ms", "msm_wg1_ms", "msm_wg2_ms", "h2d_mbytes",
                "gpu_ms", "assemble_host_ms", "total_host_ms", "kernel_launches")
 
 

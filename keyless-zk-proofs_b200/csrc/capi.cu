@@ -361,7 +361,7 @@ int kzp_prover_timings(kzp_prover* p, float* out, int cap)
         return 0;
     const ProveTimings& t = p->prover->timings();
     float v[12] = {t.h2d_ms,     t.spmv_ms,     t.ntt_ms, t.msm_h_ms,         t.msm_wsort_ms,  t.msm_wg1_ms,
-                   t.msm_wg2_ms, t.reserved_ms, t.gpu_ms, t.assemble_host_ms, t.total_host_ms,
+                   t.msm_wg2_ms, t.h2d_mbytes, t.gpu_ms, t.assemble_host_ms, t.total_host_ms,
                    (float)t.kernel_launches};
     int   n     = cap < 12 ? cap : 12;
     for (int i = 0; i < n; i++)

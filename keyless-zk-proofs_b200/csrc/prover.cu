@@ -46,30 +46,6 @@ double now_ms()
         .count();
 }
 
-// Copy into the pinned staging buffer with non-temporal stores: the lines go to DRAM instead of staying dirty in the
-// writing core's cache, where the copy engine's reads would have to snoop them out (measured on the B200 host: a
-// freshly memcpy'd 43 MB pinned buffer DMAs at ~17 GB/s, a written-back one at 54 GB/s).
-void stream_copy(uint8_t* dst, const uint8_t* src, size_t len)
-{
-#if defined(__x86_64__)
-    if ((((uintptr_t)dst) & 15u) == 0)
-    {
-        size_t n16 = len / 16;
-        for (size_t i = 0; i < n16; i++)
-        {
-            __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + i);
-            _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + i, v);
-        }
-        _mm_sfence();
-        size_t done = n16 * 16;
-        if (done < len)
-            memcpy(dst + done, src + done, len - done);
-        return;
-    }
-#endif
-    memcpy(dst, src, len);
-}
-
 template <class XY>
 void scalar_mul(XY& out, const XY& base, const uint8_t* k32)
 {
@@ -351,6 +327,128 @@ std::string assemble_proof(const HostVk& vk, const ShardPartials* ps, int count,
     return j;
 }
 
+// ---- packed witness transfer ------------------------------------------------------------------------------
+// A circom witness is mostly bits and bytes (keyless: ~96 % of the wires are below 256), so shipping 32 bytes per
+// wire over PCIe is the slowest part of the end-to-end path (43 MB, ~1.1 ms DMA-bound). The staging workers classify
+// every value while they copy it: one byte per wire (the value when it is below 256), one flag bit per wire, and the
+// full 32 bytes only for the others. A slice of kPackWires wires becomes [small bytes][flag words][full values...]
+// and only that prefix crosses the bus; k_witness_expand rebuilds the plain n_vars x 32-byte vector in HBM.
+constexpr uint32_t kPackWires  = 32768;                                   // wires per slice (1 MiB of plain values)
+constexpr size_t   kPackSmall  = kPackWires;                              // 1 byte per wire
+constexpr size_t   kPackFlags  = kPackWires / 8;                          // 1 bit per wire
+constexpr size_t   kPackHead   = kPackSmall + kPackFlags;
+constexpr size_t   kPackStride = kPackHead + (size_t)kPackWires * 32;     // worst case: every value is full width
+constexpr uint32_t kPackGroup  = 128;                                     // wires classified per inner step
+
+// Classifies `count` values (count a multiple of kPackGroup; the caller zero-pads) that start at wire `first` of
+// the slice whose packed image begins at `slice`; *n_full is the slice's running count of full-width values.
+void pack_values(uint8_t* slice, uint32_t first, const uint8_t* vals, uint32_t count, uint32_t* n_full)
+{
+    uint8_t*  small = slice + first;
+    uint8_t*  flags = slice + kPackSmall + first / 8;
+    uint8_t*  full  = slice + kPackHead;
+    uint32_t  nf    = *n_full;
+    const __m128i zero     = _mm_setzero_si128();
+    const __m128i not_byte0 = _mm_set_epi32(-1, -1, -1, (int)0xffffff00u);
+    for (uint32_t g = 0; g < count; g += kPackGroup)
+    {
+        alignas(16) uint8_t  sm[kPackGroup];
+        alignas(16) uint32_t fl[kPackGroup / 32];
+        for (uint32_t w = 0; w < kPackGroup / 32; w++)
+        {
+            uint32_t bits = 0;
+            for (uint32_t j = 0; j < 32; j++)
+            {
+                const uint8_t* v  = vals + (size_t)(g + 32 * w + j) * 32;
+                __m128i        lo = _mm_loadu_si128(reinterpret_cast<const __m128i*>(v));
+                __m128i        hi = _mm_loadu_si128(reinterpret_cast<const __m128i*>(v + 16));
+                __m128i        x  = _mm_or_si128(hi, _mm_and_si128(lo, not_byte0));
+                bool           is_small = _mm_movemask_epi8(_mm_cmpeq_epi8(x, zero)) == 0xffff;
+                if (is_small)
+                    sm[32 * w + j] = v[0];
+                else
+                {
+                    sm[32 * w + j] = 0;
+                    bits |= 1u << j;
+                    __m128i* dst = reinterpret_cast<__m128i*>(full + (size_t)nf * 32);
+                    _mm_stream_si128(dst, lo);
+                    _mm_stream_si128(dst + 1, hi);
+                    nf++;
+                }
+            }
+            fl[w] = bits;
+        }
+        for (uint32_t k = 0; k < kPackGroup / 16; k++)
+            _mm_stream_si128(reinterpret_cast<__m128i*>(small + g) + k, _mm_load_si128(reinterpret_cast<const __m128i*>(sm) + k));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(flags + g / 8), _mm_load_si128(reinterpret_cast<const __m128i*>(fl)));
+    }
+    _mm_sfence();
+    *n_full = nf;
+}
+
+// One CTA per slice, 1024 threads: thread t owns flag word t (wires 32 t .. 32 t + 31 of the slice). A block-wide
+// exclusive scan of the popcounts gives every word the index of its first full-width value; the warp then walks its
+// 32 words with the lanes on consecutive wires, so the 32-byte stores are coalesced.
+__global__ void __launch_bounds__(1024) k_witness_expand(const uint8_t* __restrict__ pack, uint4* __restrict__ w, uint32_t n_vars)
+{
+    __shared__ uint32_t warp_tot[32];
+    const uint8_t*  slice = pack + (size_t)blockIdx.x * kPackStride;
+    const uint8_t*  small = slice;
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(slice + kPackSmall);
+    const uint4*    full  = reinterpret_cast<const uint4*>(slice + kPackHead);
+    uint32_t        tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t        word = flags[tid];
+    uint32_t        cnt  = __popc(word);
+    uint32_t        inc  = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o)
+            inc += t;
+    }
+    if (lane == 31)
+        warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0)
+    {
+        uint32_t v = warp_tot[lane], x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= (uint32_t)o)
+                x += t;
+        }
+        warp_tot[lane] = x - v;
+    }
+    __syncthreads();
+    uint32_t base = warp_tot[wid] + inc - cnt; // index of this word's first full-width value
+    for (uint32_t j = 0; j < 32; j++)
+    {
+        uint32_t wj   = __shfl_sync(0xffffffffu, word, j);
+        uint32_t bj   = __shfl_sync(0xffffffffu, base, j);
+        uint32_t loc  = (wid * 32 + j) * 32 + lane; // wire within the slice
+        uint32_t wire = blockIdx.x * kPackWires + loc;
+        if (wire >= n_vars)
+            continue;
+        uint4 lo, hi;
+        if ((wj >> lane) & 1u)
+        {
+            uint32_t r = bj + __popc(wj & ((1u << lane) - 1u));
+            lo         = full[2 * (size_t)r];
+            hi         = full[2 * (size_t)r + 1];
+        }
+        else
+        {
+            lo = make_uint4(small[loc], 0, 0, 0);
+            hi = make_uint4(0, 0, 0, 0);
+        }
+        w[2 * (size_t)wire]     = lo;
+        w[2 * (size_t)wire + 1] = hi;
+    }
+}
+
 // Persistent staging workers (spawning threads per proof costs more than the copy they do).
 class SlicePool
 {
@@ -455,7 +553,10 @@ public:
     Fr *      d_w = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_h = nullptr;
     Fr *      d_keep_a = nullptr, *d_keep_b = nullptr;
     bool      keep_ab  = false;
-    uint8_t*  pinned_w = nullptr;
+    uint8_t*  pinned_w = nullptr; // packed slices (kPackStride each)
+    uint8_t*  d_pack   = nullptr; // device image of the packed slices
+    size_t    n_pack_slices = 0;
+    uint64_t  h2d_bytes = 0;     // bytes the last upload moved over PCIe
     uint8_t*  pinned_out = nullptr; // 5 result points
 
     MsmSort            sort_w, sort_h;
@@ -591,11 +692,13 @@ public:
         KZP_CUDA_CHECK(cudaMalloc(&d_b, vec));
         KZP_CUDA_CHECK(cudaMalloc(&d_c, vec));
         KZP_CUDA_CHECK(cudaMalloc(&d_h, vec));
-        KZP_CUDA_CHECK(cudaMallocHost(&pinned_w, (size_t)n_vars * 32));
+        n_pack_slices = ((size_t)n_vars + kPackWires - 1) / kPackWires;
+        KZP_CUDA_CHECK(cudaMallocHost(&pinned_w, std::max<size_t>(1, n_pack_slices) * kPackStride));
+        KZP_CUDA_CHECK(cudaMalloc(&d_pack, std::max<size_t>(1, n_pack_slices) * kPackStride));
         KZP_CUDA_CHECK(cudaMallocHost(&pinned_out, sizeof(ShardPartials)));
         {
             const char* te = getenv("KZP_UPLOAD_THREADS");
-            int         nt = te ? atoi(te) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+            int         nt = te ? atoi(te) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
             pool.reset(new SlicePool(std::max(nt, 0)));
         }
 
@@ -641,6 +744,7 @@ public:
         cudaFree(csr.wire);
         cudaFree(csr.coef);
         cudaFree(d_w);
+        cudaFree(d_pack);
         cudaFree(d_a);
         cudaFree(d_b);
         cudaFree(d_c);
@@ -657,26 +761,51 @@ public:
         cudaStreamDestroy(st_copy);
     }
 
-    // Host -> pinned staging -> device, pipelined: worker threads fill slices of the pinned buffer (memcpy from
-    // memory, or pread() straight from the witness file: no page faults on a fresh mapping) while the calling
-    // thread hands every finished slice to the copy engine.
-    //   KZP_UPLOAD_THREADS (default min(8, cores/2)), KZP_UPLOAD_SLICE_KB (default 1024), KZP_UPLOAD_NT (default 1).
-    // Measured on the B200 host (16 cores), 43 MB witness: 2.9 ms with cached stores, 1.15-1.25 ms with streaming stores.
-    template <class Fill>
-    void upload_with(Fill&& fill)
+    // Host -> pinned staging -> device, pipelined: worker threads classify and pack slices of kPackWires values into
+    // the pinned buffer (reading them from memory, or with pread() straight from the witness file: no page faults
+    // on a fresh mapping) while the calling thread hands every finished slice's packed prefix to the copy engine;
+    // k_witness_expand then rebuilds the plain vector in HBM.   KZP_UPLOAD_THREADS (default min(16, cores)).
+    // Measured on the B200 host (16 cores), 43 MB keyless witness: plain copy 1.15 ms (DMA-bound at ~38 GB/s);
+    // packed: 3.7 MB over the bus, 0.5 ms with 16 workers (pread-bound), end to end 13.6 -> 13.0 ms.
+    // read(bounce, value_index, count) returns a pointer to `count` plain 32-byte values starting at wire
+    // `value_index` (either `bounce`, filled by the call, or the caller's own memory), nullptr on failure.
+    template <class Read>
+    void upload_with(Read&& read)
     {
         set_device();
-        static const size_t slice = getenv("KZP_UPLOAD_SLICE_KB") ? (size_t)atoi(getenv("KZP_UPLOAD_SLICE_KB")) << 10 : (1u << 20);
-        const size_t total    = (size_t)n_vars * 32;
-        const size_t n_slices = (total + slice - 1) / slice;
+        const size_t n_slices = n_pack_slices;
         std::vector<std::atomic<int>> ready(n_slices);
+        std::vector<uint32_t>         n_full(n_slices, 0);
         for (auto& r : ready)
             r.store(0, std::memory_order_relaxed);
         std::atomic<int> failed{0};
         auto             job = [&](size_t k) {
-            size_t off = k * slice, len = std::min(slice, total - off);
-            if (!fill(pinned_w + off, off, len))
-                failed.store(1);
+            constexpr uint32_t          kChunk = 4096; // values per read: 128 KiB, stays in the reading core's cache
+            static thread_local uint8_t bounce[(size_t)kChunk * 32] __attribute__((aligned(64)));
+            uint32_t first_wire = (uint32_t)(k * kPackWires);
+            uint32_t in_slice   = std::min<uint32_t>(kPackWires, n_vars - first_wire);
+            uint8_t* slice      = pinned_w + k * kPackStride;
+            uint32_t nf         = 0;
+            for (uint32_t done = 0; done < in_slice && !failed.load(std::memory_order_relaxed); done += kChunk)
+            {
+                uint32_t cnt = std::min(kChunk, in_slice - done);
+                const uint8_t* src = read(bounce, (uint64_t)first_wire + done, cnt);
+                if (!src)
+                {
+                    failed.store(1);
+                    break;
+                }
+                uint32_t padded = (cnt + kPackGroup - 1) / kPackGroup * kPackGroup;
+                if (padded != cnt)
+                {
+                    if (src != bounce)
+                        memcpy(bounce, src, (size_t)cnt * 32);
+                    memset(bounce + (size_t)cnt * 32, 0, (size_t)(padded - cnt) * 32);
+                    src = bounce;
+                }
+                pack_values(slice, done, src, padded, &nf);
+            }
+            n_full[k] = nf;
             ready[k].store(1, std::memory_order_release);
         };
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H2D0], st_copy));
@@ -686,25 +815,33 @@ public:
         else
             for (size_t k = 0; k < n_slices; k++)
                 job(k);
-        cudaError_t err = cudaSuccess;
+        cudaError_t err   = cudaSuccess;
+        uint64_t    moved = 0;
         for (size_t k = 0; k < n_slices; k++)
         {
             while (!ready[k].load(std::memory_order_acquire))
                 std::this_thread::yield();
-            size_t off = k * slice, len = std::min(slice, total - off);
+            size_t len = kPackHead + (size_t)n_full[k] * 32;
             if (err == cudaSuccess && !failed.load())
-                err = cudaMemcpyAsync((uint8_t*)d_w + off, pinned_w + off, len, cudaMemcpyHostToDevice, st_copy);
+                err = cudaMemcpyAsync(d_pack + k * kPackStride, pinned_w + k * kPackStride, len, cudaMemcpyHostToDevice, st_copy);
+            moved += len;
         }
         KZP_CUDA_CHECK(err);
         if (failed.load())
             throw LoadError("reading the witness failed");
+        if (n_slices > 0)
+        {
+            k_witness_expand<<<(unsigned int)n_slices, 1024, 0, st_copy>>>(d_pack, reinterpret_cast<uint4*>(d_w), n_vars);
+            KZP_CUDA_CHECK(cudaGetLastError());
+        }
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H2D1], st_copy));
+        h2d_bytes = moved;
         if (getenv("KZP_DEBUG_UPLOAD"))
         {
             double t1 = now_ms();
             cudaStreamSynchronize(st_copy);
-            fprintf(stderr, "[kzp upload] staged+enqueued %.3f ms, DMA drained +%.3f ms, %zu slices, %zu workers\n",
-                    t1 - dbg_t0, now_ms() - t1, n_slices, pool ? pool->size() : 0);
+            fprintf(stderr, "[kzp upload] staged+enqueued %.3f ms, DMA+expand drained +%.3f ms, %zu slices, %zu workers, %.2f MB moved\n",
+                    t1 - dbg_t0, now_ms() - t1, n_slices, pool ? pool->size() : 0, moved / 1e6);
         }
         witness_resident = true;
     }
@@ -713,39 +850,27 @@ public:
     {
         if (n < n_vars)
             throw FormatError("witness has fewer values than the zkey has variables");
-        static const int nt = getenv("KZP_UPLOAD_NT") ? atoi(getenv("KZP_UPLOAD_NT")) : 1;
-        upload_with([&](uint8_t* dst, size_t off, size_t len) {
-            if (nt)
-                stream_copy(dst, values + off, len);
-            else
-                memcpy(dst, values + off, len);
-            return true;
-        });
+        upload_with([&](uint8_t*, uint64_t first, uint32_t) -> const uint8_t* { return values + first * 32; });
     }
 
     void upload_fd(int fd, uint64_t file_offset, uint64_t n)
     {
         if (n < n_vars)
             throw FormatError("witness has fewer values than the zkey has variables");
-        // KZP_UPLOAD_NT=1 (default): pread() into a cache-resident bounce buffer, then stream_copy() to the pinned
-        // buffer; 0: pread() straight into the pinned buffer (leaves the lines dirty in the reading core's cache)
-        static const int nt = getenv("KZP_UPLOAD_NT") ? atoi(getenv("KZP_UPLOAD_NT")) : 1;
-        upload_with([&](uint8_t* dst, size_t off, size_t len) {
-            constexpr size_t            kBounce = 128u << 10;
-            static thread_local uint8_t bounce[kBounce] __attribute__((aligned(64)));
+        upload_with([&](uint8_t* bounce, uint64_t first, uint32_t count) -> const uint8_t* {
+            uint8_t* dst = bounce;
+            size_t   len = (size_t)count * 32;
+            off_t    off = (off_t)(file_offset + first * 32);
             while (len > 0)
             {
-                size_t  want = nt ? std::min(len, kBounce) : len;
-                ssize_t got  = ::pread(fd, nt ? bounce : dst, want, (off_t)(file_offset + off));
+                ssize_t got = ::pread(fd, dst, len, off);
                 if (got <= 0)
-                    return false;
-                if (nt)
-                    stream_copy(dst, bounce, (size_t)got);
+                    return nullptr;
                 dst += got;
-                off += (size_t)got;
+                off += got;
                 len -= (size_t)got;
             }
-            return true;
+            return bounce;
         });
     }
 
@@ -811,7 +936,7 @@ public:
             KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 256, sc_c.result, 128, cudaMemcpyDeviceToHost, st_w));
             KZP_CUDA_CHECK(cudaEventRecord(ev[EV_WG1], st_w));
         }
-        launches_     = 1 + ntt_kernels + 1 + 2 * kMsmSortLaunches + 3 * kMsmReduceLaunches;
+        launches_     = 1 + ntt_kernels + 1 + 2 * kMsmSortLaunches + 3 * kMsmReduceLaunches; // + 1 per upload (expand)
         gpu_in_flight = true;
     }
 
@@ -842,6 +967,7 @@ public:
             return ms;
         };
         tm.h2d_ms       = el(EV_H2D0, EV_H2D1);
+        tm.h2d_mbytes   = (float)(h2d_bytes / 1e6);
         tm.spmv_ms      = el(EV_H0, EV_SPMV);
         tm.ntt_ms       = el(EV_SPMV, EV_NTT);
         tm.msm_h_ms     = el(EV_NTT, EV_HMSM);

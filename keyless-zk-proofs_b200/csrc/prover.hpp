@@ -14,14 +14,14 @@ namespace kzp
 // stage timings of the last proof, milliseconds (CUDA events on the launching streams, except *_host)
 struct ProveTimings
 {
-    float h2d_ms      = 0; // witness host -> device
+    float h2d_ms      = 0; // witness host -> device (packed copy + expansion kernel)
     float spmv_ms     = 0;
     float ntt_ms      = 0; // 3 x (iNTT + coset + NTT) + pointwise
     float msm_h_ms    = 0;
     float msm_wsort_ms = 0; // digit sort of the witness (shared by A, B1, B2, C)
     float msm_wg1_ms   = 0; // A, B1, C: one batched G1 launch per stage
     float msm_wg2_ms   = 0; // B2
-    float reserved_ms  = 0;
+    float h2d_mbytes   = 0; // MB the last witness upload moved over PCIe (packed: bits/bytes travel as one byte)
     float gpu_ms      = 0; // first kernel to last kernel (both streams)
     float assemble_host_ms = 0;
     float total_host_ms    = 0; // wall clock of prove_*()

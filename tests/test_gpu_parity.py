@@ -592,3 +592,41 @@ def test_cli_proof_and_public_json(gpu, kzp, oracle, workdir, name, zkey, wtns):
     assert oracle.groth16_verify(oracle.vk_from_zkey(zk), [int(v) for v in public], pa, pb, pc)
     r = subprocess.run([kzp.CLI_PATH, os.path.join(d, zkey), os.path.join(d, zkey), pj, uj], capture_output=True, text=True)
     assert r.returncode == 3
+
+
+# ---------------------------------------------------------------- packed witness upload (prover.cu pack_values / k_witness_expand)
+@pytest.mark.parametrize("mix", ["edges", "all_full", "all_small", "alternating"])
+def test_packed_witness_upload_arbitrary_values(gpu, kzp, oracle, ref, port, workdir, mix):
+    """The witness crosses PCIe packed (one byte for values below 256, 32 bytes otherwise). A Groth16 prover accepts
+    any vector, satisfying or not, so arbitrary witnesses — every classification boundary, slices that are all
+    full-width / all small, a ragged last slice (n_vars = 70001 = 2 slices + 4465) — must give the reference's bytes,
+    through the file path and through the in-memory path."""
+    z, w0 = os.path.join(workdir, "pack.zkey"), os.path.join(workdir, "pack0.wtns")
+    if not os.path.exists(z):
+        port.make_setup(72000, 70001, 5, z, w0)
+    o, rnd = oracle, random.Random(sum(map(ord, mix)))
+    n = 70001
+    edge = [0, 1, 2, 254, 255, 256, 257, 0x100, 0xFFFF, 1 << 8, 1 << 16, 1 << 63, 1 << 64, 1 << 127, 1 << 128, 1 << 248,
+            (1 << 248) + 1, 255 << 8, o.R_MOD - 1, o.R_MOD - 255, o.R_MOD - 256, (1 << 253) + 7]
+    if mix == "edges":
+        vals = [edge[rnd.randrange(len(edge))] for _ in range(n)]
+    elif mix == "all_full":
+        vals = [rnd.randrange(256, o.R_MOD) for _ in range(n)]
+    elif mix == "all_small":
+        vals = [rnd.randrange(256) for _ in range(n)]
+    else:
+        vals = [(rnd.randrange(256) if (i // 97) % 2 else rnd.randrange(o.R_MOD)) for i in range(n)]
+    vals[0] = 1
+    w = os.path.join(workdir, "pack_%s.wtns" % mix)
+    o.write_wtns(w, vals)
+    r, s = o.le32(rnd.randrange(o.R_MOD >> 2)), o.le32(rnd.randrange(o.R_MOD >> 2))
+    rj, _ = ref.prove(z, w, r, s)
+    _, rh, rm = ref.dump(z, w, 1 << 17)
+    with kzp.FullProver(z) as p:
+        js, _ = p.prove(w, r, s)
+        assert js == rj and p.h_coefficients() == rh and p.msm_results() == rm
+        moved = p.timings()["h2d_mbytes"] * 1e6
+        full = sum(1 for v in vals if v >= 256)
+        assert abs(moved - (3 * (32768 + 4096) + 32 * full)) < 64  # three slice headers + the full-width values only (float MB)
+        js2, _ = p.prove_mem(b"".join(o.le32(v) for v in vals), r, s)
+        assert js2 == rj
