@@ -44,6 +44,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries print there too (NCCL's version banner goes to stdout even with
+    NCCL_DEBUG_FILE set), so file descriptor 1 is pointed at stderr for the whole run and the result line is written to
+    a private duplicate of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def data_dir():
     for d in ("/dev/shm", "/tmp"):
         if os.path.isdir(d) and os.access(d, os.W_OK):
@@ -192,7 +215,7 @@ def run_reference_arm(args, zkey, wtns, info, rank):
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 METRIC = "keyless Groth16 prove throughput (proofs/s); p50 latency (ms) in latency_ms_p50"
@@ -217,6 +240,7 @@ def main():
     ap.add_argument("--workload", default="keyless", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -408,7 +432,7 @@ def main():
             line["cpu_baseline"] = {"value": 1.0 / t, "unit": "proofs/s", "latency_ms": 1e3 * t, "cores": cores, "kind": kind,
                                     "sample": "1 full proof of the same zkey/witness after 1 warm-up (generic GMP field "
                                               "path + OpenMP stand-in for oneTBB: no nasm/oneTBB offline)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     prover.close()
     if distributed:
         dist.destroy_process_group()
