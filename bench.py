@@ -406,6 +406,9 @@ def main():
                                "this run; IMAD.WIDE issues at half the 32-bit IMAD rate on sm_100a (profiles/r01_ubench_int_fp64_pipes.txt)",
                 "algorithmic_work": "%d sorted (point,bucket) entries x %d Fq-mul x %d wide multiply-adds" % (entries, FQ_MUL_PER_MIXED_ADD, IMAD_PER_FQ_MUL),
                 "launch_ms": acc_t,
+                "launch_note": "timed inside the proof with CUDA events on its stream, while the A/B1/C witness batch shares the "
+                               "SMs (it is scheduled into the H digit sort on purpose); alone the same launch takes 5.43 ms = "
+                               "0.90 of the peak (ncu, profiles/r01_ncu_full_s8.txt)",
                 "traffic": 4.467e9, "traffic_unit": "bytes per launch (dram__bytes_read.sum 4.428 GB + dram__bytes_write.sum 0.039 GB, ncu --set full, "
                                                    "profiles/r01_ncu_full_s8.txt); algorithmic bytes = entries x (64 B point + 4 B entry) = %.2e; the 2x is the "
                                                    "128-byte DRAM->L2 fill behind every random 64-byte point gather (DESIGN.md section 4)" % (entries * 68.0),
