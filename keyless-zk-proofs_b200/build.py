@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libkzp_b200.so")
 CLI = os.path.join(HERE, "kzp_prove")  # command-line prover over the C ABI (csrc/cli_main.cpp)
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["kernels.cu", "msm_sort.cu", "msm_g1.cu", "msm_g2.cu", "prover.cu", "capi.cu", "pool.cu", "verify.cu", "fullprover_abi.cu"]
+SOURCES = ["kernels.cu", "msm_sort.cu", "msm_g1.cu", "msm_g2.cu", "prover.cu", "capi.cu", "pool.cpp", "verify.cpp", "fullprover_abi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc not found and no prebuilt libkzp_b200.so present")
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        obj = os.path.join(BUILD, os.path.splitext(src)[0] + ".o")
         cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -11,11 +11,6 @@
 
 #include "ff.cuh"
 
-#if defined(__x86_64__) && !defined(__CUDA_ARCH__)
-#include <x86intrin.h>
-#define KZP_HOST_ADC 1
-#endif
-
 namespace kzp
 {
 
@@ -84,22 +79,11 @@ struct alignas(16) HostFp
             bw                  = (d >> 64) & 1;
         }
     }
-    // branch-free (the reduction decision is data dependent and mispredicts half of the time otherwise) and written
-    // with the add-with-carry intrinsics: gcc turns the unsigned __int128 idiom into setc/movzx sequences (18 ns per
-    // operation measured), the intrinsics into plain adc/sbb chains
+    // branch-free: the reduction decision is data dependent and mispredicts half of the time otherwise. (The
+    // _addcarry_u64 / _subborrow_u64 intrinsics are 3x faster in an isolated loop but make the pairing 40 % slower
+    // inside the library build, so the plain unsigned __int128 form stays.)
     static void add(HostFp& r, const HostFp& a, const HostFp& b)
     {
-#if defined(KZP_HOST_ADC)
-        unsigned long long s[4], t[4];
-        unsigned char      c = 0, bw = 0;
-        for (int i = 0; i < 4; i++)
-            c = _addcarry_u64(c, a.v[i], b.v[i], &s[i]);
-        for (int i = 0; i < 4; i++)
-            bw = _subborrow_u64(bw, s[i], p(i), &t[i]);
-        uint64_t take = (uint64_t)0 - (uint64_t)(c | (bw ^ 1)); // s >= p <=> carry out, or no borrow from s - p
-        for (int i = 0; i < 4; i++)
-            r.v[i] = (t[i] & take) | (s[i] & ~take);
-#else
         uint64_t          s[4], t[4];
         unsigned __int128 c = 0;
         for (int i = 0; i < 4; i++)
@@ -118,21 +102,9 @@ struct alignas(16) HostFp
         uint64_t take = (uint64_t)0 - ((uint64_t)c | (bw ^ 1));
         for (int i = 0; i < 4; i++)
             r.v[i] = (t[i] & take) | (s[i] & ~take);
-#endif
     }
     static void sub(HostFp& r, const HostFp& a, const HostFp& b)
     {
-#if defined(KZP_HOST_ADC)
-        unsigned long long s[4], t[4];
-        unsigned char      bw = 0, c = 0;
-        for (int i = 0; i < 4; i++)
-            bw = _subborrow_u64(bw, a.v[i], b.v[i], &s[i]);
-        uint64_t mask = (uint64_t)0 - (uint64_t)bw; // a < b: add p back
-        for (int i = 0; i < 4; i++)
-            c = _addcarry_u64(c, s[i], p(i) & mask, &t[i]);
-        for (int i = 0; i < 4; i++)
-            r.v[i] = t[i];
-#else
         uint64_t s[4];
         uint64_t bw = 0;
         for (int i = 0; i < 4; i++)
@@ -149,7 +121,6 @@ struct alignas(16) HostFp
             r.v[i] = (uint64_t)c;
             c >>= 64;
         }
-#endif
     }
     static void neg(HostFp& r, const HostFp& a)
     {
