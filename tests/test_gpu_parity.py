@@ -630,3 +630,33 @@ def test_packed_witness_upload_arbitrary_values(gpu, kzp, oracle, ref, port, wor
         assert abs(moved - (3 * (32768 + 4096) + 32 * full)) < 64  # three slice headers + the full-width values only (float MB)
         js2, _ = p.prove_mem(b"".join(o.le32(v) for v in vals), r, s)
         assert js2 == rj
+
+
+def test_pool_spreads_over_devices(gpu, kzp, oracle):
+    """With more than one GPU visible: one prover per device, requests alternate between them, every proof equals the
+    reference's bytes. (Skipped on a single-GPU box; the 8-GPU service benchmark exercises the same path.)"""
+    if gpu < 2:
+        pytest.skip("needs at least two CUDA devices")
+    import threading
+
+    d = os.path.join(GOLDEN, "syn256")
+    exp = json.load(open(os.path.join(d, "expected.json")))
+    r, s = bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"])
+    wt = os.path.join(d, "syn256.wtns")
+    devices = list(range(min(gpu, 4)))
+    with kzp.ProverPool(os.path.join(d, "syn256.zkey"), devices=devices) as pool:
+        assert pool.devices == devices
+        bad = []
+
+        def client():
+            for _ in range(8):
+                js, _ = pool.prove(wt, r, s)
+                if js != exp["proof"]:
+                    bad.append(js)
+
+        th = [threading.Thread(target=client) for _ in range(2 * len(devices))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not bad
+        st = pool.stats()["proofs_per_slot"]
+        assert sum(st) == 16 * len(devices) and min(st) > 0
