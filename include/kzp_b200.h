@@ -174,6 +174,11 @@ int kzp_host_pairing_check(const uint8_t* g1, const uint8_t* g2, int n, int* res
 int kzp_host_verify(const char* zkey_path, const char* proof_json, const uint8_t* public32, uint32_t n_public,
                     int* valid_out);
 const char* kzp_verify_last_error(void);
+/* Host-only: how one slice (count <= 32768 values of 32 bytes) of a witness is packed for the trip over PCIe
+ * (csrc/prover.cu): out (>= 1,085,440 bytes, 16-byte aligned) = [count small bytes, padded to 32768][4096 flag bytes]
+ * [32 bytes per value >= 256]; *packed_bytes = 36,864 + 32 * *n_full is the prefix that is actually copied. */
+int kzp_host_pack_witness_slice(const uint8_t* values, uint32_t count, uint8_t* out, uint64_t out_cap, uint64_t* packed_bytes,
+                                uint32_t* n_full);
 int kzp_host_fq_decimal(const uint8_t* mont32, char* out, size_t cap);
 int kzp_host_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out);
 

@@ -142,6 +142,8 @@ def lib() -> ctypes.CDLL:
         "kzp_host_pairing_check": (c.c_int, [u8p, u8p, c.c_int, i32p]),
         "kzp_host_verify": (c.c_int, [c.c_char_p, c.c_char_p, u8p, c.c_uint32, i32p]),
         "kzp_verify_last_error": (c.c_char_p, []),
+        "kzp_host_pack_witness_slice": (c.c_int, [u8p, c.c_uint32, vp, c.c_uint64, c.POINTER(c.c_uint64),
+                                                   c.POINTER(c.c_uint32)]),
         "kzp_host_fq_decimal": (c.c_int, [u8p, c.c_char_p, c.c_size_t]),
         "kzp_host_field_op": (c.c_int, [c.c_int, c.c_int, u8p, u8p, u8p]),
     }
@@ -479,6 +481,20 @@ def host_verify(zkey_path: str, proof_json: str, public: Sequence[int]) -> bool:
     if rc != 0:
         raise KzpError("kzp_host_verify: " + lib().kzp_verify_last_error().decode())
     return bool(res.value)
+
+
+def host_pack_witness_slice(values: bytes):
+    """Packs up to 32768 witness values the way the staging workers do; returns (small bytes, flag bytes, full-width
+    values, bytes that cross PCIe)."""
+    n = len(values) // 32
+    cap = 32768 + 4096 + 32768 * 32
+    raw = ctypes.create_string_buffer(cap + 64)
+    base = ctypes.addressof(raw)
+    off = (-base) % 64
+    nb, nf = ctypes.c_uint64(), ctypes.c_uint32()
+    _check(lib().kzp_host_pack_witness_slice(values, n, ctypes.c_void_p(base + off), cap, ctypes.byref(nb), ctypes.byref(nf)))
+    blob = raw.raw[off:off + cap]
+    return blob[:32768], blob[32768:32768 + 4096], blob[36864:36864 + 32 * nf.value], nb.value
 
 
 def imad_peak(iters: int = 4096, device: int = -1):

@@ -814,6 +814,21 @@ int kzp_host_assemble(const char* zkey_path, const uint8_t* partials, int count,
     });
 }
 
+int kzp_host_pack_witness_slice(const uint8_t* values, uint32_t count, uint8_t* out, uint64_t out_cap, uint64_t* packed_bytes,
+                                uint32_t* n_full)
+{
+    return guarded([&] {
+        if (!values || !out || out_cap < pack_slice_capacity() || ((uintptr_t)out & 15u))
+            throw FormatError("output buffer too small or not 16-byte aligned");
+        uint32_t nf = 0;
+        size_t   nb = pack_witness_slice(values, count, out, &nf);
+        if (packed_bytes)
+            *packed_bytes = nb;
+        if (n_full)
+            *n_full = nf;
+    });
+}
+
 int kzp_host_fq_decimal(const uint8_t* mont32, char* out, size_t cap)
 {
     HFq v;

@@ -1114,4 +1114,32 @@ void DeviceProver::copy_ab(uint8_t* out) const
     KZP_CUDA_CHECK(cudaMemcpy(out + vec, impl_->d_keep_b, vec, cudaMemcpyDeviceToHost));
 }
 
+size_t pack_slice_capacity() { return kPackStride; }
+
+size_t pack_witness_slice(const uint8_t* values, uint32_t count, uint8_t* out, uint32_t* n_full)
+{
+    if (count > kPackWires)
+        throw FormatError("a slice holds at most 32768 values");
+    constexpr uint32_t   kChunk = 4096;
+    std::vector<uint8_t> bounce((size_t)kChunk * 32 + 64);
+    uint8_t*             b  = bounce.data() + ((64 - ((uintptr_t)bounce.data() & 63)) & 63);
+    uint32_t             nf = 0;
+    for (uint32_t done = 0; done < count; done += kChunk)
+    {
+        uint32_t       cnt    = std::min(kChunk, count - done);
+        uint32_t       padded = (cnt + kPackGroup - 1) / kPackGroup * kPackGroup;
+        const uint8_t* src    = values + (size_t)done * 32;
+        if (padded != cnt)
+        {
+            memcpy(b, src, (size_t)cnt * 32);
+            memset(b + (size_t)cnt * 32, 0, (size_t)(padded - cnt) * 32);
+            src = b;
+        }
+        pack_values(out, done, src, padded, &nf);
+    }
+    if (n_full)
+        *n_full = nf;
+    return kPackHead + (size_t)nf * 32;
+}
+
 } // namespace kzp

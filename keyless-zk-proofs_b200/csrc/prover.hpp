@@ -53,6 +53,13 @@ struct HostVk
 std::string assemble_proof(const HostVk& vk, const ShardPartials* parts, int count, const uint8_t* r32,
                            const uint8_t* s32, MsmArtefacts* art_out);
 
+// Host-only view of the packed witness transfer (prover.cu): packs `count` <= 32768 plain 32-byte values exactly as a
+// staging worker packs one slice — `out` (pack_slice_capacity() bytes, 16-byte aligned) receives
+// [1 byte per wire][1 flag bit per wire][32 bytes per value >= 256]; returns the number of bytes that would cross
+// PCIe and stores the number of full-width values in *n_full. Used by the CPU test suite.
+size_t pack_slice_capacity();
+size_t pack_witness_slice(const uint8_t* values, uint32_t count, uint8_t* out, uint32_t* n_full);
+
 class DeviceProverImpl;
 
 class DeviceProver

@@ -318,3 +318,34 @@ def test_host_verify_agrees_with_oracle(kzp, oracle, name, zkey):
         kzp.host_verify(z, "{}", exp["public"])
     with pytest.raises(kzp.KzpError):
         kzp.host_verify(z, proof.replace(js["pi_a"][0], str(oracle.Q_MOD)), exp["public"])
+
+
+def test_witness_packing_round_trip(kzp, oracle):
+    """The host half of the packed witness transfer (pack_values in csrc/prover.cu): values below 256 travel as one
+    byte, the rest as 32 bytes behind a flag bit. Re-expanding the packed slice in Python gives the input back, for
+    every classification boundary and for counts that are not multiples of the 128-value inner step."""
+    rnd = random.Random(33)
+    edge = [0, 1, 255, 256, 257, 0xFFFF, 1 << 8, 1 << 63, 1 << 64, 1 << 128, 1 << 248, (1 << 248) + 1, oracle.R_MOD - 1,
+            (1 << 256) - 1, 255 << 248, 1 << 255]
+    for count in (1, 3, 127, 128, 129, 4095, 4096, 4097, 10000, 32768):
+        vals = [rnd.choice(edge) if rnd.random() < 0.5 else (rnd.randrange(256) if rnd.random() < 0.7 else rnd.randrange(1 << 256))
+                for _ in range(count)]
+        small, flags, full, moved = kzp.host_pack_witness_slice(b"".join(v.to_bytes(32, "little") for v in vals))
+        n_full = sum(1 for v in vals if v >= 256)
+        assert len(full) == 32 * n_full and moved == 32768 + 4096 + 32 * n_full
+        k = 0
+        for i, v in enumerate(vals):
+            is_full = (flags[i >> 3] >> (i & 7)) & 1
+            assert is_full == (1 if v >= 256 else 0), (count, i)
+            if is_full:
+                assert int.from_bytes(full[32 * k:32 * k + 32], "little") == v
+                assert small[i] == 0
+                k += 1
+            else:
+                assert small[i] == v
+        # padding of the last 128-value group is classified as zeros
+        pad_end = (count + 127) // 128 * 128
+        assert all(b == 0 for b in small[count:pad_end])
+        assert all(((flags[i >> 3] >> (i & 7)) & 1) == 0 for i in range(count, pad_end))
+    with pytest.raises(kzp.KzpError):
+        kzp.host_pack_witness_slice(bytes(32 * 32769))
