@@ -156,12 +156,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+REF_FLAVOUR = ""
+
+
 def cpu_reference_prover(zkey):
     """The reference's own CPU prover (oracle/_ref) or, when that library did not travel, the C port."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import refutil
-    ref = refutil.load_ref()
+    ref, flavour = refutil.load_ref_asm(), "x86-64 assembly field path (the reference's fr.asm / fq.asm, MULX/ADCX/ADOX, assembled with GNU as)"
+    if ref is None or os.environ.get("KZP_REF_GENERIC"):
+        ref, flavour = refutil.load_ref(), "portable GMP-mpn field path (the asm build is absent or this CPU lacks ADX/BMI2)"
+    global REF_FLAVOUR
     if ref is not None:
+        REF_FLAVOUR = flavour + " + OpenMP stand-in for oneTBB"
         h = ref.lib.kzp_ref_prover_new(zkey.encode(), 1, None)
         buf = ctypes.create_string_buffer(8192)
         ms = ctypes.c_int()
@@ -174,6 +181,7 @@ def cpu_reference_prover(zkey):
             return time.perf_counter() - t0
         return "reference", cores, prove
     port = refutil.load_port()
+    REF_FLAVOUR = "C restatement oracle/kzp_port.c (oracle/_ref did not travel)"
     cores = port.lib.kzp_port_num_threads()
     r, s = (12345).to_bytes(32, "little"), (67890).to_bytes(32, "little")
 
@@ -210,8 +218,7 @@ def run_reference_arm(args, zkey, wtns, info, rank):
         "config": workload_config(args, info),
         "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": cores, "kind": kind,
                          "sample": "%d full proofs of the same zkey/witness, one at a time (prover-service serialises "
-                                   "proofs behind one mutex); generic GMP field path + OpenMP stand-in for oneTBB "
-                                   "(no nasm/oneTBB offline)" % len(times)},
+                                   "proofs behind one mutex); %s" % (len(times), REF_FLAVOUR)},
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -433,8 +440,7 @@ def main():
             prove(wtns)  # first call pages the key in
             t = prove(wtns)
             line["cpu_baseline"] = {"value": 1.0 / t, "unit": "proofs/s", "latency_ms": 1e3 * t, "cores": cores, "kind": kind,
-                                    "sample": "1 full proof of the same zkey/witness after 1 warm-up (generic GMP field "
-                                              "path + OpenMP stand-in for oneTBB: no nasm/oneTBB offline)"}
+                                    "sample": "1 full proof of the same zkey/witness after 1 warm-up; " + REF_FLAVOUR}
         emit(line)
     prover.close()
     if distributed:

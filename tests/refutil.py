@@ -5,6 +5,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libkzp_ref.so")
+REF_ASM_PATH = os.path.join(ROOT, "oracle", "_ref", "libkzp_ref_asm.so")  # the reference with its x86-64 asm field path
 PORT_PATH = os.path.join(ROOT, "oracle", "libkzp_port.so")
 
 
@@ -126,6 +127,22 @@ def load_ref():
     if not os.path.exists(REF_PATH):
         return None
     return Ref(ctypes.CDLL(REF_PATH))
+
+
+def cpu_has_adx_bmi2():
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return False
+    return " adx" in flags and " bmi2" in flags
+
+
+def load_ref_asm():
+    """The reference built with its own x86-64 assembly field arithmetic (oracle/Makefile ref_asm); None when it was
+    not built or this CPU lacks MULX/ADCX/ADOX."""
+    if not os.path.exists(REF_ASM_PATH) or not cpu_has_adx_bmi2():
+        return None
+    return Ref(ctypes.CDLL(REF_ASM_PATH))
 
 
 def load_port():

@@ -259,3 +259,28 @@ def test_pairing_constants(oracle):
     l3, l2, l1, l0 = 1, 6 * x * x + 1, -36 * x**3 - 18 * x * x - 12 * x + 1, -36 * x**3 - 30 * x * x - 18 * x - 2
     assert (p**4 - p**2 + 1) % r == 0 and l0 + l1 * p + l2 * p**2 + l3 * p**3 == (p**4 - p**2 + 1) // r
     assert (p - 1) % 6 == 0
+
+
+def test_reference_asm_build_equals_portable_build(oracle, ref, workdir):
+    """oracle/_ref/libkzp_ref_asm.so = the reference compiled with its own x86-64 assembly field arithmetic
+    (fr.asm / fq.asm rewritten for GNU as by oracle/nasm2gas.py at build time). It is the CPU baseline of bench.py,
+    so it must be the same prover: recorded proofs, raw field operations on random and edge inputs, MSM results."""
+    import refutil
+
+    asm = refutil.load_ref_asm()
+    if asm is None:
+        pytest.skip("asm build absent or CPU without ADX/BMI2")
+    for name, zkey, wtns in (("toy", "toy_1.zkey", "toy.wtns"), ("syn256", "syn256.zkey", "syn256.wtns")):
+        d = os.path.join(GOLDEN, name)
+        exp = json.load(open(os.path.join(d, "expected.json")))
+        js, _ = asm.prove(os.path.join(d, zkey), os.path.join(d, wtns), bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"]))
+        assert js == exp["proof"], name
+        _, h, m = asm.dump(os.path.join(d, zkey), os.path.join(d, wtns), len(bytes.fromhex(exp["h"])) // 32)
+        assert h.hex() == exp["h"] and m.hex() == exp["msm"], name
+    rnd = random.Random(17)
+    for field, mod in ((0, oracle.R_MOD), (1, oracle.Q_MOD)):
+        vals = [0, 1, 2, mod - 1, mod - 2, (1 << 64) - 1, 1 << 64, 1 << 128, 1 << 253] + [rnd.randrange(mod) for _ in range(500)]
+        a = b"".join(oracle.le32(v) for v in vals)
+        b = b"".join(oracle.le32(v) for v in reversed(vals))
+        for op in (0, 1, 2, 3, 4, 5, 6):
+            assert asm.field_op(field, op, a, b) == ref.field_op(field, op, a, b), (field, op)
