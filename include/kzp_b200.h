@@ -124,6 +124,11 @@ int kzp_pool_prove(kzp_pool* pool, const char* wtns_path, const uint8_t* r32, co
                    int* error_out, int* prover_time_ms, int* slot_out);
 int kzp_pool_prove_mem(kzp_pool* pool, const uint8_t* witness, uint64_t n, const uint8_t* r32, const uint8_t* s32,
                        char** json_out, int* error_out, int* prover_time_ms, int* slot_out);
+/* Fused verify-before-return: with on != 0 every proof is checked under the zkey's verifying key
+ * (kzp_host_verify, host only) before it is returned — after the prover has been released, so the GPU is already on the
+ * next request. A proof that does not verify (a witness that does not satisfy the circuit) is dropped and the call
+ * returns KZP_RESPONSE_ERROR / KZP_PROVER_ERROR_INVALID_INPUT. Off by default. */
+int kzp_pool_set_verify(kzp_pool* pool, int on);
 /* proofs served per slot (returns the number of slots written) and the deepest queue seen */
 int kzp_pool_stats(kzp_pool* pool, uint64_t* proofs_per_slot, int cap, uint64_t* max_waiting);
 /* host-only exercise of the checkout queue (no GPU needed; used by the CPU test suite) */

@@ -123,6 +123,7 @@ def lib() -> ctypes.CDLL:
         "kzp_pool_device": (c.c_int, [vp, c.c_int]),
         "kzp_pool_prove": (c.c_int, [vp, c.c_char_p, u8p, u8p, c.POINTER(vp), i32p, i32p, i32p]),
         "kzp_pool_prove_mem": (c.c_int, [vp, u8p, c.c_uint64, u8p, u8p, c.POINTER(vp), i32p, i32p, i32p]),
+        "kzp_pool_set_verify": (c.c_int, [vp, c.c_int]),
         "kzp_pool_stats": (c.c_int, [vp, c.POINTER(c.c_uint64), c.c_int, c.POINTER(c.c_uint64)]),
         "kzp_pool_sched_selftest": (c.c_int, [c.c_int, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_uint64), i32p,
                                               c.POINTER(c.c_uint64)]),
@@ -370,6 +371,10 @@ class ProverPool:
         rc = lib().kzp_pool_prove_mem(self._h, witness, len(witness) // 32, r, s, ctypes.byref(out),
                                       ctypes.byref(err), ctypes.byref(ms), ctypes.byref(slot))
         return self._finish(rc, out, err, ms, slot)
+
+    def set_verify(self, on: bool = True):
+        """Verify every proof under the zkey's VK before returning it (host pairing check, after the prover is released)."""
+        _check(lib().kzp_pool_set_verify(self._h, 1 if on else 0))
 
     def stats(self):
         arr, mw = (ctypes.c_uint64 * max(1, self.size))(), ctypes.c_uint64()

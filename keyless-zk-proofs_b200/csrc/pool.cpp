@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/kzp_b200.h"
+#include "binfile.hpp"
 #include "pool.hpp"
 
 using namespace kzp;
@@ -20,6 +21,9 @@ struct kzp_pool
     std::vector<int>         devices;
     SlotScheduler*           sched = nullptr;
     int                      state = KZP_STATE_OK;
+    std::string              zkey_path;
+    uint32_t                 n_public = 0;
+    std::atomic<int>         verify{0}; // verify every proof under the zkey's VK before returning it
 };
 
 static std::vector<int> pool_devices(const int* devices, int n)
@@ -59,7 +63,8 @@ kzp_pool* kzp_pool_new(const char* zkey_path, const int* devices, int n_devices,
         return nullptr;
     try
     {
-        pool->devices = pool_devices(devices, n_devices);
+        pool->zkey_path = zkey_path ? zkey_path : "";
+        pool->devices   = pool_devices(devices, n_devices);
         size_t n      = pool->devices.size();
         pool->provers.assign(n, nullptr);
         std::vector<int>         states(n, KZP_STATE_ZKEY_FILE_LOAD_ERROR);
@@ -74,6 +79,11 @@ kzp_pool* kzp_pool_new(const char* zkey_path, const int* devices, int n_devices,
             if (!pool->provers[i] || states[i] != KZP_STATE_OK)
                 pool->state = pool->provers[i] ? states[i] : KZP_STATE_ZKEY_FILE_LOAD_ERROR;
         pool->sched = new SlotScheduler((int)n);
+        if (pool->state == KZP_STATE_OK)
+        {
+            int st = 0;
+            kzp_host_parse_zkey(pool->zkey_path.c_str(), nullptr, &pool->n_public, nullptr, nullptr, &st);
+        }
     }
     catch (...)
     {
@@ -110,8 +120,20 @@ int kzp_pool_device(const kzp_pool* pool, int slot)
     return pool->devices[slot];
 }
 
-template <class Run>
-static int pool_run(kzp_pool* pool, char** json_out, int* error_out, int* prover_time_ms, int* slot_out, Run&& run)
+// Fused verify-before-return: the service re-verifies every proof it hands out
+// (prover_handler.rs:329-336); with kzp_pool_set_verify(pool, 1) that check runs here, on the calling thread and
+// AFTER the prover has been released, so the GPU already works on the next request while the pairing is checked.
+int kzp_pool_set_verify(kzp_pool* pool, int on)
+{
+    if (!pool)
+        return KZP_ERR_STATE;
+    pool->verify.store(on ? 1 : 0);
+    return KZP_OK;
+}
+
+template <class Run, class Publics>
+static int pool_run(kzp_pool* pool, char** json_out, int* error_out, int* prover_time_ms, int* slot_out, Run&& run,
+                    Publics&& publics)
 {
     if (json_out)
         *json_out = nullptr;
@@ -136,23 +158,61 @@ static int pool_run(kzp_pool* pool, char** json_out, int* error_out, int* prover
         *slot_out = slot;
     int rc = run(pool->provers[slot]);
     pool->sched->release(slot);
+    if (rc == KZP_RESPONSE_SUCCESS && pool->verify.load() && json_out && *json_out)
+    {
+        std::vector<uint8_t> pub((size_t)pool->n_public * 32);
+        int                  valid = 0;
+        bool                 ok    = publics(pub.data(), pool->n_public) &&
+                  kzp_host_verify(pool->zkey_path.c_str(), *json_out, pub.data(), pool->n_public, &valid) == KZP_OK && valid;
+        if (!ok)
+        {
+            kzp_free(*json_out);
+            *json_out = nullptr;
+            if (error_out)
+                *error_out = KZP_PROVER_ERROR_INVALID_INPUT; // the witness does not satisfy the circuit
+            return KZP_RESPONSE_ERROR;
+        }
+    }
     return rc;
 }
 
 int kzp_pool_prove(kzp_pool* pool, const char* wtns_path, const uint8_t* r32, const uint8_t* s32, char** json_out,
                    int* error_out, int* prover_time_ms, int* slot_out)
 {
-    return pool_run(pool, json_out, error_out, prover_time_ms, slot_out, [&](kzp_prover* p) {
-        return kzp_prover_prove(p, wtns_path, r32, s32, json_out, error_out, prover_time_ms);
-    });
+    return pool_run(
+        pool, json_out, error_out, prover_time_ms, slot_out,
+        [&](kzp_prover* p) { return kzp_prover_prove(p, wtns_path, r32, s32, json_out, error_out, prover_time_ms); },
+        [&](uint8_t* out, uint32_t n_public) {
+            // public signals = witness values 1 .. nPublic (wtns_utils.hpp:28-43)
+            try
+            {
+                MappedFile file(wtns_path ? wtns_path : "");
+                BinView    bin(file.data(), file.size(), "wtns", 2);
+                WtnsHeader wh = parse_wtns(bin);
+                if (wh.values_bytes < 32ull * (n_public + 1))
+                    return false;
+                memcpy(out, wh.values + 32, 32ull * n_public);
+                return true;
+            }
+            catch (...)
+            {
+                return false;
+            }
+        });
 }
 
 int kzp_pool_prove_mem(kzp_pool* pool, const uint8_t* witness, uint64_t n, const uint8_t* r32, const uint8_t* s32,
                        char** json_out, int* error_out, int* prover_time_ms, int* slot_out)
 {
-    return pool_run(pool, json_out, error_out, prover_time_ms, slot_out, [&](kzp_prover* p) {
-        return kzp_prover_prove_mem(p, witness, n, r32, s32, json_out, error_out, prover_time_ms);
-    });
+    return pool_run(
+        pool, json_out, error_out, prover_time_ms, slot_out,
+        [&](kzp_prover* p) { return kzp_prover_prove_mem(p, witness, n, r32, s32, json_out, error_out, prover_time_ms); },
+        [&](uint8_t* out, uint32_t n_public) {
+            if (!witness || n < (uint64_t)n_public + 1)
+                return false;
+            memcpy(out, witness + 32, 32ull * n_public);
+            return true;
+        });
 }
 
 int kzp_pool_stats(kzp_pool* pool, uint64_t* proofs_per_slot, int cap, uint64_t* max_waiting)

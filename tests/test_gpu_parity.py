@@ -660,3 +660,32 @@ def test_pool_spreads_over_devices(gpu, kzp, oracle):
         assert not bad
         st = pool.stats()["proofs_per_slot"]
         assert sum(st) == 16 * len(devices) and min(st) > 0
+
+
+def test_pool_fused_verify_before_return(gpu, kzp, oracle, workdir):
+    """kzp_pool_set_verify: a satisfying witness still returns its proof (file and in-memory paths); a witness that
+    does not satisfy the circuit yields a proof that cannot verify, which the pool drops with INVALID_INPUT — what
+    prover-service does with ark-groth16 after every proof (prover_handler.rs:329-336)."""
+    d = os.path.join(GOLDEN, "syn256")
+    exp = json.load(open(os.path.join(d, "expected.json")))
+    wt = os.path.join(d, "syn256.wtns")
+    good = oracle.read_wtns(wt)
+    bad = list(good)
+    bad[len(bad) // 2] = (bad[len(bad) // 2] + 1) % oracle.R_MOD
+    bad_path = os.path.join(workdir, "syn256_bad.wtns")
+    oracle.write_wtns(bad_path, bad)
+    with kzp.ProverPool(os.path.join(d, "syn256.zkey"), devices=[0]) as pool:
+        js_unchecked, _ = pool.prove(bad_path)            # verification off: the (worthless) proof is returned
+        zk = oracle.read_zkey(os.path.join(d, "syn256.zkey"))
+        assert not oracle.groth16_verify(oracle.vk_from_zkey(zk), exp["public"], *oracle.proof_from_json(js_unchecked))
+        pool.set_verify(True)
+        js, _ = pool.prove(wt)
+        assert kzp.host_verify(os.path.join(d, "syn256.zkey"), js, exp["public"])
+        js, _ = pool.prove_mem(b"".join(oracle.le32(v) for v in good), bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"]))
+        assert js == exp["proof"]
+        with pytest.raises(kzp.InvalidInput):
+            pool.prove(bad_path)
+        with pytest.raises(kzp.InvalidInput):
+            pool.prove_mem(b"".join(oracle.le32(v) for v in bad))
+        pool.set_verify(False)
+        pool.prove(bad_path)
