@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--warmup", type=int, default=3, help="proofs per prover before the timed window")
     ap.add_argument("--workload", default="keyless", choices=sorted(bench.WORKLOADS))
+    ap.add_argument("--verify", action="store_true", help="fused verify-before-return (kzp_pool_set_verify)")
     args = ap.parse_args()
     os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
     zkey, wtns, info = bench.ensure_inputs(args.workload)
@@ -41,6 +42,8 @@ def main():
     t0 = time.time()
     pool = kzp.ProverPool(zkey, devices=devices)
     load_s = time.time() - t0
+    if args.verify:
+        pool.set_verify(True)
     inflight = args.inflight or 2 * pool.size
 
     for _ in range(args.warmup * pool.size):
@@ -80,7 +83,7 @@ def main():
         "n_gpus": n_gpus, "provers_per_gpu": args.per_gpu, "inflight": inflight, "seconds": elapsed, "proofs": len(lat),
         "latency_ms": {"p50": statistics.median(lat), "p95": lat[int(0.95 * (len(lat) - 1))], "max": lat[-1]},
         "proofs_per_slot": st["proofs_per_slot"], "max_waiting": st["max_waiting"],
-        "distinct_final_proofs": distinct, "load_seconds": load_s,
+        "distinct_final_proofs": distinct, "load_seconds": load_s, "verify_before_return": bool(args.verify),
         "config": bench.workload_config(argparse.Namespace(workload=args.workload, gpus=n_gpus), info),
         "api": "kzp_pool_prove(wtns_path): GPU-per-request checkout + FullProver.prove path (file -> pinned -> HBM -> proof JSON)",
     }
