@@ -36,8 +36,11 @@ WORKLOADS = {
     "keyless": (1376867, 1343588, 2),
     "small": (60000, 58000, 1),
 }
-FQ_MUL_PER_MIXED_ADD = 10      # XYZZ madd-2008-s in G1: 8M + 2S (curve.cpp:203-249)
-IMAD_PER_FQ_MUL = 128          # 8-limb CIOS: 2*8*8 wide (32x32+64) multiply-adds; the 8 low IMADs for m are not counted
+# XYZZ madd-2008-s in G1 (curve.cpp:203-249) is 8M + 2S. As issued by csrc/ec.cuh + csrc/ff.cuh: 6 products of 128 wide
+# (32x32+64) multiply-adds, 2 dedicated squarings of 100 (28 off-diagonal + 8 diagonal + 64 reduction) and one dual
+# product (Q - x3) R + (-y1) PPP with a single reduction, 192. The 8 low IMADs per reduction (m) are not counted.
+IMAD_PER_FQ_MUL = 128
+IMAD_PER_MIXED_ADD = 6 * 128 + 2 * 100 + 192
 
 
 def log(*a):
@@ -378,7 +381,7 @@ def main():
         value = n * args.steps / elapsed
         acc_t = statistics.median(a for a, _ in acc_ms)
         entries = acc_ms[-1][1]
-        imads = entries * FQ_MUL_PER_MIXED_ADD * IMAD_PER_FQ_MUL
+        imads = entries * IMAD_PER_MIXED_ADD
         achieved = imads / (acc_t * 1e-3) / 1e12
         ntt_t = statistics.median(ntt_ms)
         ntt_bytes = 6 * 2 * info["domain"] * 32
@@ -411,7 +414,7 @@ def main():
                 "achieved": achieved, "peak": imad_peak / 1e12, "unit": "T wide-multiply-add/s", "frac": achieved / (imad_peak / 1e12),
                 "peak_source": "kzp_imad_peak: carry-chained mad.lo.cc/madc.hi.cc (IMAD.WIDE.U32[.X]) on all SMs, measured in "
                                "this run; IMAD.WIDE issues at half the 32-bit IMAD rate on sm_100a (profiles/r01_ubench_int_fp64_pipes.txt)",
-                "algorithmic_work": "%d sorted (point,bucket) entries x %d Fq-mul x %d wide multiply-adds" % (entries, FQ_MUL_PER_MIXED_ADD, IMAD_PER_FQ_MUL),
+                "algorithmic_work": "%d sorted (point,bucket) entries x %d wide multiply-adds per mixed addition (6 products x 128 + 2 squarings x 100 + 1 dual product x 192)" % (entries, IMAD_PER_MIXED_ADD),
                 "launch_ms": acc_t,
                 "launch_note": "timed inside the proof with CUDA events on its stream, while the A/B1/C witness batch shares the "
                                "SMs (it is scheduled into the H digit sort on purpose); alone the same launch takes 5.43 ms = "

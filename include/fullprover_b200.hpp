@@ -14,7 +14,7 @@
 //   _ZN14ProverResponseD1Ev                                                        fullprover.hpp:52
 //   _ZN14ProverResponse12empty_stringE                                             fullprover.hpp:42
 //
-// Layouts (checked by static_asserts in csrc/fullprover_abi.cu and by tests/test_abi_symbols.py):
+// Layouts (checked by static_asserts in csrc/fullprover_abi.cu and by tests/test_host_library.py::test_cxx_abi_against_reference_header):
 //   FullProver      16 bytes : impl pointer @0, state @8 (Rust reads .state directly, lib.rs:53)
 //   ProverResponse  24 bytes : type @0, raw_json @8, error @16, metrics.prover_time @20
 //

@@ -40,6 +40,9 @@ extern "C" {
 #define KZP_STATE_OK 0
 #define KZP_STATE_ZKEY_FILE_LOAD_ERROR 1
 #define KZP_STATE_UNSUPPORTED_ZKEY_CURVE 2
+/* not in the reference's enum: the CUDA context died under this prover (sticky error). The handle answers every
+ * later call with PROVER_NOT_READY; the Itanium shim reports it the same way (prove() is const there). */
+#define KZP_STATE_DEVICE_FAULT 3
 /* ProverResponseType (fullprover.hpp:5-9) */
 #define KZP_RESPONSE_SUCCESS 0
 #define KZP_RESPONSE_ERROR 1
@@ -71,6 +74,11 @@ void        kzp_prover_free(kzp_prover* p); /* FullProver::~FullProver */
  * canonical); pass NULL for fresh randomness (groth16.cpp:296-316). */
 int kzp_prover_prove(kzp_prover* p, const char* wtns_path, const uint8_t* r32, const uint8_t* s32,
                      char** json_out, int* error_out, int* prover_time_ms);
+/* Error classes: a malformed / unreadable / wrong-curve witness -> INVALID_INPUT (or WITNESS_GENERATION_INVALID_CURVE);
+ * a CUDA failure (launch error, out of memory, lost device) -> PROVER_NOT_READY, and when the error is sticky the
+ * handle's state becomes KZP_STATE_DEVICE_FAULT. kzp_prover_last_status gives the KZP_ERR_* class of the last failure. */
+int kzp_prover_state(const kzp_prover* p);       /* KZP_STATE_* now (health check) */
+int kzp_prover_last_status(const kzp_prover* p); /* KZP_OK or the KZP_ERR_* of the last failed call */
 /* Additive entry: witness values already in memory, n x 32-byte LE canonical. */
 int kzp_prover_prove_mem(kzp_prover* p, const uint8_t* witness, uint64_t n, const uint8_t* r32,
                          const uint8_t* s32, char** json_out, int* error_out, int* prover_time_ms);
@@ -119,6 +127,7 @@ kzp_pool* kzp_pool_new(const char* zkey_path, const int* devices, int n_devices,
 void      kzp_pool_free(kzp_pool* pool); /* waits for proofs in flight */
 int       kzp_pool_size(const kzp_pool* pool);
 int       kzp_pool_device(const kzp_pool* pool, int slot);
+int       kzp_pool_healthy(const kzp_pool* pool); /* provers whose state is still KZP_STATE_OK (health check) */
 /* kzp_prover_prove / kzp_prover_prove_mem on the next free prover; *slot_out (optional) says which one ran it */
 int kzp_pool_prove(kzp_pool* pool, const char* wtns_path, const uint8_t* r32, const uint8_t* s32, char** json_out,
                    int* error_out, int* prover_time_ms, int* slot_out);
@@ -126,8 +135,10 @@ int kzp_pool_prove_mem(kzp_pool* pool, const uint8_t* witness, uint64_t n, const
                        char** json_out, int* error_out, int* prover_time_ms, int* slot_out);
 /* Fused verify-before-return: with on != 0 every proof is checked under the zkey's verifying key
  * (kzp_host_verify, host only) before it is returned — after the prover has been released, so the GPU is already on the
- * next request. A proof that does not verify (a witness that does not satisfy the circuit) is dropped and the call
- * returns KZP_RESPONSE_ERROR / KZP_PROVER_ERROR_INVALID_INPUT. Off by default. */
+ * next request. A proof that does not verify is dropped: KZP_RESPONSE_ERROR / KZP_PROVER_ERROR_INVALID_INPUT when the
+ * witness is at fault (unreadable public signals, or the device that produced it is still healthy: the witness does
+ * not satisfy the circuit), KZP_PROVER_ERROR_NOT_READY when the verifier itself failed or the producing device has
+ * faulted since (the slot is then retired). Off by default. */
 int kzp_pool_set_verify(kzp_pool* pool, int on);
 /* proofs served per slot (returns the number of slots written) and the deepest queue seen */
 int kzp_pool_stats(kzp_pool* pool, uint64_t* proofs_per_slot, int cap, uint64_t* max_waiting);
@@ -153,7 +164,7 @@ int kzp_msm_run(kzp_msm* m, const uint8_t* scalars, uint8_t* out);
 int kzp_msm_bench(kzp_msm* m, const uint8_t* scalars, int iters, float* ms_per_msm, uint64_t* entries);
 
 /* field: 0 Fr, 1 Fq, 2 Fq2 (64-byte elements); op: 0 mul 1 add 2 sub 3 neg 4 toMontgomery 5 fromMontgomery
- * 6 square 7 inverse. Host buffers, `count` elements; b may be NULL for unary ops. */
+ * 6 square 7 inverse 8 a*b + b*b (dual product with one reduction, Fr / Fq only). Host buffers, `count` elements; b may be NULL for unary ops. */
 int kzp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t count,
                  int device);
 /* group: 0 G1, 1 G2; op: 0 xyzz += affine, 1 xyzz += xyzz, 2 double. p/out XYZZ (128/256 B per point). */

@@ -222,7 +222,7 @@ static inline ZkeyHeader parse_zkey(const BinView& bin)
 
     if (h.domain_size == 0 || (h.domain_size & (h.domain_size - 1)) != 0)
         throw FormatError("zkey domain size is not a power of two");
-    if (h.n_public + 1 > h.n_vars)
+    if ((uint64_t)h.n_public + 1 > (uint64_t)h.n_vars) // 64-bit: nPublic = 0xffffffff must not wrap to 0
         throw FormatError("zkey nPublic exceeds nVars");
 
     const Section& c4 = bin.section(4);
@@ -240,7 +240,7 @@ static inline ZkeyHeader parse_zkey(const BinView& bin)
     h.points_a  = pts(5, h.n_vars, 64);
     h.points_b1 = pts(6, h.n_vars, 64);
     h.points_b2 = pts(7, h.n_vars, 128);
-    h.points_c  = pts(8, h.n_vars - h.n_public - 1, 64);
+    h.points_c  = pts(8, (uint64_t)h.n_vars - h.n_public - 1, 64);
     h.points_h  = pts(9, h.domain_size, 64);
     return h;
 }

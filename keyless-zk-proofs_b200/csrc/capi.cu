@@ -89,10 +89,23 @@ static void use_device(int device)
 // ------------------------------------------------------------------------------------------- prover
 struct kzp_prover
 {
-    DeviceProver* prover = nullptr;
-    int           state  = KZP_STATE_OK;
+    DeviceProver* prover      = nullptr;
+    int           state       = KZP_STATE_OK;
+    int           last_status = KZP_OK; // KZP_ERR_* class of the last failed call on this handle
     std::string   why;
 };
+
+// After a CUDA failure: is the context still usable? A sticky error (illegal address, launch failure, ECC, lost
+// device) makes every later runtime call fail with the same code; out-of-memory and invalid-argument errors do not.
+static bool device_is_dead()
+{
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess)
+        e = cudaGetLastError();
+    else
+        cudaGetLastError();
+    return e != cudaSuccess && e != cudaErrorMemoryAllocation;
+}
 
 kzp_prover* kzp_prover_new_sharded(const char* zkey_path, int device, int rank, int world, int* state_out)
 {
@@ -173,8 +186,22 @@ static int prove_common(kzp_prover* p, Run&& run, char** json_out, int* error_ou
     std::string json;
     auto        t0 = std::chrono::steady_clock::now();
     int         rc = guarded([&] { json = run(); });
+    p->last_status = rc;
+    if (rc == KZP_ERR_CUDA)
+    {
+        // Not the client's fault: answer PROVER_NOT_READY, and when the device is gone for good take the handle out
+        // of service so that health checks and the pool see it (every later call answers NOT_READY at once).
+        std::string what = g_last_error;
+        if (device_is_dead())
+        {
+            p->state = KZP_STATE_DEVICE_FAULT;
+            p->why   = "CUDA device fault: " + what;
+        }
+        g_last_error = what;
+        return fail(KZP_PROVER_ERROR_NOT_READY);
+    }
     if (rc != KZP_OK)
-        return fail(KZP_PROVER_ERROR_INVALID_INPUT);
+        return fail(KZP_PROVER_ERROR_INVALID_INPUT); // KZP_ERR_FORMAT / KZP_ERR_IO: the witness is at fault
     auto t1 = std::chrono::steady_clock::now();
     if (prover_time_ms)
         *prover_time_ms = (int)std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count();
@@ -277,9 +304,15 @@ int kzp_prover_prove(kzp_prover* p, const char* wtns_path, const uint8_t* r32, c
                            prover_time_ms);
     });
     if (rc != KZP_OK)
+    {
+        p->last_status = rc;
         return fail(KZP_PROVER_ERROR_INVALID_INPUT);
+    }
     return ret;
 }
+
+int kzp_prover_state(const kzp_prover* p) { return p ? p->state : KZP_STATE_ZKEY_FILE_LOAD_ERROR; }
+int kzp_prover_last_status(const kzp_prover* p) { return p ? p->last_status : KZP_ERR_STATE; }
 
 #define KZP_REQUIRE_READY(p)                                                                     \
     if (!(p) || (p)->state != KZP_STATE_OK || !(p)->prover)                                        \
@@ -700,7 +733,7 @@ int kzp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t*
                  int device)
 {
     return guarded([&] {
-        if (field < 0 || field > 2 || op < 0 || op > 7)
+        if (field < 0 || field > 2 || op < 0 || op > 8 || (op == 8 && field == 2))
             throw FormatError("bad field/op");
         use_device(device);
         size_t esz = field == 2 ? 64 : 32;
@@ -857,6 +890,17 @@ static void host_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out)
     case 3: F::neg(r, x); break;
     case 6: F::sqr(r, x); break;
     case 7: F::inv(r, x); break;
+    case 8:
+        if constexpr (F::kFusedMulAdd2)
+            F::mul_add2(r, x, y, y, y);
+        else
+        {
+            F t, u;
+            F::mul(t, x, y);
+            F::mul(u, y, y);
+            F::add(r, t, u);
+        }
+        break;
     default: r = x;
     }
     memcpy(out, &r, sizeof(F));

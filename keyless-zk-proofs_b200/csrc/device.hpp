@@ -174,7 +174,7 @@ extern template struct MsmBases<G2Xyzz>;
 
 // ------------------------------------------------------------------ diagnostics / tests
 // elementwise field kernels: field 0 = Fr, 1 = Fq, 2 = Fq2; op: 0 mul 1 add 2 sub 3 neg 4 toMont 5 fromMont
-// 6 sqr 7 inv. Device pointers.
+// 6 sqr 7 inv 8 a*b + b*b (single-reduction dual product, prime fields only). Device pointers.
 void field_op(int field, int op, const void* a, const void* b, void* out, uint64_t count,
               cudaStream_t st);
 // out[i] = op(p[i], q[i]) on points; group 0 = G1, 1 = G2; op: 0 madd (xyzz += affine), 1 add (xyzz += xyzz),

@@ -23,6 +23,8 @@ struct alignas(16) Fp2T
     F a; // real part
     F b; // coefficient of u
 
+    static constexpr bool kFusedMulAdd2 = false; // the group law keeps the two-product form over Fq2
+
     static KZP_HD Fp2T zero()
     {
         Fp2T r;
@@ -245,10 +247,21 @@ struct alignas(16) XyzzT
         F::sub(acc.x, acc.x, PPP);
         F::sub(acc.x, acc.x, Q);
         F::sub(acc.x, acc.x, Q);
-        F::mul(t, acc.y, PPP);
-        F::sub(acc.y, Q, acc.x);
-        F::mul(acc.y, acc.y, R);
-        F::sub(acc.y, acc.y, t);
+        if constexpr (F::kFusedMulAdd2)
+        {
+            // y3 = (Q - x3) R - y1 PPP as ONE dual product with a single reduction (same residue, canonical)
+            F ny;
+            F::neg(ny, acc.y);
+            F::sub(t, Q, acc.x);
+            F::mul_add2(acc.y, t, R, ny, PPP);
+        }
+        else
+        {
+            F::mul(t, acc.y, PPP);
+            F::sub(acc.y, Q, acc.x);
+            F::mul(acc.y, acc.y, R);
+            F::sub(acc.y, acc.y, t);
+        }
         F::mul(acc.zz, acc.zz, PP);
         F::mul(acc.zzz, acc.zzz, PPP);
     }
@@ -289,10 +302,20 @@ struct alignas(16) XyzzT
         F::sub(acc.x, acc.x, PPP);
         F::sub(acc.x, acc.x, Q);
         F::sub(acc.x, acc.x, Q);
-        F::mul(t, S1, PPP);
-        F::sub(acc.y, Q, acc.x);
-        F::mul(acc.y, acc.y, R);
-        F::sub(acc.y, acc.y, t);
+        if constexpr (F::kFusedMulAdd2)
+        {
+            F ns;
+            F::neg(ns, S1);
+            F::sub(t, Q, acc.x);
+            F::mul_add2(acc.y, t, R, ns, PPP);
+        }
+        else
+        {
+            F::mul(t, S1, PPP);
+            F::sub(acc.y, Q, acc.x);
+            F::mul(acc.y, acc.y, R);
+            F::sub(acc.y, acc.y, t);
+        }
         F::mul(acc.zz, acc.zz, q.zz);
         F::mul(acc.zz, acc.zz, PP);
         F::mul(acc.zzz, acc.zzz, q.zzz);

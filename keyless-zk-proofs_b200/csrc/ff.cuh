@@ -73,6 +73,7 @@ struct alignas(16) Fp
     uint32_t v[8];
 
     typedef P Params;
+    static constexpr bool kFusedMulAdd2 = true; // mul_add2 is a single-reduction dual product (used by the group law)
 
     static KZP_HD Fp zero()
     {
@@ -417,7 +418,235 @@ struct alignas(16) Fp
 #endif
     }
 
-    static KZP_HD void sqr(Fp& r, const Fp& a) { mul(r, a, a); }
+#if defined(__CUDA_ARCH__)
+    // acc[0..2N) += {x0..x(N-1)} * b as one carry chain of N wide multiply-adds; returns the carry out of acc[2N-1]
+    static KZP_D uint32_t row1(uint32_t& a0, uint32_t& a1, uint32_t x0, uint32_t b)
+    {
+        uint32_t c;
+        asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+            "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+            "addc.u32 %2, 0, 0;"
+            : "+r"(a0), "+r"(a1), "=r"(c)
+            : "r"(x0), "r"(b));
+        return c;
+    }
+    static KZP_D uint32_t row2(uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3, uint32_t x0, uint32_t x1,
+                               uint32_t b)
+    {
+        uint32_t c;
+        asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+            "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+            "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+            "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+            "addc.u32 %4, 0, 0;"
+            : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "=r"(c)
+            : "r"(x0), "r"(x1), "r"(b));
+        return c;
+    }
+    static KZP_D uint32_t row3(uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3, uint32_t& a4, uint32_t& a5,
+                               uint32_t x0, uint32_t x1, uint32_t x2, uint32_t b)
+    {
+        uint32_t c;
+        asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+            "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+            "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+            "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+            "addc.u32 %6, 0, 0;"
+            : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "=r"(c)
+            : "r"(x0), "r"(x1), "r"(x2), "r"(b));
+        return c;
+    }
+    static KZP_D void wide(uint32_t& lo, uint32_t& hi, uint32_t x, uint32_t y)
+    {
+        uint64_t p = (uint64_t)x * y;
+        lo         = (uint32_t)p;
+        hi         = (uint32_t)(p >> 32);
+    }
+
+    // One Montgomery reduction round on T = X + (Y << 32) + pend: adds m * p with m chosen so that limb 0 cancels,
+    // divides by 2^32 and shifts `inject` in at limb 7 of the quotient (the next limb of a 512-bit operand, or 0).
+    static KZP_D void redc_round(uint32_t (&x)[8], uint32_t (&y)[8], uint32_t& pend, uint32_t inject)
+    {
+        uint32_t m = (x[0] + pend) * P::NP0;
+        chain_odd_pend(x[0], pend, y, P::P1, P::P3, P::P5, P::P7, m);
+        chain_even(x, y[7], P::P0, P::P2, P::P4, P::P6, m);
+        pend = x[1];
+        uint32_t t0 = y[0], t1 = y[1], t2 = y[2], t3 = y[3], t4 = y[4], t5 = y[5], t6 = y[6], t7 = y[7];
+        y[0] = x[2]; y[1] = x[3]; y[2] = x[4]; y[3] = x[5]; y[4] = x[6]; y[5] = x[7];
+        y[6] = inject; y[7] = 0;
+        x[0] = t0; x[1] = t1; x[2] = t2; x[3] = t3; x[4] = t4; x[5] = t5; x[6] = t6; x[7] = t7;
+    }
+
+    // r = pend + X + (Y << 32), brought below p by one conditional subtraction (the value is < 2p)
+    static KZP_D void merge_reduce(Fp& r, const uint32_t (&x)[8], const uint32_t (&y)[8], uint32_t pend)
+    {
+        uint32_t s0, s1, s2, s3, s4, s5, s6, s7;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+            : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]),
+              "r"(x[7]), "r"(pend), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]),
+              "r"(y[5]), "r"(y[6]));
+        uint32_t t0, t1, t2, t3, t4, t5, t6, t7, bw;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7),
+              "=r"(bw)
+            : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7), "r"(P::P0),
+              "r"(P::P1), "r"(P::P2), "r"(P::P3), "r"(P::P4), "r"(P::P5), "r"(P::P6), "r"(P::P7));
+        bool keep = (bw != 0);
+        r.v[0] = keep ? s0 : t0; r.v[1] = keep ? s1 : t1; r.v[2] = keep ? s2 : t2;
+        r.v[3] = keep ? s3 : t3; r.v[4] = keep ? s4 : t4; r.v[5] = keep ? s5 : t5;
+        r.v[6] = keep ? s6 : t6; r.v[7] = keep ? s7 : t7;
+    }
+#endif
+
+    // r = a^2 * R^-1 mod p, canonical (Fr_rawMSquare: fr_raw_generic.cpp:150-190 computes the same value).
+    // Device: the 28 off-diagonal products once (even- and odd-aligned accumulators as in mul), doubled, plus the
+    // 8 diagonal squares, then 8 reduction rounds: 28 + 8 + 64 = 100 wide multiply-adds instead of 128.
+    static KZP_HD void sqr(Fp& r, const Fp& a)
+    {
+#if defined(__CUDA_ARCH__)
+        const uint32_t a0 = a.v[0], a1 = a.v[1], a2 = a.v[2], a3 = a.v[3], a4 = a.v[4], a5 = a.v[5], a6 = a.v[6],
+                       a7 = a.v[7];
+        // O[k], E[k]: limb k of the odd- / even-aligned sums of a_i a_j, i < j (product i,j starts at limb i + j)
+        uint32_t O1, O2, O3, O4, O5, O6, O7, O8, O9, O10 = 0, O11, O12 = 0, O13, O14 = 0;
+        uint32_t E2, E3, E4, E5, E6, E7, E8 = 0, E9 = 0, E10, E11 = 0, E12, E13 = 0;
+        wide(O1, O2, a1, a0); wide(O3, O4, a3, a0); wide(O5, O6, a5, a0); wide(O7, O8, a7, a0);
+        wide(E2, E3, a2, a0); wide(E4, E5, a4, a0); wide(E6, E7, a6, a0);
+        O9 = row3(O3, O4, O5, O6, O7, O8, a2, a4, a6, a1);
+        (void)row3(E4, E5, E6, E7, E8, E9, a3, a5, a7, a1);
+        (void)row3(O5, O6, O7, O8, O9, O10, a3, a5, a7, a2);
+        E10 = row2(E6, E7, E8, E9, a4, a6, a2);
+        O11 = row2(O7, O8, O9, O10, a4, a6, a3);
+        (void)row2(E8, E9, E10, E11, a5, a7, a3);
+        (void)row2(O9, O10, O11, O12, a5, a7, a4);
+        E12 = row1(E10, E11, a6, a4);
+        O13 = row1(O11, O12, a6, a5);
+        (void)row1(E12, E13, a7, a5);
+        (void)row1(O13, O14, a7, a6);
+        // M = E + O (limbs 1..14), D = 2 M (limbs 1..15)
+        uint32_t M2, M3, M4, M5, M6, M7, M8, M9, M10, M11, M12, M13, M14;
+        asm("add.cc.u32 %0, %13, %26;\n\t"
+            "addc.cc.u32 %1, %14, %27;\n\t"
+            "addc.cc.u32 %2, %15, %28;\n\t"
+            "addc.cc.u32 %3, %16, %29;\n\t"
+            "addc.cc.u32 %4, %17, %30;\n\t"
+            "addc.cc.u32 %5, %18, %31;\n\t"
+            "addc.cc.u32 %6, %19, %32;\n\t"
+            "addc.cc.u32 %7, %20, %33;\n\t"
+            "addc.cc.u32 %8, %21, %34;\n\t"
+            "addc.cc.u32 %9, %22, %35;\n\t"
+            "addc.cc.u32 %10, %23, %36;\n\t"
+            "addc.cc.u32 %11, %24, %37;\n\t"
+            "addc.u32 %12, %25, 0;"
+            : "=r"(M2), "=r"(M3), "=r"(M4), "=r"(M5), "=r"(M6), "=r"(M7), "=r"(M8), "=r"(M9), "=r"(M10), "=r"(M11),
+              "=r"(M12), "=r"(M13), "=r"(M14)
+            : "r"(O2), "r"(O3), "r"(O4), "r"(O5), "r"(O6), "r"(O7), "r"(O8), "r"(O9), "r"(O10), "r"(O11), "r"(O12),
+              "r"(O13), "r"(O14), "r"(E2), "r"(E3), "r"(E4), "r"(E5), "r"(E6), "r"(E7), "r"(E8), "r"(E9), "r"(E10),
+              "r"(E11), "r"(E12), "r"(E13));
+        uint32_t T[16];
+        T[0]  = 0;
+        T[1]  = O1 << 1;
+        T[2]  = __funnelshift_l(O1, M2, 1);
+        T[3]  = __funnelshift_l(M2, M3, 1);
+        T[4]  = __funnelshift_l(M3, M4, 1);
+        T[5]  = __funnelshift_l(M4, M5, 1);
+        T[6]  = __funnelshift_l(M5, M6, 1);
+        T[7]  = __funnelshift_l(M6, M7, 1);
+        T[8]  = __funnelshift_l(M7, M8, 1);
+        T[9]  = __funnelshift_l(M8, M9, 1);
+        T[10] = __funnelshift_l(M9, M10, 1);
+        T[11] = __funnelshift_l(M10, M11, 1);
+        T[12] = __funnelshift_l(M11, M12, 1);
+        T[13] = __funnelshift_l(M12, M13, 1);
+        T[14] = __funnelshift_l(M13, M14, 1);
+        T[15] = M14 >> 31;
+        // T += sum a_i^2 2^(64 i): one chain of 8 wide multiply-adds over all 16 limbs
+        asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+            "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+            "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+            "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+            "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+            "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+            "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+            "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+            "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+            "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+            "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+            "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+            "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+            "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+            "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+            "madc.hi.u32 %15, %23, %23, %15;"
+            : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]),
+              "+r"(T[8]), "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7));
+        // Montgomery reduction of the 512-bit square, the upper limbs entering one per round
+        uint32_t x[8], y[8], pend = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            x[i] = T[i];
+            y[i] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            redc_round(x, y, pend, T[8 + i]);
+        // after the last round the injected limb sits at y[6] (limb 7 of the quotient): that is T[15], in place
+        merge_reduce(r, x, y, pend);
+#else
+        mul(r, a, a);
+#endif
+    }
+
+    // r = (a*b + c*d) * R^-1 mod p, canonical, with ONE reduction: 128 product + 64 reduction multiply-adds
+    // instead of 256 for two products and an addition. T stays < 3p*2^32 < 2^288 through the rounds and the
+    // result is < (2p^2 + Rp)/R < 2p.
+    static KZP_HD void mul_add2(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d)
+    {
+#if defined(__CUDA_ARCH__)
+        uint32_t x[8], y[8], pend = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            x[i] = 0;
+            y[i] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            uint32_t bi = b.v[i], di = d.v[i];
+            chain_odd_pend(x[0], pend, y, a.v[1], a.v[3], a.v[5], a.v[7], bi);
+            chain_even(x, y[7], a.v[0], a.v[2], a.v[4], a.v[6], bi);
+            chain_odd(y, c.v[1], c.v[3], c.v[5], c.v[7], di);
+            chain_even(x, y[7], c.v[0], c.v[2], c.v[4], c.v[6], di);
+            pend = 0; // folded into x[0] by chain_odd_pend
+            redc_round(x, y, pend, 0);
+        }
+        merge_reduce(r, x, y, pend);
+#else
+        Fp t, u;
+        mul(t, a, b);
+        mul(u, c, d);
+        add(r, t, u);
+#endif
+    }
 
     // canonical integer -> Montgomery (Fr_rawToMontgomery: fr_raw_generic.cpp:192-196)
     static KZP_HD void to_mont(Fp& r, const Fp& a)

@@ -9,7 +9,9 @@
 //     every call selects its CUDA device itself
 // Configuration comes from the environment because the header is frozen:
 //   KZP_DEVICE   CUDA device index (default 0)
-//   KZP_FIXED_RS 128 hex digits = r then s, 32 bytes each little-endian (tests only)
+//   KZP_FIXED_RS 128 hex digits = r then s, 32 bytes each little-endian — ONLY in a translation unit compiled with
+//                -DKZP_TEST_HOOKS (the ABI parity test builds its own copy of this file that way and links it in front
+//                of the library). The release library is built without it: fixing r and s removes zero-knowledge.
 //   KZP_LOG      when set, print the reference's stdout log lines (fullprover.cpp:67-78,237-238)
 #include <cstddef>
 #include <cstdio>
@@ -41,6 +43,7 @@ static_assert(offsetof(ProverResponse, raw_json) == 8 && offsetof(ProverResponse
                   offsetof(ProverResponse, metrics) == 20,
               "ProverResponse member offsets");
 
+#if defined(KZP_TEST_HOOKS)
 bool parse_fixed_rs(unsigned char* r, unsigned char* s)
 {
     const char* env = getenv("KZP_FIXED_RS");
@@ -68,6 +71,9 @@ bool parse_fixed_rs(unsigned char* r, unsigned char* s)
     }
     return true;
 }
+#else
+bool parse_fixed_rs(unsigned char*, unsigned char*) { return false; } // release build: r, s always come from the CSPRNG
+#endif
 
 void log_line(const char* level, const char* msg)
 {

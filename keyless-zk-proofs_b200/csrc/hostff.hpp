@@ -19,6 +19,8 @@ struct alignas(16) HostFp
 {
     uint64_t v[4];
 
+    static constexpr bool kFusedMulAdd2 = false;
+
     static uint64_t p(int i)
     {
         return (uint64_t)modulus_limb<P>(2 * i) | ((uint64_t)modulus_limb<P>(2 * i + 1) << 32);

@@ -406,6 +406,12 @@ __global__ void __launch_bounds__(128)
     case 3: F::neg(r, x); break;
     case 6: F::sqr(r, x); break;
     case 7: F::inv(r, x); break;
+    case 8: // a*b + b*b through the single-reduction dual product (prime fields)
+        if constexpr (F::kFusedMulAdd2)
+            F::mul_add2(r, x, y, y, y);
+        else
+            r = x;
+        break;
     default: r = x;
     }
     out[i] = r;

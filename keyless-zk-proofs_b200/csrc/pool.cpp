@@ -23,8 +23,19 @@ struct kzp_pool
     int                      state = KZP_STATE_OK;
     std::string              zkey_path;
     uint32_t                 n_public = 0;
-    std::atomic<int>         verify{0}; // verify every proof under the zkey's VK before returning it
+    std::atomic<int>         verify{0};    // verify every proof under the zkey's VK before returning it
+    std::atomic<int>         in_flight{0}; // callers inside pool_run (queueing, proving or verifying)
 };
+
+namespace
+{
+struct InFlight
+{
+    std::atomic<int>& n;
+    explicit InFlight(std::atomic<int>& c) : n(c) { n.fetch_add(1); }
+    ~InFlight() { n.fetch_sub(1); }
+};
+} // namespace
 
 static std::vector<int> pool_devices(const int* devices, int n)
 {
@@ -101,10 +112,11 @@ void kzp_pool_free(kzp_pool* pool)
     if (pool->sched)
     {
         pool->sched->close();
-        // proofs in flight hold their slot until they return; wait for them before tearing the provers down
-        while (pool->sched->busy() > 0)
-            std::this_thread::sleep_for(std::chrono::milliseconds(1));
     }
+    // Every caller that entered pool_run — still queueing (woken by close()), proving, or in the verify step, which
+    // reads the pool after its slot went back — must have left before anything is destroyed.
+    while (pool->in_flight.load() > 0)
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
     for (kzp_prover* p : pool->provers)
         kzp_prover_free(p);
     delete pool->sched;
@@ -112,6 +124,16 @@ void kzp_pool_free(kzp_pool* pool)
 }
 
 int kzp_pool_size(const kzp_pool* pool) { return pool ? (int)pool->provers.size() : 0; }
+
+int kzp_pool_healthy(const kzp_pool* pool)
+{
+    if (!pool || pool->state != KZP_STATE_OK)
+        return 0;
+    int n = 0;
+    for (kzp_prover* p : pool->provers)
+        n += kzp_prover_state(p) == KZP_STATE_OK ? 1 : 0;
+    return n;
+}
 
 int kzp_pool_device(const kzp_pool* pool, int slot)
 {
@@ -147,7 +169,8 @@ static int pool_run(kzp_pool* pool, char** json_out, int* error_out, int* prover
             *error_out = KZP_PROVER_ERROR_NOT_READY;
         return KZP_RESPONSE_ERROR;
     }
-    int slot = pool->sched->acquire();
+    InFlight guard(pool->in_flight);
+    int      slot = pool->sched->acquire();
     if (slot < 0)
     {
         if (error_out)
@@ -156,21 +179,34 @@ static int pool_run(kzp_pool* pool, char** json_out, int* error_out, int* prover
     }
     if (slot_out)
         *slot_out = slot;
-    int rc = run(pool->provers[slot]);
-    pool->sched->release(slot);
+    kzp_prover* prover = pool->provers[slot];
+    int         rc     = run(prover);
+    // a prover whose device faulted is taken out of rotation instead of answering every later request with an error
+    if (kzp_prover_state(prover) != KZP_STATE_OK)
+        pool->sched->retire(slot);
+    else
+        pool->sched->release(slot);
     if (rc == KZP_RESPONSE_SUCCESS && pool->verify.load() && json_out && *json_out)
     {
-        std::vector<uint8_t> pub((size_t)pool->n_public * 32);
-        int                  valid = 0;
-        bool                 ok    = publics(pub.data(), pool->n_public) &&
-                  kzp_host_verify(pool->zkey_path.c_str(), *json_out, pub.data(), pool->n_public, &valid) == KZP_OK && valid;
-        if (!ok)
-        {
+        auto drop = [&](int err) {
             kzp_free(*json_out);
             *json_out = nullptr;
             if (error_out)
-                *error_out = KZP_PROVER_ERROR_INVALID_INPUT; // the witness does not satisfy the circuit
+                *error_out = err;
             return KZP_RESPONSE_ERROR;
+        };
+        std::vector<uint8_t> pub((size_t)pool->n_public * 32);
+        int                  valid = 0;
+        if (!publics(pub.data(), pool->n_public))
+            return drop(KZP_PROVER_ERROR_INVALID_INPUT); // the witness has no public signals to check against
+        if (kzp_host_verify(pool->zkey_path.c_str(), *json_out, pub.data(), pool->n_public, &valid) != KZP_OK)
+            return drop(KZP_PROVER_ERROR_NOT_READY); // the verifier could not run (zkey unreadable, malformed proof)
+        if (!valid)
+        {
+            // The prover returned a well-formed proof that does not verify. With a healthy device that is a witness
+            // which does not satisfy the circuit (the client's fault); a device that has faulted since then is ours.
+            return drop(kzp_prover_state(prover) == KZP_STATE_OK ? KZP_PROVER_ERROR_INVALID_INPUT
+                                                                 : KZP_PROVER_ERROR_NOT_READY);
         }
     }
     return rc;

@@ -20,7 +20,7 @@ namespace kzp
 class SlotScheduler
 {
   public:
-    explicit SlotScheduler(int slots) : jobs_(slots > 0 ? slots : 0, 0)
+    explicit SlotScheduler(int slots) : jobs_(slots > 0 ? slots : 0, 0), alive_(slots > 0 ? slots : 0)
     {
         for (int i = 0; i < slots; i++)
             free_.push_back(i);
@@ -34,8 +34,8 @@ class SlotScheduler
         uint64_t                     depth  = next_ticket_ - serving_;
         if (depth > max_waiting_)
             max_waiting_ = depth;
-        cv_.wait(lk, [&] { return closed_ || (ticket == serving_ && !free_.empty()); });
-        if (closed_)
+        cv_.wait(lk, [&] { return closed_ || alive_ == 0 || (ticket == serving_ && !free_.empty()); });
+        if (closed_ || alive_ == 0)
         {
             // keep the queue moving for the waiters behind this one
             if (ticket == serving_)
@@ -56,6 +56,18 @@ class SlotScheduler
         {
             std::lock_guard<std::mutex> lk(m_);
             free_.push_back(slot);
+        }
+        cv_.notify_all();
+    }
+
+    // The slot's prover is out of service (device fault): it is never handed out again. When the last slot is retired
+    // every waiter and every later acquire() gets -1.
+    void retire(int slot)
+    {
+        (void)slot;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            alive_--;
         }
         cv_.notify_all();
     }
@@ -81,11 +93,16 @@ class SlotScheduler
         std::lock_guard<std::mutex> lk(m_);
         return max_waiting_;
     }
-    // number of slots currently handed out
+    // number of slots currently handed out (retired slots are neither free nor busy)
     int busy()
     {
         std::lock_guard<std::mutex> lk(m_);
-        return (int)jobs_.size() - (int)free_.size();
+        return alive_ - (int)free_.size();
+    }
+    int alive()
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        return alive_;
     }
 
   private:
@@ -93,6 +110,7 @@ class SlotScheduler
     std::condition_variable cv_;
     std::deque<int>         free_;
     std::vector<uint64_t>   jobs_;
+    int                     alive_       = 0; // slots not retired
     uint64_t                next_ticket_ = 0, serving_ = 0, max_waiting_ = 0;
     bool                    closed_      = false;
 };

@@ -7,11 +7,12 @@
 #include <memory>
 #include <mutex>
 #include <unistd.h>
+#include <cerrno>
+#include <sys/random.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <random>
 #include <thread>
 #include <vector>
 #if defined(__x86_64__)
@@ -72,17 +73,31 @@ bool fr_bytes_geq_modulus(const uint8_t* b)
     return HFr::geq_p(t);
 }
 
+// 32 bytes from the kernel CSPRNG (the reference uses libsodium's randombytes_buf, random_generator.hpp:4-8, which
+// reads the same source). The zero-knowledge of every proof rests on r and s: no fallback to a userspace PRNG; if
+// the kernel cannot deliver, the proof fails with a CudaError-class (service-side) error.
+void csprng_bytes(uint8_t* out, size_t n)
+{
+    size_t got = 0;
+    while (got < n)
+    {
+        ssize_t k = ::getrandom(out + got, n - got, 0);
+        if (k < 0)
+        {
+            if (errno == EINTR)
+                continue;
+            throw CudaError(std::string("getrandom failed: ") + strerror(errno));
+        }
+        got += (size_t)k;
+    }
+}
+
 void sample_blinding(uint8_t* out32)
 {
     // groth16.cpp:296-316: 32 random bytes, clear the top two bits, reject values >= r
-    std::random_device rd;
     for (;;)
     {
-        for (int i = 0; i < 8; i++)
-        {
-            uint32_t v = rd();
-            memcpy(out32 + 4 * i, &v, 4);
-        }
+        csprng_bytes(out32, 32);
         out32[31] &= 0x3f;
         if (!fr_bytes_geq_modulus(out32))
             return;
@@ -647,6 +662,21 @@ public:
     {
         if (world < 1 || rank < 0 || rank >= world)
             throw FormatError("invalid shard rank/world");
+        // a constructor that throws half-way (CSR out of range, log_n > 27, out of memory) must not leak the streams,
+        // events and device buffers it already made: the destructor does not run for a partly built object
+        try
+        {
+            construct(path);
+        }
+        catch (...)
+        {
+            teardown();
+            throw;
+        }
+    }
+
+    void construct(const std::string& path)
+    {
         MappedFile file(path);
         BinView    bin(file.data(), file.size(), "zkey", 1);
         ZkeyHeader zh = parse_zkey(bin);
@@ -725,10 +755,16 @@ public:
         KZP_CUDA_CHECK(cudaDeviceSynchronize());
     }
 
-    ~DeviceProverImpl()
+    ~DeviceProverImpl() { teardown(); }
+
+    void teardown()
     {
         pool.reset();
-        cudaSetDevice(device);
+        if (cudaSetDevice(device) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return; // no such device: nothing was allocated
+        }
         cudaDeviceSynchronize();
         msm_bases_destroy(bases_a);
         msm_bases_destroy(bases_b1);
@@ -757,11 +793,12 @@ public:
         cudaFreeHost(pinned_w);
         cudaFreeHost(pinned_out);
         for (auto& e : ev)
-            cudaEventDestroy(e);
-        cudaStreamDestroy(st_h);
-        cudaStreamDestroy(st_w);
-        cudaStreamDestroy(st_w2);
-        cudaStreamDestroy(st_copy);
+            if (e)
+                cudaEventDestroy(e);
+        for (cudaStream_t* s : {&st_h, &st_w, &st_w2, &st_copy})
+            if (*s)
+                cudaStreamDestroy(*s);
+        cudaGetLastError();
     }
 
     // Host -> pinned staging -> device, pipelined: worker threads classify and pack slices of kPackWires values into

@@ -121,7 +121,7 @@ int kzp_host_verify(const char* zkey_path, const char* proof_json, const uint8_t
             return KZP_ERR_FORMAT;
         }
         const Section& ic = bin.section(3);
-        if (ic.size < 64ull * (n_public + 1))
+        if (ic.size < 64ull * ((uint64_t)n_public + 1))
             throw FormatError("zkey IC section too short");
 
         // proof points (Proof::toJson layout, groth16.cpp:379-410): pi_a [x, y, 1], pi_b [[x.a, x.b], [y.a, y.b], [1, 0]]

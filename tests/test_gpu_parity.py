@@ -40,7 +40,8 @@ def test_field_ops(gpu, kzp, oracle, field):
     want = {0: [o.mont_mul(x, y, mod) for x, y in zip(a, b)], 1: [(x + y) % mod for x, y in zip(a, b)],
             2: [(x - y) % mod for x, y in zip(a, b)], 3: [(-x) % mod for x in a],
             4: [o.to_mont(x, mod) for x in a], 5: [o.from_mont(x, mod) for x in a],
-            6: [o.mont_mul(x, x, mod) for x in a]}
+            6: [o.mont_mul(x, x, mod) for x in a],
+            8: [(o.mont_mul(x, y, mod) + o.mont_mul(y, y, mod)) % mod for x, y in zip(a, b)]}  # dual product, one reduction
     for op, w in want.items():
         got = _ints(o, kzp.field_op(field, op, A, B))
         assert got == w, "field %d op %d" % (field, op)
@@ -452,11 +453,13 @@ def test_error_behaviour(gpu, kzp, oracle, workdir):
 
 
 def test_cxx_abi_drop_in(gpu, kzp, oracle, workdir):
-    """The Itanium-ABI class the Rust binding links against (include/fullprover_b200.hpp), driven from C++ with the
-    blinding scalars injected through KZP_FIXED_RS: same bytes as the reference."""
+    """The Itanium-ABI class the Rust binding links against (include/fullprover_b200.hpp), driven from C++.
+    (1) Through the RELEASE library: its shim ignores KZP_FIXED_RS (compiled out), so the proof differs from the
+    recorded one but verifies under the circuit's VK. (2) Through a test build of the same shim source
+    (-DKZP_TEST_HOOKS, linked in front of the library) with r, s injected: the reference's bytes."""
     toy = os.path.join(GOLDEN, "toy")
     exp = json.load(open(os.path.join(toy, "expected.json")))
-    src, exe = os.path.join(workdir, "abi_run.cpp"), os.path.join(workdir, "abi_run")
+    src = os.path.join(workdir, "abi_run.cpp")
     open(src, "w").write(r'''
 #include <cstdio>
 #include <cstring>
@@ -469,13 +472,23 @@ int main(int argc, char** argv) {
     return 0;
 }
 ''')
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
-                           kzp.LIB_PATH, "-Wl,-rpath," + os.path.dirname(kzp.LIB_PATH)])
+    inc = os.path.join(ROOT, "include")
+    shim = os.path.join(ROOT, "keyless-zk-proofs_b200", "csrc", "fullprover_abi.cu")
+    link = [kzp.LIB_PATH, "-Wl,-rpath," + os.path.dirname(kzp.LIB_PATH)]
+    rel, hooked = os.path.join(workdir, "abi_run"), os.path.join(workdir, "abi_run_hooked")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", inc, src, "-o", rel] + link)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-DKZP_TEST_HOOKS", "-I", inc, src, "-x", "c++", shim, "-o", hooked] + link)
     env = dict(os.environ, KZP_FIXED_RS=exp["r"] + exp["s"])
-    out = subprocess.check_output([exe, os.path.join(toy, "toy_1.zkey"), os.path.join(toy, "toy.wtns")], text=True, env=env)
-    state, rtype, err, js = out.strip().split(" ", 3)
+    args = [os.path.join(toy, "toy_1.zkey"), os.path.join(toy, "toy.wtns")]
+    state, rtype, err, js = subprocess.check_output([hooked] + args, text=True, env=env).strip().split(" ", 3)
     assert (state, rtype, err) == ("0", "0", "0")
     assert js == exp["proof"]
+    state, rtype, err, js = subprocess.check_output([rel] + args, text=True, env=env).strip().split(" ", 3)
+    assert (state, rtype, err) == ("0", "0", "0")
+    assert js != exp["proof"], "the release shim honoured KZP_FIXED_RS"
+    zk = oracle.read_zkey(args[0])
+    pa, pb, pc = oracle.proof_from_json(js)
+    assert oracle.groth16_verify(oracle.vk_from_zkey(zk), exp["public"], pa, pb, pc)
 
 
 @pytest.mark.slow

@@ -62,7 +62,8 @@ def test_host_field_ops_match_oracle(kzp, oracle):
             if i % 13 == 0:
                 b = 0
             for op, want in ((0, oracle.mont_mul(a, b, mod)), (1, (a + b) % mod), (2, (a - b) % mod), (3, (-a) % mod),
-                             (4, oracle.to_mont(a, mod)), (5, oracle.from_mont(a, mod)), (6, oracle.mont_mul(a, a, mod))):
+                             (4, oracle.to_mont(a, mod)), (5, oracle.from_mont(a, mod)), (6, oracle.mont_mul(a, a, mod)),
+                             (8, (oracle.mont_mul(a, b, mod) + oracle.mont_mul(b, b, mod)) % mod)):
                 out = ctypes.create_string_buffer(32)
                 assert L.kzp_host_field_op(field, op, oracle.le32(a), oracle.le32(b), out) == 0
                 assert oracle.from_le(out.raw) == want, (field, op, hex(a), hex(b))
@@ -227,6 +228,54 @@ int main(int argc, char** argv) {
     out = subprocess.check_output([exe, "/nonexistent/k.zkey"], text=True).split()
     # state ZKEY_FILE_LOAD_ERROR(1), response ERROR(1), error PROVER_NOT_READY(1)
     assert out[:3] == ["1", "1", "1"]
+
+
+REF_HEADER_DIR = "/root/reference/rust-rapidsnark/rapidsnark/src"
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF_HEADER_DIR, "fullprover.hpp")),
+                    reason="the reference tree is only mounted in the build container")
+def test_cxx_abi_against_reference_header(kzp, workdir):
+    """A translation unit compiled against the REFERENCE'S OWN rust-rapidsnark/rapidsnark/src/fullprover.hpp (what
+    bindgen reads, build.rs:183-206) links against libkzp_b200.so: every constructor, destructor and prove() symbol the
+    reference header declares resolves in the library, the object layouts it implies are the ones the library was
+    built for, and the no-GPU behaviour is the reference's (state instead of exception, PROVER_NOT_READY)."""
+    src = os.path.join(workdir, "abi_ref.cpp")
+    exe = os.path.join(workdir, "abi_ref")
+    open(src, "w").write(r'''
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include "fullprover.hpp"   // the reference's header, not the repo's re-declaration
+static_assert(sizeof(FullProver) == 16, "FullProver size");
+static_assert(sizeof(ProverResponse) == 24, "ProverResponse size");
+static_assert(offsetof(ProverResponse, raw_json) == 8 && offsetof(ProverResponse, error) == 16 &&
+              offsetof(ProverResponse, metrics) == 20, "ProverResponse member offsets");
+static_assert(sizeof(ProverResponseMetrics) == 4, "metrics");
+static_assert((int)SUCCESS == 0 && (int)ERROR == 1, "ProverResponseType");
+static_assert((int)OK == 0 && (int)ZKEY_FILE_LOAD_ERROR == 1 && (int)UNSUPPORTED_ZKEY_CURVE == 2, "FullProverState");
+static_assert((int)NONE == 0 && (int)PROVER_NOT_READY == 1 && (int)INVALID_INPUT == 2 &&
+              (int)WITNESS_GENERATION_INVALID_CURVE == 3, "ProverError");
+int main(int argc, char** argv) {
+    FullProver p(argv[1]);
+    int state; memcpy(&state, reinterpret_cast<char*>(&p) + 8, 4);
+    ProverResponse r = p.prove("/nonexistent.wtns");
+    ProverResponse e(INVALID_INPUT);
+    printf("%d %d %d %d [%s] %d\n", state, (int)r.type, (int)r.error, r.metrics.prover_time, r.raw_json, (int)e.error);
+    return 0;
+}
+''')
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", REF_HEADER_DIR, src, "-o", exe,
+                           kzp.LIB_PATH, "-Wl,-rpath," + os.path.dirname(kzp.LIB_PATH)])
+    # the executable's undefined FullProver / ProverResponse symbols are exactly the library's exported ones
+    und = {l.split()[-1] for l in subprocess.check_output(["nm", "-u", exe], text=True).splitlines()
+           if "FullProver" in l or "ProverResponse" in l}
+    dyn = {l.split()[-1] for l in subprocess.check_output(["nm", "-D", "--defined-only", kzp.LIB_PATH], text=True).splitlines()}
+    assert und and und <= dyn, und - dyn
+    assert {"_ZN10FullProverC1EPKc", "_ZN10FullProverD1Ev", "_ZNK10FullProver5proveEPKc"} <= und
+    if kzp.device_count() == 0:
+        out = subprocess.check_output([exe, "/nonexistent/k.zkey"], text=True).split()
+        assert out[:3] == ["1", "1", "1"] and out[-1] == "2"
 
 
 def test_pool_checkout_queue(kzp):
