@@ -157,6 +157,9 @@ int kzp_fr_ntt_bench(uint32_t log_n, int iters, int device, float* ms_per_chain)
 typedef struct kzp_msm kzp_msm;
 /* group: 0 = G1 (64-byte bases), 1 = G2 (128-byte bases); bases affine Montgomery, (0,0) = infinity */
 kzp_msm* kzp_msm_new(int group, const uint8_t* bases, uint64_t n, int device);
+/* window_bits: signed-digit window size c, 16..22 (0 = default 16, or $KZP_MSM_WINDOW): W = ceil(255 / c) table
+ * windows share one set of 2^(c-1) buckets. two_level != 0 forces the two-pass digit sort (always used for c != 16). */
+kzp_msm* kzp_msm_new_ex(int group, const uint8_t* bases, uint64_t n, int device, int window_bits, int two_level);
 void     kzp_msm_free(kzp_msm* m);
 /* scalars: n x 32-byte LE integers; out: affine canonical LE (64 / 128 bytes), zeros for infinity */
 int kzp_msm_run(kzp_msm* m, const uint8_t* scalars, uint8_t* out);

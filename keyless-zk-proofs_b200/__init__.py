@@ -131,6 +131,10 @@ def lib() -> ctypes.CDLL:
         "kzp_fr_coset_chain": (c.c_int, [u8p, c.c_uint64, c.c_int]),
         "kzp_fr_ntt_bench": (c.c_int, [c.c_uint32, c.c_int, c.c_int, c.POINTER(c.c_float)]),
         "kzp_msm_new": (vp, [c.c_int, u8p, c.c_uint64, c.c_int]),
+        "kzp_msm_new_ex": (vp, [c.c_int, u8p, c.c_uint64, c.c_int, c.c_int, c.c_int]),
+        "kzp_prover_state": (c.c_int, [vp]),
+        "kzp_prover_last_status": (c.c_int, [vp]),
+        "kzp_pool_healthy": (c.c_int, [vp]),
         "kzp_msm_free": (None, [vp]),
         "kzp_msm_run": (c.c_int, [vp, u8p, u8p]),
         "kzp_msm_bench": (c.c_int, [vp, u8p, c.c_int, c.POINTER(c.c_float), c.POINTER(c.c_uint64)]),
@@ -413,11 +417,16 @@ def fr_ntt_bench(log_n: int, iters: int = 10, device: int = -1) -> float:
 class Msm:
     """Curve::multiMulByScalar (curve.hpp:209-215) with the bases resident on the GPU."""
 
-    def __init__(self, group: int, bases: bytes, device: int = -1):
+    def __init__(self, group: int, bases: bytes, device: int = -1, window_bits: int = 0, two_level: bool = False):
+        """window_bits: signed-digit window size (16..22; 0 = the default, 16); two_level forces the two-pass digit
+        sort that every window size other than 16 uses."""
         self.group = group
         self.point_bytes = 64 if group == 0 else 128
         self.n = len(bases) // self.point_bytes
-        self._h = lib().kzp_msm_new(group, bases, self.n, device)
+        if window_bits or two_level:
+            self._h = lib().kzp_msm_new_ex(group, bases, self.n, device, window_bits, 1 if two_level else 0)
+        else:
+            self._h = lib().kzp_msm_new(group, bases, self.n, device)
         if not self._h:
             raise KzpError("kzp_msm_new failed: " + last_error())
 

@@ -594,10 +594,21 @@ static void msm_launch(kzp_msm* m, const uint32_t* scalars)
 
 kzp_msm* kzp_msm_new(int group, const uint8_t* bases, uint64_t n, int device)
 {
+    const char* env = getenv("KZP_MSM_WINDOW");
+    return kzp_msm_new_ex(group, bases, n, device, env ? atoi(env) : 0, 0);
+}
+
+kzp_msm* kzp_msm_new_ex(int group, const uint8_t* bases, uint64_t n, int device, int window_bits, int two_level)
+{
     kzp_msm* m  = nullptr;
     int      rc = guarded([&] {
         if (group != 0 && group != 1)
             throw FormatError("group must be 0 (G1) or 1 (G2)");
+        if (window_bits == 0)
+            window_bits = 16;
+        if (window_bits < (int)kMsmMinWindowBits || window_bits > (int)kMsmMaxWindowBits)
+            throw FormatError("window_bits must be 0 (default) or 16..22");
+        const uint32_t c = (uint32_t)window_bits;
         use_device(device);
         m         = new kzp_msm();
         m->group  = group;
@@ -605,14 +616,14 @@ kzp_msm* kzp_msm_new(int group, const uint8_t* bases, uint64_t n, int device)
         m->n      = n;
         if (group == 0)
         {
-            msm_bases_create<G1Xyzz>(m->b1, bases, n, true, 0);
-            msm_sort_create(m->sort, m->b1.n, m->b1.scalar_idx, 0);
+            msm_bases_create<G1Xyzz>(m->b1, bases, n, true, 0, c);
+            msm_sort_create(m->sort, m->b1.n, m->b1.scalar_idx, 0, c, two_level != 0);
             msm_scratch_create<G1Xyzz>(m->s1, m->sort, 0);
         }
         else
         {
-            msm_bases_create<G2Xyzz>(m->b2, bases, n, true, 0);
-            msm_sort_create(m->sort, m->b2.n, m->b2.scalar_idx, 0);
+            msm_bases_create<G2Xyzz>(m->b2, bases, n, true, 0, c);
+            msm_sort_create(m->sort, m->b2.n, m->b2.scalar_idx, 0, c, two_level != 0);
             msm_scratch_create<G2Xyzz>(m->s2, m->sort, 0);
         }
     });
@@ -722,7 +733,7 @@ int kzp_msm_bench(kzp_msm* m, const uint8_t* scalars, int iters, float* ms_per_m
         if (entries)
         {
             uint32_t total = 0;
-            KZP_CUDA_CHECK(cudaMemcpy(&total, m->sort.offsets + kMsmBuckets + 1, 4, cudaMemcpyDeviceToHost));
+            KZP_CUDA_CHECK(cudaMemcpy(&total, m->sort.offsets + m->sort.shape.buckets + 1, 4, cudaMemcpyDeviceToHost));
             *entries = total;
         }
     });

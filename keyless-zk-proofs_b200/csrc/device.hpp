@@ -74,14 +74,34 @@ void spmv_abc(const CoefCsr& m, const Fr* w, Fr* a, Fr* b, Fr* c, cudaStream_t s
 void h_pointwise(const Fr* a, const Fr* b, const Fr* c, Fr* h, uint64_t n, cudaStream_t st);
 
 // ------------------------------------------------------------------ MSM
-// Signed 16-bit windows, 16 windows, and a per-key table of 2^(16 j) * P_i so that all windows share
-// ONE bucket set (2^15 buckets): bucket reduction and window combination happen once per MSM.
+// Signed c-bit windows and a per-key table of 2^(c j) * P_i, j < W = ceil(255 / c), so that all windows share ONE
+// bucket set (2^(c-1) buckets): bucket reduction and window combination happen once per MSM, and with the table
+// resident in HBM the number of mixed additions per scalar is W, whatever c is. c = 16 (16 windows, 2^15 buckets)
+// suits the witness MSMs, whose scalars are mostly single digits; the H MSM, whose scalars are uniform 254-bit
+// values, runs c = 20 (13 windows, 2^19 buckets: 19 % fewer additions).
 // The digit sort of a scalar vector (MsmSort) is separate from the group-specific part so that the
 // MSMs that share scalars (A, B1, C in G1 and B2 in G2 all run over the witness, groth16.cpp:88-112)
 // sort once and run their bucket work as one batched launch per stage.
-constexpr int      kMsmWindowBits   = 16;
-constexpr int      kMsmWindows      = 16;
-constexpr uint32_t kMsmBuckets      = 1u << (kMsmWindowBits - 1); // bucket ids 1..kMsmBuckets
+struct MsmShape
+{
+    uint32_t c       = 16;       // window bits
+    uint32_t windows = 16;       // ceil(255 / c): a scalar below r < 2^254 plus the signed-digit carry
+    uint32_t buckets = 1u << 15; // 2^(c-1), bucket ids 1..buckets
+    uint32_t levels  = 3;        // base-32 digits of a bucket index: ceil((c - 1) / 5)
+};
+inline MsmShape msm_shape(uint32_t c)
+{
+    MsmShape s;
+    s.c       = c;
+    s.windows = (255 + c - 1) / c;
+    s.buckets = 1u << (c - 1);
+    s.levels  = (c - 1 + 4) / 5;
+    return s;
+}
+constexpr uint32_t kMsmMinWindowBits = 16;   // W = ceil(255 / c) <= 16: the window index is a 4-bit field of a sorted entry
+constexpr uint32_t kMsmMaxWindowBits = 22;
+constexpr uint32_t kMsmMaxWindows    = 16;
+constexpr int      kMsmMaxLevels     = 5;
 constexpr int      kMsmMaxBatch     = 3;                           // MSMs per batched launch
 constexpr uint32_t kMsmHeavyRecords = 8;    // a bucket with more partial sums than max(this, 2 x average) is "heavy":
                                             // pre-reduced by whole blocks instead of one finalise thread
@@ -92,52 +112,64 @@ constexpr uint32_t kMsmMaxHeavy     = 1024; // heavy buckets handled that way (t
 constexpr uint32_t kMsmEntryBaseBits = 27;  // sorted entry = base | window << 27 | sign << 31
 constexpr uint32_t kMsmEntryBaseMask = (1u << kMsmEntryBaseBits) - 1u;
 constexpr uint32_t kMsmFoldBlock    = 128;  // buckets per block of the finalise+fold kernel
-constexpr int      kMsmFoldLevels   = (kMsmWindowBits - 1 + 4) / 5; // base-32 digits of a bucket index
 
 struct MsmSort
 {
+    MsmShape  shape;
     uint32_t  n             = 0;       // scalars covered
     uint32_t  scalar_offset = 0;       // scalar index of element 0 when scalar_idx == nullptr
     const uint32_t* scalar_idx = nullptr; // optional gather list (n entries, not owned)
     uint32_t  cap_entries   = 0;
-    uint32_t* counts        = nullptr; // kMsmBuckets + 2
-    uint32_t* offsets       = nullptr; // kMsmBuckets + 2 (offsets[b] = first entry of bucket b; [B+1] = total)
-    uint32_t* cursor        = nullptr; // kMsmBuckets + 2
+    uint32_t* counts        = nullptr; // buckets + 2
+    uint32_t* offsets       = nullptr; // buckets + 2 (offsets[b] = first entry of bucket b; [B+1] = total)
+    uint32_t* cursor        = nullptr; // buckets + 2
     uint32_t* sorted        = nullptr; // cap_entries
-    uint32_t* cta_hist      = nullptr; // sort_ctas x (kMsmBuckets + 1): per-CTA bucket histograms
+    // one-level path (c == 16): per-CTA shared-memory histograms over all 2^15 buckets, global cursors
+    uint32_t* cta_hist      = nullptr; // sort_ctas x (buckets + 1): per-CTA bucket histograms
     uint32_t  sort_ctas     = 0;       // CTAs of the histogram pass (one per SM at most)
     uint32_t  per_cta       = 0;       // scalars per CTA (multiple of the block size)
+    // two-level path (any c): partition by the high bucket bits through shared-memory staging, then one CTA sorts
+    // each partition by the low bits in shared memory; every global write is part of a contiguous run
+    bool      two_level     = false;
+    uint32_t  part_bits     = 0;       // partitions = 2^part_bits, sub-buckets per partition = buckets >> part_bits
+    uint32_t* part_cnt      = nullptr; // partitions + 1 counts, then offsets (exclusive scan; [P] = total)
+    uint32_t* part_cursor   = nullptr; // partitions
+    uint2*    inter         = nullptr; // cap_entries records (entry, bucket index - 1) grouped by partition
 };
 
 template <class XY>
 struct MsmBases
 {
     typedef typename XY::Affine Affine;
+    MsmShape  shape;
     uint32_t  n          = 0;       // table columns (bases kept)
     uint32_t* scalar_idx = nullptr; // n, only when infinity bases were filtered out: scalar index of each kept base
     uint8_t*  skip       = nullptr; // n, only when infinity columns were kept: 1 = column is infinity
-    Affine*   table      = nullptr; // kMsmWindows x n affine points: table[j*n + i] = 2^(16 j) * P_i
+    Affine*   table      = nullptr; // windows x n affine points: table[j*n + i] = 2^(c j) * P_i
 };
 
 template <class XY>
 struct MsmScratch
 {
+    MsmShape  shape;
     uint32_t  chunk         = 32;      // sorted entries per accumulate thread (per MSM: G2 wants smaller chunks)
     uint32_t* heavy_count   = nullptr; // 1: number of heavy buckets of the current sort at this chunk size
     uint32_t* heavy_ids     = nullptr; // kMsmMaxHeavy
-    uint32_t* heavy_slot    = nullptr; // kMsmBuckets + 2: 0 = light bucket, k + 1 = k-th heavy bucket
-    XY*       records       = nullptr; // cap_entries / chunk + kMsmBuckets + 2 partial sums, grouped by bucket
+    uint32_t* heavy_slot    = nullptr; // buckets + 2: 0 = light bucket, k + 1 = k-th heavy bucket
+    XY*       records       = nullptr; // cap_entries / chunk + buckets + 2 partial sums, grouped by bucket
     XY*       heavy_partial = nullptr; // kMsmMaxHeavy x kMsmHeavyBlocks
     XY*       heavy_sum     = nullptr; // kMsmMaxHeavy
     uint32_t* heavy_done    = nullptr; // kMsmMaxHeavy arrival counters (self-resetting)
-    XY*       s0part        = nullptr; // (kMsmBuckets / kMsmFoldBlock) x 32 : per block, per low digit
-    XY*       s1part        = nullptr; // (kMsmBuckets / kMsmFoldBlock) x 4  : per block, per warp
-    XY*       classes       = nullptr; // kMsmFoldLevels x 32 weighted class sums
+    XY*       s0part        = nullptr; // (buckets / kMsmFoldBlock) x 32 : per block, per low digit
+    XY*       s1part        = nullptr; // (buckets / kMsmFoldBlock) x 4  : per block, per warp
+    XY*       classes       = nullptr; // levels x 32 weighted class sums
     XY*       result        = nullptr; // 1 (device)
     cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr; // bracket the bucket-accumulation kernel of the last run
 };
 
-void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_t scalar_offset);
+// window_bits: 16 = the one-level sort; anything else (kMsmMinWindowBits..kMsmMaxWindowBits) the two-level sort
+void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_t scalar_offset, uint32_t window_bits = 16,
+                     bool force_two_level = false);
 void msm_sort_destroy(MsmSort& s);
 // scalars: device array of 32-byte little-endian integers (canonical or not; reduced mod r on the fly).
 void msm_sort_run(MsmSort& s, const uint32_t* scalars, cudaStream_t st);
@@ -148,7 +180,7 @@ uint32_t msm_default_chunk(uint64_t n);
 // otherwise all `count` columns are kept (infinity columns are all-zero and cost one load per digit).
 template <class XY>
 void msm_bases_create(MsmBases<XY>& out, const uint8_t* points_host, uint64_t count, bool filter_inf,
-                      cudaStream_t st);
+                      cudaStream_t st, uint32_t window_bits = 16);
 template <class XY>
 void msm_bases_destroy(MsmBases<XY>& b);
 // chunk = sorted entries per accumulate thread (0 = msm_default_chunk(sort.n))
@@ -166,7 +198,7 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
 template <class XY>
 void msm_last_accumulate(const MsmSort& sort, const MsmScratch<XY>& s, float* ms, uint64_t* entries);
 // kernels launched by one msm_sort_run / one msm_reduce_batch
-constexpr uint32_t kMsmSortLaunches   = 4; // hist, column sums, bucket scan, scatter
+constexpr uint32_t kMsmSortLaunches   = 4; // hist, column sums, bucket scan, scatter  |  count, scan, partition, local sort
 constexpr uint32_t kMsmReduceLaunches = 6;
 
 extern template struct MsmBases<G1Xyzz>;

@@ -4,9 +4,9 @@
 // Replaces ParallelMultiexp<Curve>::multiexp (rust-rapidsnark/rapidsnark/src/multiexp.cpp:183-245) and the
 // group law it calls (curve.cpp). Integer pipes only.
 //
-// Reduction sum_b b * B_b over bucket ids b = idx + 1, idx = i2 * 1024 + i1 * 32 + i0 (base-32 digits):
+// Reduction sum_b b * B_b over bucket ids b = idx + 1, idx = ... + i2 * 1024 + i1 * 32 + i0 (base-32 digits):
 //     result = sum_b B_b + sum_l 32^l * sum_v v * S_l[v],      S_l[v] = sum of the buckets whose digit l equals v
-// so the 2^15 buckets collapse into 3 x 32 plain class sums (perfectly parallel trees, no weights) and one
+// so the 2^(c-1) buckets collapse into levels x 32 plain class sums (3 levels for c = 16, 4 for c = 20) (perfectly parallel trees, no weights) and one
 // 32-term weighted sum that a single block finishes by bit decomposition. Every stage is sized by sequential
 // point additions, which is what bounds these latency-limited kernels.
 #pragma once
@@ -50,7 +50,7 @@ struct MsmBatchArgs
 template <class XY>
 __global__ void __launch_bounds__(128)
     k_msm_accumulate(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
-                     MsmBatchArgs<XY> args, uint32_t chunk, uint32_t n)
+                     MsmBatchArgs<XY> args, uint32_t chunk, uint32_t n, uint32_t nbuckets)
 {
     typedef typename XY::Affine Affine;
     typedef typename XY::Field  F;
@@ -58,14 +58,14 @@ __global__ void __launch_bounds__(128)
     const uint8_t* __restrict__ skip    = args.skip[blockIdx.y];
     XY* __restrict__            records = args.records[blockIdx.y];
     uint32_t t     = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t total = offsets[kMsmBuckets + 1];
+    uint32_t total = offsets[nbuckets + 1];
     uint64_t start64 = (uint64_t)t * chunk;
     if (start64 >= total)
         return;
     uint32_t start = (uint32_t)start64;
     uint32_t end   = min(start + chunk, total);
     // largest b in [1, B] with offsets[b] <= start
-    uint32_t lo = 1, hi = kMsmBuckets;
+    uint32_t lo = 1, hi = nbuckets;
     while (lo < hi)
     {
         uint32_t mid = (lo + hi + 1) >> 1;
@@ -152,13 +152,13 @@ __device__ __forceinline__ XY load_cg(const XY* p)
 // slot in the heavy list and is pre-reduced by whole blocks (k_msm_heavy) instead of one finalise thread.
 static __global__ void __launch_bounds__(256)
     k_msm_classify(const uint32_t* __restrict__ offsets, uint32_t chunk, uint32_t* __restrict__ heavy_count,
-                   uint32_t* __restrict__ heavy_ids, uint32_t* __restrict__ heavy_slot)
+                   uint32_t* __restrict__ heavy_ids, uint32_t* __restrict__ heavy_slot, uint32_t nbuckets)
 {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (b > kMsmBuckets)
+    if (b > nbuckets)
         return;
-    uint32_t total = offsets[kMsmBuckets + 1];
-    uint32_t thr   = max(kMsmHeavyRecords, 2u * (total / chunk / kMsmBuckets + 1u));
+    uint32_t total = offsets[nbuckets + 1];
+    uint32_t thr   = max(kMsmHeavyRecords, 2u * (total / chunk / nbuckets + 1u));
     uint32_t lo = offsets[b], hi = offsets[b + 1];
     uint32_t slot = 0;
     if (hi > lo && (hi - 1) / chunk - lo / chunk + 1 > thr)
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256)
 // ---- bucket finalisation + first fold -------------------------------------------------------------------
 // Block = kMsmFoldBlock (128) consecutive buckets, thread = bucket: sum its records (or take the heavy sum), then
 // fold inside the block: lane sums over the 4 warps (digit 0 classes) and warp sums (digit 1 class of each warp;
-// higher digits are constant over a block). grid = (kMsmBuckets / 128, batch).
+// higher digits are constant over a block). grid = (buckets / 128, batch).
 template <class XY>
 __global__ void __launch_bounds__(kMsmFoldBlock)
     k_msm_finalize_fold(const uint32_t* __restrict__ offsets, MsmBatchArgs<XY> args, uint32_t chunk)
@@ -346,15 +346,15 @@ __global__ void __launch_bounds__(kMsmFoldBlock)
         args.s1part[blockIdx.y][(size_t)blockIdx.x * (kMsmFoldBlock / 32) + (tid >> 5)] = sm[tid];
 }
 
-// ---- second fold: the kMsmFoldLevels x 32 class sums -----------------------------------------------------
+// ---- second fold: the levels x 32 class sums -----------------------------------------------------
 // Block (l, v) sums every partial of the buckets whose base-32 digit l equals v and scales it by 32^l.
-// grid = (32 * kMsmFoldLevels, batch), 256 threads.
+// grid = (32 * levels, batch), 256 threads.
 template <class XY>
-__global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args)
+__global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args, uint32_t nbuckets)
 {
     extern __shared__ uint4 smem_raw[];
     XY*                     sm   = reinterpret_cast<XY*>(smem_raw);
-    constexpr uint32_t      nblk = kMsmBuckets / kMsmFoldBlock;
+    const uint32_t          nblk = nbuckets / kMsmFoldBlock;
     constexpr uint32_t      wpb  = kMsmFoldBlock / 32; // warps (digit-1 classes) per fold block
     const XY* __restrict__  s0   = args.s0part[blockIdx.y];
     const XY* __restrict__  s1   = args.s1part[blockIdx.y];
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args)
 // Warps 0..4 build Z_k = sum of E[v] over v with bit k set, warp 5 builds T, thread 0 runs Horner over k.
 // grid = (1, batch), 192 threads.
 template <class XY>
-__global__ void __launch_bounds__(192) k_msm_final(MsmBatchArgs<XY> args)
+__global__ void __launch_bounds__(192) k_msm_final(MsmBatchArgs<XY> args, int levels)
 {
     extern __shared__ uint4 smem_raw[];
     XY*                     sm  = reinterpret_cast<XY*>(smem_raw);
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(192) k_msm_final(MsmBatchArgs<XY> args)
         if ((lane >> w) & 1u)
         {
 #pragma unroll 1
-            for (int l = 1; l < kMsmFoldLevels; l++)
+            for (int l = 1; l < levels; l++)
             {
                 XY u = cls[32 * l + lane];
                 cold_add(e, u);
@@ -537,8 +537,11 @@ __global__ void __launch_bounds__(128)
 
 template <class XY>
 void msm_bases_create(MsmBases<XY>& out, const uint8_t* points_host, uint64_t count, bool filter_inf,
-                      cudaStream_t st)
+                      cudaStream_t st, uint32_t window_bits)
 {
+    if (window_bits < kMsmMinWindowBits || window_bits > kMsmMaxWindowBits)
+        throw CudaError("MSM window size out of range");
+    out.shape = msm_shape(window_bits);
     typedef typename XY::Affine Affine;
     const size_t                psz = sizeof(Affine);
     std::vector<uint32_t>       idx;
@@ -606,14 +609,14 @@ void msm_bases_create(MsmBases<XY>& out, const uint8_t* points_host, uint64_t co
         KZP_CUDA_CHECK(cudaMalloc(&out.scalar_idx, n * 4));
         KZP_CUDA_CHECK(cudaMemcpyAsync(out.scalar_idx, idx.data(), n * 4, cudaMemcpyHostToDevice, st));
     }
-    KZP_CUDA_CHECK(cudaMalloc(&out.table, n * kMsmWindows * psz));
+    KZP_CUDA_CHECK(cudaMalloc(&out.table, n * out.shape.windows * psz));
     KZP_CUDA_CHECK(cudaMemcpyAsync(out.table, src, n * psz, cudaMemcpyHostToDevice, st));
     XY* cur = nullptr;
     KZP_CUDA_CHECK(cudaMalloc(&cur, n * sizeof(XY)));
     unsigned int grid = msm_div_up(n, 128);
-    for (int j = 1; j < kMsmWindows; j++)
+    for (int j = 1; j < (int)out.shape.windows; j++)
     {
-        k_tbl_double<XY><<<grid, 128, 0, st>>>(cur, out.n, kMsmWindowBits, j == 1 ? out.table : nullptr);
+        k_tbl_double<XY><<<grid, 128, 0, st>>>(cur, out.n, (int)out.shape.c, j == 1 ? out.table : nullptr);
         KZP_CUDA_CHECK(cudaGetLastError());
         k_tbl_normalise<XY><<<msm_div_up(n, 128 * 8), 128, 0, st>>>(cur, out.n, out.table + (size_t)j * n);
         KZP_CUDA_CHECK(cudaGetLastError());
@@ -651,8 +654,9 @@ template <class XY>
 void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort, uint32_t chunk)
 {
     msm_set_smem_attrs<XY>(); // function attributes are per device: set on the device that owns the scratch
-    size_t nb   = kMsmBuckets + 2;
-    size_t nblk = kMsmBuckets / kMsmFoldBlock;
+    s.shape     = sort.shape;
+    size_t nb   = (size_t)s.shape.buckets + 2;
+    size_t nblk = s.shape.buckets / kMsmFoldBlock;
     s.chunk     = chunk ? chunk : msm_default_chunk(sort.n);
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_count, 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_ids, kMsmMaxHeavy * 4));
@@ -664,7 +668,7 @@ void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort, uint32_t chunk)
     KZP_CUDA_CHECK(cudaMemset(s.heavy_done, 0, (size_t)kMsmMaxHeavy * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.s0part, nblk * 32 * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.s1part, nblk * (kMsmFoldBlock / 32) * sizeof(XY)));
-    KZP_CUDA_CHECK(cudaMalloc(&s.classes, (size_t)kMsmFoldLevels * 32 * sizeof(XY)));
+    KZP_CUDA_CHECK(cudaMalloc(&s.classes, (size_t)kMsmMaxLevels * 32 * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.result, sizeof(XY)));
     KZP_CUDA_CHECK(cudaEventCreate(&s.ev_acc0));
     KZP_CUDA_CHECK(cudaEventCreate(&s.ev_acc1));
@@ -701,7 +705,7 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     for (int k = 0; k < kMsmMaxBatch; k++)
     {
         int j = k < nb ? k : 0;
-        if (bases[j]->n != sort.n)
+        if (bases[j]->n != sort.n || bases[j]->shape.c != sort.shape.c || scr[j]->shape.c != sort.shape.c)
             throw CudaError("MSM bases do not match the digit sort");
         a.table[k]         = bases[j]->table;
         a.skip[k]          = bases[j]->skip;
@@ -721,10 +725,11 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     a.heavy_count = scr[0]->heavy_count;
     a.heavy_ids   = scr[0]->heavy_ids;
     a.heavy_slot  = scr[0]->heavy_slot;
+    const uint32_t nbuckets = sort.shape.buckets;
     dim3 by(1, (unsigned int)nb, 1);
     KZP_CUDA_CHECK(cudaMemsetAsync(a.heavy_count, 0, 4, st));
-    k_msm_classify<<<msm_div_up(kMsmBuckets, 256), 256, 0, st>>>(sort.offsets, chunk, a.heavy_count, a.heavy_ids,
-                                                                  a.heavy_slot);
+    k_msm_classify<<<msm_div_up(nbuckets, 256), 256, 0, st>>>(sort.offsets, chunk, a.heavy_count, a.heavy_ids,
+                                                               a.heavy_slot, nbuckets);
     KZP_CUDA_CHECK(cudaGetLastError());
     KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc0, st));
     if (sort.n > 0)
@@ -734,7 +739,7 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
         static const int acc_smem = getenv("KZP_ACC_SMEM") ? atoi(getenv("KZP_ACC_SMEM")) : 0; // experiment: cap occupancy
         if (acc_smem > 48 * 1024)
             KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_accumulate<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize, acc_smem));
-        k_msm_accumulate<XY><<<by, 128, (size_t)(nb == 1 && sizeof(XY) == 128 ? acc_smem : 0), st>>>(sort.offsets, sort.sorted, a, chunk, sort.n);
+        k_msm_accumulate<XY><<<by, 128, (size_t)(nb == 1 && sizeof(XY) == 128 ? acc_smem : 0), st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
         KZP_CUDA_CHECK(cudaGetLastError());
     }
     KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc1, st));
@@ -750,14 +755,14 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     by.x = heavy_g;
     k_msm_heavy<XY><<<by, heavy_t, heavy_t * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
-    by.x = kMsmBuckets / kMsmFoldBlock;
+    by.x = nbuckets / kMsmFoldBlock;
     k_msm_finalize_fold<XY><<<by, kMsmFoldBlock, kMsmFoldBlock * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
-    by.x = 32 * kMsmFoldLevels;
-    k_msm_fold2<XY><<<by, fold2_t, fold2_t * sizeof(XY), st>>>(a);
+    by.x = 32 * sort.shape.levels;
+    k_msm_fold2<XY><<<by, fold2_t, fold2_t * sizeof(XY), st>>>(a, nbuckets);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = 1;
-    k_msm_final<XY><<<by, 192, 192 * sizeof(XY), st>>>(a);
+    k_msm_final<XY><<<by, 192, 192 * sizeof(XY), st>>>(a, (int)sort.shape.levels);
     KZP_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -771,7 +776,7 @@ void msm_last_accumulate(const MsmSort& sort, const MsmScratch<XY>& s, float* ms
         t = 0;
     }
     uint32_t total = 0;
-    KZP_CUDA_CHECK(cudaMemcpy(&total, sort.offsets + kMsmBuckets + 1, 4, cudaMemcpyDeviceToHost));
+    KZP_CUDA_CHECK(cudaMemcpy(&total, sort.offsets + sort.shape.buckets + 1, 4, cudaMemcpyDeviceToHost));
     if (ms)
         *ms = t;
     if (entries)

@@ -5,7 +5,7 @@ namespace kzp
 {
 
 template struct MsmBases<G1Xyzz>;
-template void msm_bases_create<G1Xyzz>(MsmBases<G1Xyzz>&, const uint8_t*, uint64_t, bool, cudaStream_t);
+template void msm_bases_create<G1Xyzz>(MsmBases<G1Xyzz>&, const uint8_t*, uint64_t, bool, cudaStream_t, uint32_t);
 template void msm_bases_destroy<G1Xyzz>(MsmBases<G1Xyzz>&);
 template void msm_scratch_create<G1Xyzz>(MsmScratch<G1Xyzz>&, const MsmSort&, uint32_t);
 template void msm_scratch_destroy<G1Xyzz>(MsmScratch<G1Xyzz>&);

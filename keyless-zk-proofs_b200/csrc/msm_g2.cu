@@ -5,7 +5,7 @@ namespace kzp
 {
 
 template struct MsmBases<G2Xyzz>;
-template void msm_bases_create<G2Xyzz>(MsmBases<G2Xyzz>&, const uint8_t*, uint64_t, bool, cudaStream_t);
+template void msm_bases_create<G2Xyzz>(MsmBases<G2Xyzz>&, const uint8_t*, uint64_t, bool, cudaStream_t, uint32_t);
 template void msm_bases_destroy<G2Xyzz>(MsmBases<G2Xyzz>&);
 template void msm_scratch_create<G2Xyzz>(MsmScratch<G2Xyzz>&, const MsmSort&, uint32_t);
 template void msm_scratch_destroy<G2Xyzz>(MsmScratch<G2Xyzz>&);

@@ -36,19 +36,36 @@ __device__ __forceinline__ void load_scalar(const uint32_t* __restrict__ scalars
     }
 }
 
-// signed base-2^16 digits d_j in [-2^15, 2^15], sum d_j 2^(16 j) = s, for s < 2^255
+// signed base-2^C digits d_j in [-2^(C-1), 2^(C-1)], sum d_j 2^(C j) = s, for s < 2^255 (j must be a compile-time
+// constant after unrolling: the limb index is then static and the scalar stays in registers)
+template <int C>
 __device__ __forceinline__ int32_t next_digit(const Fr& s, int j, uint32_t& carry)
 {
-    uint32_t raw = (s.v[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-    uint32_t v   = raw + carry;
-    if (v > 0x8000u)
+    constexpr uint32_t mask = (1u << C) - 1u, half = 1u << (C - 1);
+    const int          o = C * j, limb = o >> 5, sh = o & 31;
+    uint32_t           lo = limb < 8 ? s.v[limb] : 0u;
+    uint32_t           hi = limb + 1 < 8 ? s.v[limb + 1] : 0u;
+    uint32_t           raw = (sh ? __funnelshift_r(lo, hi, sh) : lo) & mask;
+    uint32_t           v   = raw + carry;
+    if (v > half)
     {
         carry = 1;
-        return (int32_t)v - 0x10000;
+        return (int32_t)v - (int32_t)(1u << C);
     }
     carry = 0;
     return (int32_t)v;
 }
+
+template <int C>
+struct SortCfg
+{
+    static constexpr int      W = (255 + C - 1) / C;
+    static constexpr uint32_t B = 1u << (C - 1);
+};
+
+// ---- one-level sort (c = 16) ------------------------------------------------------------------------------
+constexpr int      kMsmWindows = SortCfg<16>::W;
+constexpr uint32_t kMsmBuckets = SortCfg<16>::B;
 
 __device__ __forceinline__ bool scalar_is_small(const Fr& s)
 {
@@ -92,7 +109,7 @@ static __global__ void __launch_bounds__(kSortThreads, 1)
 #pragma unroll
             for (int j = 0; j < kMsmWindows; j++)
             {
-                int32_t d = next_digit(s, j, carry);
+                int32_t d = next_digit<16>(s, j, carry);
                 if (d != 0)
                     atomicAdd(&sm_cnt[d < 0 ? -d : d], 1u);
             }
@@ -224,7 +241,7 @@ static __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int j = 0; j < kMsmWindows; j++)
     {
-        int32_t d = next_digit(s, j, carry);
+        int32_t d = next_digit<16>(s, j, carry);
         if (d != 0)
         {
             uint32_t bkt = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
@@ -232,6 +249,312 @@ static __global__ void __launch_bounds__(256)
             sorted[pos]  = i | ((uint32_t)j << kMsmEntryBaseBits) | (d < 0 ? 0x80000000u : 0u);
         }
     }
+}
+
+
+// ---- two-level sort (any window size) ---------------------------------------------------------------------
+// With 2^19 buckets (c = 20) neither the per-CTA histogram (2 MB of counters) nor one global cursor per bucket
+// (every entry a lone atomic + a lone 4-byte store: the one-level scatter is L2-request bound) works. Two passes,
+// every global write part of a contiguous run:
+//   count     per-partition totals (partition = high bits of the bucket index), shared-memory counters per tile
+//   scan      partition offsets
+//   partition one CTA per tile of scalars: digits -> counting sort by partition in shared memory -> one global
+//             atomic per (tile, partition) reserves a run -> 8-byte records (entry, bucket index) copied out in
+//             partition order, consecutive threads on consecutive addresses
+//   local     one CTA per partition: counting sort by the low bucket bits, staged in shared memory and written
+//             as one contiguous block; the same CTA writes the bucket offsets of its partition
+constexpr int    kS2Threads   = 1024;
+constexpr size_t kS2SmemMax   = 227 * 1024;
+constexpr int    kS2MaxParts  = 1024;
+constexpr int    kS2MaxSubBits = 12;
+constexpr uint32_t kS2LocalCap = 48 * 1024; // entries one partition may have to take the staged path
+
+template <int C, class Fn>
+__device__ __forceinline__ void for_each_digit(const Fr& s, uint32_t i, Fn&& fn)
+{
+    uint32_t carry = 0;
+#pragma unroll
+    for (int j = 0; j < SortCfg<C>::W; j++)
+    {
+        int32_t d = next_digit<C>(s, j, carry);
+        if (d != 0)
+        {
+            uint32_t bkt = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            fn(bkt - 1u, i | ((uint32_t)j << kMsmEntryBaseBits) | (d < 0 ? 0x80000000u : 0u));
+        }
+    }
+}
+
+template <int C>
+static __global__ void __launch_bounds__(kS2Threads, 1)
+    k_s2_count(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ scalar_idx, uint32_t scalar_offset,
+               uint32_t n, uint32_t tile, uint32_t sub_bits, uint32_t parts, uint32_t* __restrict__ part_cnt)
+{
+    __shared__ uint32_t cnt[kS2MaxParts];
+    for (uint32_t p = threadIdx.x; p < parts; p += kS2Threads)
+        cnt[p] = 0;
+    __syncthreads();
+    const uint32_t lo = blockIdx.x * tile, hi = min(n, lo + tile);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kS2Threads)
+    {
+        Fr s;
+        load_scalar(scalars, scalar_idx ? scalar_idx[i] : scalar_offset + i, s);
+        for_each_digit<C>(s, i, [&](uint32_t b, uint32_t) { atomicAdd(&cnt[b >> sub_bits], 1u); });
+    }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < parts; p += kS2Threads)
+        if (cnt[p])
+            atomicAdd(&part_cnt[p], cnt[p]);
+}
+
+// part_cnt[0..P) -> exclusive offsets in place, part_cnt[P] = total; cursors = offsets; offsets[0] = 0 and
+// offsets[B + 1] = total (the per-bucket offsets in between are written by the local pass)
+static __global__ void __launch_bounds__(kS2MaxParts)
+    k_s2_scan(uint32_t* __restrict__ part_cnt, uint32_t* __restrict__ part_cursor, uint32_t parts,
+              uint32_t* __restrict__ offsets, uint32_t buckets)
+{
+    __shared__ uint32_t warp_sums[32];
+    uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t v   = tid < parts ? part_cnt[tid] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o)
+            inc += t;
+    }
+    if (lane == 31)
+        warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0)
+    {
+        uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (uint32_t)o)
+                wi += t;
+        }
+        warp_sums[lane] = wi - ws;
+    }
+    __syncthreads();
+    uint32_t excl = warp_sums[wid] + inc - v;
+    if (tid < parts)
+    {
+        part_cnt[tid]    = excl;
+        part_cursor[tid] = excl;
+    }
+    if (tid == parts - 1)
+    {
+        part_cnt[parts]      = excl + v;
+        offsets[0]           = 0;
+        offsets[buckets + 1] = excl + v;
+    }
+}
+
+template <int C>
+static __global__ void __launch_bounds__(kS2Threads, 1)
+    k_s2_partition(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ scalar_idx, uint32_t scalar_offset,
+                   uint32_t n, uint32_t tile, uint32_t sub_bits, uint32_t parts, uint32_t* __restrict__ part_cursor,
+                   uint2* __restrict__ inter)
+{
+    extern __shared__ uint4 s2_smem[];
+    uint32_t* cnt   = reinterpret_cast<uint32_t*>(s2_smem); // counts, then write cursors
+    uint32_t* start = cnt + parts;                          // first staging slot of each partition
+    uint32_t* gbase = start + parts;                        // first global slot of this tile's run
+    uint2*    stage = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(s2_smem) + ((3 * parts * 4 + 15u) & ~15u));
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t s_total;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (uint32_t p = tid; p < parts; p += kS2Threads)
+        cnt[p] = 0;
+    __syncthreads();
+    const uint32_t lo = blockIdx.x * tile, hi = min(n, lo + tile);
+    for (uint32_t i = lo + tid; i < hi; i += kS2Threads)
+    {
+        Fr s;
+        load_scalar(scalars, scalar_idx ? scalar_idx[i] : scalar_offset + i, s);
+        for_each_digit<C>(s, i, [&](uint32_t b, uint32_t) { atomicAdd(&cnt[b >> sub_bits], 1u); });
+    }
+    __syncthreads();
+    // exclusive scan of the (<= 1024) partition counts, one per thread; reserve the global runs
+    {
+        uint32_t v = tid < parts ? cnt[tid] : 0u, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o)
+                inc += t;
+        }
+        if (lane == 31)
+            warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0)
+        {
+            uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= (uint32_t)o)
+                    wi += t;
+            }
+            warp_sums[lane] = wi - ws;
+            if (lane == 31)
+                s_total = wi;
+        }
+        __syncthreads();
+        if (tid < parts)
+        {
+            uint32_t excl = warp_sums[wid] + inc - v;
+            start[tid]    = excl;
+            cnt[tid]      = excl; // becomes the write cursor
+            gbase[tid]    = v ? atomicAdd(&part_cursor[tid], v) : 0u;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = lo + tid; i < hi; i += kS2Threads)
+    {
+        Fr s;
+        load_scalar(scalars, scalar_idx ? scalar_idx[i] : scalar_offset + i, s);
+        for_each_digit<C>(s, i, [&](uint32_t b, uint32_t e) {
+            uint32_t pos = atomicAdd(&cnt[b >> sub_bits], 1u);
+            stage[pos]   = make_uint2(e, b);
+        });
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    for (uint32_t k = tid; k < total; k += kS2Threads)
+    {
+        uint2    rec = stage[k];
+        uint32_t p   = rec.y >> sub_bits;
+        inter[gbase[p] + (k - start[p])] = rec;
+    }
+}
+
+static __global__ void __launch_bounds__(kS2Threads, 1)
+    k_s2_local(const uint2* __restrict__ inter, const uint32_t* __restrict__ part_off, uint32_t sub_bits,
+               uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted)
+{
+    extern __shared__ uint4 s2_smem[];
+    const uint32_t subs = 1u << sub_bits;
+    uint32_t*      cnt  = reinterpret_cast<uint32_t*>(s2_smem); // counts, then cursors
+    uint32_t*      stage = cnt + subs;
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t p = blockIdx.x, base = part_off[p], n_p = part_off[p + 1] - base;
+    const uint32_t sub_mask = subs - 1u;
+    const uint2*   in = inter + base;
+    for (uint32_t k = tid; k < subs; k += kS2Threads)
+        cnt[k] = 0;
+    __syncthreads();
+    for (uint32_t k = tid; k < n_p; k += kS2Threads)
+        atomicAdd(&cnt[in[k].y & sub_mask], 1u);
+    __syncthreads();
+    // exclusive scan over the sub-buckets: every thread owns `per` consecutive counters
+    {
+        const uint32_t per = (subs + kS2Threads - 1) / kS2Threads; // 1..4
+        uint32_t       loc[1u << (kS2MaxSubBits - 10)];
+        uint32_t       sum = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < (1u << (kS2MaxSubBits - 10)); q++)
+            if (q < per)
+            {
+                uint32_t idx = tid * per + q;
+                loc[q]       = sum;
+                sum += idx < subs ? cnt[idx] : 0u;
+            }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o)
+                inc += t;
+        }
+        if (lane == 31)
+            warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0)
+        {
+            uint32_t ws = warp_sums[lane], wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= (uint32_t)o)
+                    wi += t;
+            }
+            warp_sums[lane] = wi - ws;
+        }
+        __syncthreads();
+        uint32_t excl = warp_sums[wid] + inc - sum;
+#pragma unroll
+        for (uint32_t q = 0; q < (1u << (kS2MaxSubBits - 10)); q++)
+            if (q < per)
+            {
+                uint32_t idx = tid * per + q;
+                if (idx < subs)
+                {
+                    uint32_t o = excl + loc[q];
+                    cnt[idx]   = o;
+                    offsets[1u + (p << sub_bits) + idx] = base + o; // bucket id = index + 1
+                }
+            }
+    }
+    __syncthreads();
+    if (n_p <= kS2LocalCap)
+    {
+        for (uint32_t k = tid; k < n_p; k += kS2Threads)
+        {
+            uint2    rec = in[k];
+            uint32_t pos = atomicAdd(&cnt[rec.y & sub_mask], 1u);
+            stage[pos]   = rec.x;
+        }
+        __syncthreads();
+        for (uint32_t k = tid; k < n_p; k += kS2Threads)
+            sorted[base + k] = stage[k];
+    }
+    else
+    {
+        // oversized partition (skewed digits): positions still come from the shared-memory cursors, the stores go
+        // straight to global memory
+        for (uint32_t k = tid; k < n_p; k += kS2Threads)
+        {
+            uint2    rec = in[k];
+            uint32_t pos = atomicAdd(&cnt[rec.y & sub_mask], 1u);
+            sorted[base + pos] = rec.x;
+        }
+    }
+}
+
+template <int C>
+static void s2_run(MsmSort& s, const uint32_t* scalars, cudaStream_t st)
+{
+    const uint32_t parts = 1u << s.part_bits, sub_bits = (uint32_t)(C - 1) - s.part_bits;
+    const uint32_t W = SortCfg<C>::W;
+    // tile of scalars per CTA: the staging area takes 8 bytes per possible entry
+    size_t   head = ((size_t)3 * parts * 4 + 15) & ~(size_t)15;
+    uint32_t tile = (uint32_t)((kS2SmemMax - 1024 - head) / ((size_t)W * 8));
+    tile          = std::min<uint32_t>(tile / kS2Threads * kS2Threads, 4 * kS2Threads);
+    size_t   smem_a = head + (size_t)tile * W * 8;
+    size_t   smem_b = ((size_t)1 << sub_bits) * 4 + (size_t)kS2LocalCap * 4;
+    uint32_t tiles  = std::max<uint32_t>(1, sort_div_up(s.n, tile));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_s2_partition<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_s2_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    KZP_CUDA_CHECK(cudaMemsetAsync(s.part_cnt, 0, ((size_t)parts + 1) * 4, st));
+    k_s2_count<C><<<tiles, kS2Threads, 0, st>>>(scalars, s.scalar_idx, s.scalar_offset, s.n, tile, sub_bits, parts, s.part_cnt);
+    KZP_CUDA_CHECK(cudaGetLastError());
+    k_s2_scan<<<1, kS2MaxParts, 0, st>>>(s.part_cnt, s.part_cursor, parts, s.offsets, SortCfg<C>::B);
+    KZP_CUDA_CHECK(cudaGetLastError());
+    k_s2_partition<C><<<tiles, kS2Threads, smem_a, st>>>(scalars, s.scalar_idx, s.scalar_offset, s.n, tile, sub_bits, parts,
+                                                          s.part_cursor, s.inter);
+    KZP_CUDA_CHECK(cudaGetLastError());
+    k_s2_local<<<parts, kS2Threads, smem_b, st>>>(s.inter, s.part_cnt, sub_bits, s.offsets, s.sorted);
+    KZP_CUDA_CHECK(cudaGetLastError());
 }
 
 uint32_t msm_default_chunk(uint64_t n)
@@ -243,20 +566,44 @@ uint32_t msm_default_chunk(uint64_t n)
     return c;
 }
 
-void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_t scalar_offset)
+void msm_sort_create(MsmSort& s, uint32_t n, const uint32_t* scalar_idx, uint32_t scalar_offset, uint32_t window_bits,
+                     bool force_two_level)
 {
     if (n > kMsmEntryBaseMask)
         throw CudaError("MSM too large for 27-bit base ids");
+    if (window_bits < kMsmMinWindowBits || window_bits > kMsmMaxWindowBits)
+        throw CudaError("MSM window size out of range");
+    s.shape         = msm_shape(window_bits);
     s.n             = n;
     s.scalar_idx    = scalar_idx;
     s.scalar_offset = scalar_offset;
-    uint64_t cap    = (uint64_t)n * kMsmWindows;
+    uint64_t cap    = (uint64_t)n * s.shape.windows;
+    if (cap > 0xffffffffull)
+        throw CudaError("MSM too large: more than 2^32 digit entries");
     s.cap_entries   = (uint32_t)cap;
-    size_t nb       = kMsmBuckets + 2;
-    KZP_CUDA_CHECK(cudaMalloc(&s.counts, nb * 4));
+    s.two_level     = force_two_level || window_bits != 16;
+    size_t nb       = (size_t)s.shape.buckets + 2;
     KZP_CUDA_CHECK(cudaMalloc(&s.offsets, nb * 4));
-    KZP_CUDA_CHECK(cudaMalloc(&s.cursor, nb * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.sorted, std::max<uint64_t>(cap, 1) * 4));
+    if (s.two_level)
+    {
+        // partitions: enough that an average partition fits the local pass's staging area with room to spare, at
+        // most 1024 (one scan thread each), at least so many that the sub-bucket counters fit shared memory
+        uint32_t want = 0;
+        while (want < 10 && (cap >> want) > 32 * 1024)
+            want++;
+        uint32_t min_bits = window_bits - 1 > (uint32_t)kS2MaxSubBits ? window_bits - 1 - kS2MaxSubBits : 0;
+        s.part_bits       = std::min<uint32_t>(std::max(want, min_bits), window_bits - 1);
+        if (s.part_bits > 10)
+            throw CudaError("MSM window too large for the two-level sort");
+        size_t parts = (size_t)1 << s.part_bits;
+        KZP_CUDA_CHECK(cudaMalloc(&s.part_cnt, (parts + 1) * 4));
+        KZP_CUDA_CHECK(cudaMalloc(&s.part_cursor, parts * 4));
+        KZP_CUDA_CHECK(cudaMalloc(&s.inter, std::max<uint64_t>(cap, 1) * 8));
+        return;
+    }
+    KZP_CUDA_CHECK(cudaMalloc(&s.counts, nb * 4));
+    KZP_CUDA_CHECK(cudaMalloc(&s.cursor, nb * 4));
     // one CTA per SM, each owning a contiguous slice of the scalars (a multiple of the block size)
     int dev = 0, sms = 1;
     KZP_CUDA_CHECK(cudaGetDevice(&dev));
@@ -276,11 +623,29 @@ void msm_sort_destroy(MsmSort& s)
     cudaFree(s.cursor);
     cudaFree(s.sorted);
     cudaFree(s.cta_hist);
+    cudaFree(s.part_cnt);
+    cudaFree(s.part_cursor);
+    cudaFree(s.inter);
     s = MsmSort();
 }
 
 void msm_sort_run(MsmSort& s, const uint32_t* scalars, cudaStream_t st)
 {
+    if (s.two_level)
+    {
+        switch (s.shape.c)
+        {
+        case 16: s2_run<16>(s, scalars, st); break;
+        case 17: s2_run<17>(s, scalars, st); break;
+        case 18: s2_run<18>(s, scalars, st); break;
+        case 19: s2_run<19>(s, scalars, st); break;
+        case 20: s2_run<20>(s, scalars, st); break;
+        case 21: s2_run<21>(s, scalars, st); break;
+        case 22: s2_run<22>(s, scalars, st); break;
+        default: throw CudaError("MSM window size out of range");
+        }
+        return;
+    }
     k_msm_hist<<<s.sort_ctas, kSortThreads, kSortSmem, st>>>(scalars, s.scalar_idx, s.scalar_offset, s.n, s.per_cta,
                                                              s.cta_hist);
     KZP_CUDA_CHECK(cudaGetLastError());
