@@ -30,6 +30,7 @@ struct MsmBatchArgs
     const uint8_t*             skip[kMsmMaxBatch]; // per base column: 1 = infinity (nullptr = no flags)
     XY*                        records[kMsmMaxBatch];
     uint32_t*                  heavy_count; // classification is shared by the batch (same sort, same chunk)
+    uint32_t*                  work_counter; // kMsmMaxBatch chunk tickets of the accumulate kernel (heavy_count + 1)
     uint32_t*                  heavy_ids;
     uint32_t*                  heavy_slot;
     XY*                        heavy_partial[kMsmMaxBatch];
@@ -57,49 +58,62 @@ __global__ void __launch_bounds__(128)
     const Affine* __restrict__  table   = args.table[blockIdx.y];
     const uint8_t* __restrict__ skip    = args.skip[blockIdx.y];
     XY* __restrict__            records = args.records[blockIdx.y];
-    uint32_t t     = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t total = offsets[nbuckets + 1];
-    uint64_t start64 = (uint64_t)t * chunk;
-    if (start64 >= total)
-        return;
-    uint32_t start = (uint32_t)start64;
-    uint32_t end   = min(start + chunk, total);
-    // largest b in [1, B] with offsets[b] <= start
-    uint32_t lo = 1, hi = nbuckets;
-    while (lo < hi)
+    uint32_t*                   ticket  = args.work_counter + blockIdx.y;
+    const uint32_t              total   = offsets[nbuckets + 1];
+    const uint32_t              lane    = threadIdx.x & 31;
+    // The grid is sized to what is resident at once; warps take 32 consecutive chunks at a time from a ticket
+    // counter until the sorted list is used up, so no SM idles through the tail of a last partial wave.
+    for (;;)
     {
-        uint32_t mid = (lo + hi + 1) >> 1;
-        if (offsets[mid] <= start)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    uint32_t cur  = lo;
-    uint32_t next = offsets[cur + 1];
-    XY       acc;
-    XY::set_inf(acc);
-    for (uint32_t pos = start; pos < end; pos++)
-    {
-        if (pos >= next)
+        uint32_t first = 0;
+        if (lane == 0)
+            first = atomicAdd(ticket, 32u);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if ((uint64_t)first * chunk >= total)
+            return;
+        uint32_t t       = first + lane;
+        uint64_t start64 = (uint64_t)t * chunk;
+        if (start64 >= total)
+            continue;
+        uint32_t start = (uint32_t)start64;
+        uint32_t end   = min(start + chunk, total);
+        // largest b in [1, B] with offsets[b] <= start
+        uint32_t lo = 1, hi = nbuckets;
+        while (lo < hi)
         {
-            records[t + cur] = acc;
-            XY::set_inf(acc);
-            do
-            {
-                cur++;
-                next = offsets[cur + 1];
-            } while (pos >= next);
+            uint32_t mid = (lo + hi + 1) >> 1;
+            if (offsets[mid] <= start)
+                lo = mid;
+            else
+                hi = mid - 1;
         }
-        uint32_t e = sorted[pos];
-        uint32_t i = e & kMsmEntryBaseMask;
-        if (skip && skip[i])
-            continue; // infinity column: costs one byte, not a point load
-        Affine p = table[(size_t)((e >> kMsmEntryBaseBits) & 15u) * n + i];
-        if (e >> 31)
-            F::neg(p.y, p.y);
-        XY::madd(acc, p);
+        uint32_t cur  = lo;
+        uint32_t next = offsets[cur + 1];
+        XY       acc;
+        XY::set_inf(acc);
+        for (uint32_t pos = start; pos < end; pos++)
+        {
+            if (pos >= next)
+            {
+                records[t + cur] = acc;
+                XY::set_inf(acc);
+                do
+                {
+                    cur++;
+                    next = offsets[cur + 1];
+                } while (pos >= next);
+            }
+            uint32_t e = sorted[pos];
+            uint32_t i = e & kMsmEntryBaseMask;
+            if (skip && skip[i])
+                continue; // infinity column: costs one byte, not a point load
+            Affine p = table[(size_t)((e >> kMsmEntryBaseBits) & 15u) * n + i];
+            if (e >> 31)
+                F::neg(p.y, p.y);
+            XY::madd(acc, p);
+        }
+        records[t + cur] = acc;
     }
-    records[t + cur] = acc;
 }
 
 // Out-of-line group operations for the cold kernels (bucket finalisation, reduction, table construction):
@@ -316,6 +330,10 @@ __global__ void __launch_bounds__(kMsmFoldBlock)
             }
         }
     }
+    // Fold inside the block with as few idle lanes as the data allows: warp 0 sums over the 4 warps (digit-0 classes,
+    // 3 additions on 32 lanes) while warps 1 and 2 run the first level of all four warp-sum trees at once (64 lanes);
+    // the remaining 4 levels (32, 16, 8, 4 lanes) run on one warp. 9 warp-wide additions instead of 23.
+    XY* sm2 = sm + kMsmFoldBlock; // 64 entries: [row][16]
     sm[tid] = acc;
     __syncthreads();
     if (tid < 32)
@@ -329,21 +347,32 @@ __global__ void __launch_bounds__(kMsmFoldBlock)
         }
         args.s0part[blockIdx.y][(size_t)blockIdx.x * 32 + tid] = t;
     }
-    __syncthreads();
-    uint32_t lane = tid & 31;
-#pragma unroll 1
-    for (uint32_t stride = 16; stride > 0; stride >>= 1)
+    else if (tid < 96)
     {
-        if (lane < stride)
-        {
-            XY a = sm[tid], c = sm[tid + stride];
-            cold_add(a, c);
-            sm[tid] = a;
-        }
-        __syncwarp();
+        uint32_t i = tid - 32, row = i >> 4, k = i & 15;
+        XY       a = sm[row * 32 + k], c = sm[row * 32 + k + 16];
+        cold_add(a, c);
+        sm2[row * 16 + k] = a;
     }
-    if (lane == 0)
-        args.s1part[blockIdx.y][(size_t)blockIdx.x * (kMsmFoldBlock / 32) + (tid >> 5)] = sm[tid];
+    __syncthreads();
+    if (tid < 32)
+    {
+#pragma unroll 1
+        for (uint32_t width = 8; width > 0; width >>= 1)
+        {
+            // 4 rows x `width` lanes: entry k of a row takes entry k + width
+            if (tid < 4 * width)
+            {
+                uint32_t row = tid / width, k = tid % width;
+                XY       a = sm2[row * 16 + k], c = sm2[row * 16 + k + width];
+                cold_add(a, c);
+                sm2[row * 16 + k] = a;
+            }
+            __syncwarp();
+        }
+        if (tid < kMsmFoldBlock / 32)
+            args.s1part[blockIdx.y][(size_t)blockIdx.x * (kMsmFoldBlock / 32) + tid] = sm2[tid * 16];
+    }
 }
 
 // ---- second fold: the levels x 32 class sums -----------------------------------------------------
@@ -643,7 +672,7 @@ static void msm_set_smem_attrs()
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_heavy<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(256 * sizeof(XY))));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_finalize_fold<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(kMsmFoldBlock * sizeof(XY))));
+                                        (int)((kMsmFoldBlock + 64) * sizeof(XY))));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_fold2<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(256 * sizeof(XY))));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_final<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -658,7 +687,7 @@ void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort, uint32_t chunk)
     size_t nb   = (size_t)s.shape.buckets + 2;
     size_t nblk = s.shape.buckets / kMsmFoldBlock;
     s.chunk     = chunk ? chunk : msm_default_chunk(sort.n);
-    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_count, 4));
+    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_count, 4 * (1 + kMsmMaxBatch))); // [0] heavy buckets, [1..] accumulate tickets
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_ids, kMsmMaxHeavy * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_slot, nb * 4));
     KZP_CUDA_CHECK(cudaMalloc(&s.records, ((size_t)sort.cap_entries / s.chunk + nb + 1) * sizeof(XY)));
@@ -695,6 +724,25 @@ void msm_scratch_destroy(MsmScratch<XY>& s)
     s = MsmScratch<XY>();
 }
 
+// CTAs of the accumulate kernel that are resident at once on the current device (occupancy x SMs)
+template <class XY>
+static unsigned int msm_resident_blocks()
+{
+    static thread_local int cached_dev = -1;
+    static thread_local unsigned int cached = 0;
+    int dev = 0;
+    KZP_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev != cached_dev)
+    {
+        int per_sm = 0, sms = 0;
+        KZP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msm_accumulate<XY>, 128, 0));
+        KZP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        cached     = (unsigned int)std::max(1, per_sm * sms);
+        cached_dev = dev;
+    }
+    return cached;
+}
+
 template <class XY>
 void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, MsmScratch<XY>* const* scr, int nb,
                       cudaStream_t st)
@@ -722,12 +770,13 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     for (int k = 1; k < nb; k++)
         if (scr[k]->chunk != chunk)
             throw CudaError("MSM batch members must share one chunk size");
-    a.heavy_count = scr[0]->heavy_count;
+    a.heavy_count  = scr[0]->heavy_count;
+    a.work_counter = scr[0]->heavy_count + 1;
     a.heavy_ids   = scr[0]->heavy_ids;
     a.heavy_slot  = scr[0]->heavy_slot;
     const uint32_t nbuckets = sort.shape.buckets;
     dim3 by(1, (unsigned int)nb, 1);
-    KZP_CUDA_CHECK(cudaMemsetAsync(a.heavy_count, 0, 4, st));
+    KZP_CUDA_CHECK(cudaMemsetAsync(a.heavy_count, 0, 4 * (1 + kMsmMaxBatch), st));
     k_msm_classify<<<msm_div_up(nbuckets, 256), 256, 0, st>>>(sort.offsets, chunk, a.heavy_count, a.heavy_ids,
                                                                a.heavy_slot, nbuckets);
     KZP_CUDA_CHECK(cudaGetLastError());
@@ -735,7 +784,7 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     if (sort.n > 0)
     {
         uint64_t threads = ((uint64_t)sort.cap_entries + chunk - 1) / chunk;
-        by.x             = msm_div_up(threads, 128);
+        by.x             = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY>());
         static const int acc_smem = getenv("KZP_ACC_SMEM") ? atoi(getenv("KZP_ACC_SMEM")) : 0; // experiment: cap occupancy
         if (acc_smem > 48 * 1024)
             KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_accumulate<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize, acc_smem));
@@ -756,7 +805,7 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     k_msm_heavy<XY><<<by, heavy_t, heavy_t * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = nbuckets / kMsmFoldBlock;
-    k_msm_finalize_fold<XY><<<by, kMsmFoldBlock, kMsmFoldBlock * sizeof(XY), st>>>(sort.offsets, a, chunk);
+    k_msm_finalize_fold<XY><<<by, kMsmFoldBlock, (kMsmFoldBlock + 64) * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = 32 * sort.shape.levels;
     k_msm_fold2<XY><<<by, fold2_t, fold2_t * sizeof(XY), st>>>(a, nbuckets);

@@ -1,4 +1,4 @@
-// Shared-memory radix-128 NTT levels for sm_100a.
+// Shared-memory radix-128 NTT levels for sm_100a, one warp per pair of columns.
 //
 // A transform of size 2^k is split into levels of 7 stages. One level applied to index bits [lo, lo+7) is a plain
 // 128-point DFT along those bits (twiddles are powers of w_128 only) plus one "boundary" twiddle per element that
@@ -10,11 +10,19 @@
 // Stages left over when k is not a multiple of 7 run as plain radix-2 stages (kernels.cu), which compose with the
 // levels because both are exact factorisations of the same DFT (validated stage by stage in tests).
 //
-// One CTA = 256 threads = 16 tiles x 128 points = 2048 elements = 64 KiB of shared memory, stored as two planes of
-// uint4 with the column index rotated by the row (phys = 16 t + ((c + t) & 15)) so that both the column-fastest
-// accesses of the butterfly rounds and the row-fastest accesses of the contiguous level are bank-conflict free.
-// Global traffic is coalesced 128-bit accesses in runs of >= 512 B; every element is read and written once per
-// level. Each thread runs radix-8 butterflies on 8 elements held in registers (rounds of 3, 3 and 1 stages).
+// Work split: a "column" is the 128 elements t = 0..127 of one level-DFT. A WARP owns two adjacent columns
+// (2 x 128 elements, 8 KiB of shared memory); lane = (column e, row group g), 8 elements per thread. The 7 stages
+// run as three register rounds over 8 rows each:
+//   R1  rows g + 16 q        stages with half-distance 64, 32     (8 products)
+//   R2  rows 32 (g>>2) + (g&3) + 4 q   stages 16, 8               (8 products)
+//   R3  rows 8 g + q         stages 4, 2, 1                       (5 products: the twiddles of these stages depend
+//                                                                  on q only, so w^0 = 1 is skipped at compile time)
+// i.e. 21 products per thread and level plus the 8 boundary twiddles, every warp the same amount. The first round
+// loads its rows straight from global memory and the last one stores straight to it (each warp instruction touches
+// 16 rows x 64 contiguous bytes), so an element crosses shared memory twice per level, between rounds, and only
+// __syncwarp is needed: warps of a CTA drift apart and their memory phases overlap the others' arithmetic.
+// Shared-memory slot of row t: the low three bits of t are XORed with bits 3..5, which makes the 8 lanes of every
+// quarter-warp hit 8 different 16-byte bank groups in all three rounds; elements are split in two 16-byte planes.
 // Replaces FFT<Fr>::fft / ifft (rust-rapidsnark/rapidsnark/src/fft.cpp:192-246) together with kernels.cu.
 #pragma once
 
@@ -24,13 +32,11 @@ namespace kzp
 {
 
 constexpr int kNttTileBits  = 7;
-constexpr int kNttColBits   = 4;                  // columns per CTA: 16 -> 256 threads, 64 KiB, half the register file.
-                                                  // Measured with 8 (128 threads): the transform alone is 4 % faster
-                                                  // (0.95 vs 0.99 ms at 2^21) but the whole proof is 0.25 ms slower
+constexpr int kNttColBits   = 4;                  // columns per CTA: 16 = 8 warps x 2 columns
 constexpr int kNttTileCols  = 1 << kNttColBits;
 constexpr int kNttThreads   = 16 * kNttTileCols;  // every thread owns 8 elements
 constexpr int kNttTileElems = kNttTileCols << kNttTileBits;
-constexpr int kNttMinCtas   = 512 / kNttThreads;  // 128 registers per thread either way
+constexpr int kNttMinCtas   = 512 / kNttThreads;  // 128 registers per thread
 constexpr int kNttMaxBatch = 3;
 
 // vectors transformed by one launch (blockIdx.y selects): the prover runs a, b and c through every level together
@@ -39,21 +45,37 @@ struct NttBatch
     Fr* x[kNttMaxBatch];
 };
 
-__device__ __forceinline__ uint32_t ntt_phys(uint32_t t, uint32_t c) { return (uint32_t)kNttTileCols * t + ((c + t) & (uint32_t)(kNttTileCols - 1)); }
+// 16-byte slot of (row t, column e of the warp) inside the warp's plane of 256 slots
+__device__ __forceinline__ uint32_t ntt_slot(uint32_t t, uint32_t e) { return (e << 7) | (t & ~7u) | ((t ^ (t >> 3)) & 7u); }
 
-__device__ __forceinline__ void ntt_sm_store(uint4* sm, uint32_t t, uint32_t c, const Fr& v)
+__device__ __forceinline__ void ntt_sm_store(uint4* wsm, uint32_t t, uint32_t e, const Fr& v)
 {
-    uint32_t p   = ntt_phys(t, c);
-    sm[p]        = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
-    sm[kNttTileElems + p] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    uint32_t p   = ntt_slot(t, e);
+    wsm[p]       = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    wsm[256 + p] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
 }
 
-__device__ __forceinline__ void ntt_sm_load(const uint4* sm, uint32_t t, uint32_t c, Fr& v)
+__device__ __forceinline__ void ntt_sm_load(const uint4* wsm, uint32_t t, uint32_t e, Fr& v)
 {
-    uint32_t p  = ntt_phys(t, c);
-    uint4    lo = sm[p], hi = sm[kNttTileElems + p];
+    uint32_t p  = ntt_slot(t, e);
+    uint4    lo = wsm[p], hi = wsm[256 + p];
     v.v[0] = lo.x; v.v[1] = lo.y; v.v[2] = lo.z; v.v[3] = lo.w;
     v.v[4] = hi.x; v.v[5] = hi.y; v.v[6] = hi.z; v.v[7] = hi.w;
+}
+
+// twiddles w_128^j, j < 64, as two planes of 16 bytes (consecutive j 16 bytes apart: no bank conflicts)
+__device__ __forceinline__ void ntt_tw_load(const uint4* twp, uint32_t j, Fr& v)
+{
+    uint4 lo = twp[j], hi = twp[64 + j];
+    v.v[0] = lo.x; v.v[1] = lo.y; v.v[2] = lo.z; v.v[3] = lo.w;
+    v.v[4] = hi.x; v.v[5] = hi.y; v.v[6] = hi.z; v.v[7] = hi.w;
+}
+
+__device__ __forceinline__ void ntt_tw_fill(uint4* twp, const Fr* __restrict__ tw, uint32_t j, uint32_t k)
+{
+    const uint4* src = reinterpret_cast<const uint4*>(tw + ((size_t)j << (k - kNttTileBits)));
+    twp[j]           = src[0];
+    twp[64 + j]      = src[1];
 }
 
 // w^e for e < 2^k from the half table tw[i] = w^i, i < 2^(k-1)   (w^(2^(k-1)) = -1)
@@ -69,70 +91,113 @@ __device__ __forceinline__ void ntt_root(Fr& r, const Fr* __restrict__ tw, uint3
     }
 }
 
-// Radix-8 butterflies on v[0..7] = elements t = t_rest + (q << sh), q = 0..7, covering the stages with half-distance
-// 2^(sh+2), 2^(sh+1), 2^sh (DIF order) or the reverse (DIT order). nst = number of stages (3, or 1 for the last round,
-// where only the half-distance-2^sh stage runs on pairs (q, q+1)). twT[j] = w_128^j, j < 64.
-template <bool DIT>
-__device__ __forceinline__ void ntt_round(Fr (&v)[8], const Fr* twT, uint32_t t_low, uint32_t sh, int nst)
+// One butterfly stage on v[0..7]: pairs (q, q | 1 << B) for the q with bit B clear. The twiddle of pair q is
+// w_128^idx with idx = (j0 + ((q & mask) << qsh)) << ish where mask = (1 << B) - 1, i.e. j = row mod half-distance.
+// DIF: (a, b) -> (a + b, (a - b) w);  DIT: (a, b) -> (a + w b, a - w b).  KNOWN0: j0 == 0 at compile time, so
+// pairs with (q & mask) == 0 have twiddle 1 and skip the product.
+template <bool DIT, int B, bool KNOWN0>
+__device__ __forceinline__ void ntt_stage(Fr (&v)[8], const uint4* twp, uint32_t j0, uint32_t qsh, uint32_t ish)
 {
-    if (nst == 1)
-    {
-        // single stage, half-distance 2^sh with sh == 0: twiddle index j = t mod 1 = 0 -> no multiplication
 #pragma unroll
-        for (int q = 0; q < 8; q += 2)
+    for (int q = 0; q < 8; q++)
+    {
+        if (q & (1 << B))
+            continue;
+        const int q2 = q | (1 << B);
+        const int qm = q & ((1 << B) - 1);
+        if (KNOWN0 && qm == 0)
         {
-            Fr u = v[q], w = v[q + 1];
-            Fr::add(v[q], u, w);
-            Fr::sub(v[q + 1], u, w);
+            Fr a = v[q], b = v[q2];
+            Fr::add(v[q], a, b);
+            Fr::sub(v[q2], a, b);
+            continue;
         }
-        return;
-    }
-    if (!DIT)
-    {
-#pragma unroll
-        for (int u = 2; u >= 0; u--)
+        Fr w;
+        ntt_tw_load(twp, (j0 + ((uint32_t)qm << qsh)) << ish, w);
+        Fr a = v[q], b = v[q2];
+        if (DIT)
         {
-            // stage h = 2^(sh+u): pairs differ in bit u of q; j = t mod h = t_low + ((q & (2^u - 1)) << sh)
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-            {
-                if (q & (1 << u))
-                    continue;
-                int      q2  = q | (1 << u);
-                uint32_t j   = t_low + ((uint32_t)(q & ((1 << u) - 1)) << sh);
-                uint32_t idx = j << (6 - sh - u);
-                Fr       a = v[q], b = v[q2], d;
-                Fr::add(v[q], a, b);
-                Fr::sub(d, a, b);
-                if (idx != 0)
-                    Fr::mul(v[q2], d, twT[idx]);
-                else
-                    v[q2] = d;
-            }
+            Fr::mul(b, b, w);
+            Fr::add(v[q], a, b);
+            Fr::sub(v[q2], a, b);
         }
-    }
-    else
-    {
-#pragma unroll
-        for (int u = 0; u <= 2; u++)
+        else
         {
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-            {
-                if (q & (1 << u))
-                    continue;
-                int      q2  = q | (1 << u);
-                uint32_t j   = t_low + ((uint32_t)(q & ((1 << u) - 1)) << sh);
-                uint32_t idx = j << (6 - sh - u);
-                Fr       a = v[q], b = v[q2];
-                if (idx != 0)
-                    Fr::mul(b, b, twT[idx]);
-                Fr::add(v[q], a, b);
-                Fr::sub(v[q2], a, b);
-            }
+            Fr d;
+            Fr::add(v[q], a, b);
+            Fr::sub(d, a, b);
+            Fr::mul(v[q2], d, w);
         }
     }
 }
+
+// rows of the three rounds for row group g, element q
+__device__ __forceinline__ uint32_t ntt_row1(uint32_t g, uint32_t q) { return g + 16u * q; }
+__device__ __forceinline__ uint32_t ntt_row2(uint32_t g, uint32_t q) { return 32u * (g >> 2) + (g & 3u) + 4u * q; }
+__device__ __forceinline__ uint32_t ntt_row3(uint32_t g, uint32_t q) { return 8u * g + q; }
+
+// The three rounds of a 128-point DIF (R1, R2, R3) between registers: in: rows of R1, out: rows of R3.
+__device__ __forceinline__ void ntt_dif_rounds(Fr (&v)[8], uint4* wsm, const uint4* twp, uint32_t g, uint32_t e)
+{
+    // R1: half-distance 64 (q bit 2; j = g + 16 (q & 3)), 32 (q bit 1; j = g + 16 (q & 1), index j * 2)
+    ntt_stage<false, 2, false>(v, twp, g, 4, 0);
+    ntt_stage<false, 1, false>(v, twp, g, 4, 1);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        ntt_sm_store(wsm, ntt_row1(g, q), e, v[q]);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        ntt_sm_load(wsm, ntt_row2(g, q), e, v[q]);
+    // R2: half-distance 16 (j = (g & 3) + 4 (q & 3), index j * 4), 8 (j = (g & 3) + 4 (q & 1), index j * 8)
+    ntt_stage<false, 2, false>(v, twp, g & 3u, 2, 2);
+    ntt_stage<false, 1, false>(v, twp, g & 3u, 2, 3);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        ntt_sm_store(wsm, ntt_row2(g, q), e, v[q]);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        ntt_sm_load(wsm, ntt_row3(g, q), e, v[q]);
+    __syncwarp();
+    // R3: half-distance 4 (j = q & 3, index j * 16), 2 (j = q & 1, index j * 32), 1 (no twiddle)
+    ntt_stage<false, 2, true>(v, twp, 0, 0, 4);
+    ntt_stage<false, 1, true>(v, twp, 0, 0, 5);
+    ntt_stage<false, 0, true>(v, twp, 0, 0, 6);
+}
+
+// The three rounds of a 128-point DIT (R3, R2, R1): in: rows of R3, out: rows of R1.
+__device__ __forceinline__ void ntt_dit_rounds(Fr (&v)[8], uint4* wsm, const uint4* twp, uint32_t g, uint32_t e)
+{
+    ntt_stage<true, 0, true>(v, twp, 0, 0, 6);
+    ntt_stage<true, 1, true>(v, twp, 0, 0, 5);
+    ntt_stage<true, 2, true>(v, twp, 0, 0, 4);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        ntt_sm_store(wsm, ntt_row3(g, q), e, v[q]);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        ntt_sm_load(wsm, ntt_row2(g, q), e, v[q]);
+    ntt_stage<true, 1, false>(v, twp, g & 3u, 2, 3);
+    ntt_stage<true, 2, false>(v, twp, g & 3u, 2, 2);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        ntt_sm_store(wsm, ntt_row2(g, q), e, v[q]);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        ntt_sm_load(wsm, ntt_row1(g, q), e, v[q]);
+    __syncwarp();
+    ntt_stage<true, 1, false>(v, twp, g, 4, 1);
+    ntt_stage<true, 2, false>(v, twp, g, 4, 0);
+}
+
+constexpr size_t kNttWarpSmem  = 2 * 256 * sizeof(uint4);                                   // two planes of 256 slots
+constexpr size_t kNttLevelSmem = (kNttThreads / 32) * kNttWarpSmem + 2 * 64 * sizeof(uint4); // + one twiddle table
+constexpr size_t kNttMidSmem   = (kNttThreads / 32) * kNttWarpSmem + 4 * 64 * sizeof(uint4); // + two twiddle tables
 
 // One level on bits [lo, lo+7) of a size-2^k transform. tw: w^i (forward) or w^-i (inverse), i < 2^(k-1).
 // post (DIF only, may be null): element at position pos is multiplied by post[pos] on the way out.
@@ -143,220 +208,110 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
 {
     Fr* __restrict__        x = batch.x[blockIdx.y];
     extern __shared__ uint4 ntt_smem[];
-    uint4*                  sm  = ntt_smem;                                   // 2 planes x 2048 uint4
-    Fr*                     twT = reinterpret_cast<Fr*>(ntt_smem + 2 * kNttTileElems); // 64 roots of order 128
-    const uint32_t          tid = threadIdx.x;
+    const uint32_t          tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint4*                  wsm = ntt_smem + warp * (kNttWarpSmem / sizeof(uint4));
+    uint4*                  twp = ntt_smem + (kNttThreads / 32) * (kNttWarpSmem / sizeof(uint4));
     const uint32_t          hi  = lo + kNttTileBits;
     if (tid < 64)
-        twT[tid] = tw[(size_t)tid << (k - kNttTileBits)];
-
-    const uint32_t rest0    = blockIdx.x * kNttTileCols;
-    const uint32_t low_mask = (1u << lo) - 1u;
-    // element (t, c) of this CTA lives at global position pos(t, c)
-    auto pos_of = [&](uint32_t t, uint32_t c) -> uint32_t {
-        uint32_t rest = rest0 + c;
-        return ((rest >> lo) << hi) | (t << lo) | (rest & low_mask);
-    };
-
-    // ---- load (coalesced), boundary twiddle for DIT
-#pragma unroll
-    for (int q = 0; q < 8; q++)
-    {
-        uint32_t e = tid + (uint32_t)kNttThreads * q;
-        uint32_t t, c;
-        if (lo == 0)
-        {
-            c = e >> 7;
-            t = e & 127u;
-        }
-        else
-        {
-            t = e >> kNttColBits;
-            c = e & (uint32_t)(kNttTileCols - 1);
-        }
-        uint32_t pos = pos_of(t, c);
-        Fr       val = x[pos];
-        if (DIT && lo > 0)
-        {
-            uint32_t upper = pos >> lo;
-            uint32_t brv   = __brev(upper) >> (32 - (k - lo));
-            uint32_t kt    = (pos >> plo) & ((1u << (lo - plo)) - 1u);
-            uint32_t ex    = (brv * kt) << plo;
-            if (ex != 0)
-            {
-                Fr w;
-                ntt_root(w, tw, ex, k);
-                Fr::mul(val, val, w);
-            }
-        }
-        ntt_sm_store(sm, t, c, val);
-    }
+        ntt_tw_fill(twp, tw, tid, k);
     __syncthreads();
 
-    // ---- three rounds of radix-8 butterflies in registers
-    const uint32_t c = tid & (uint32_t)(kNttTileCols - 1);
-    const uint32_t g = tid >> kNttColBits; // 0..15
+    const uint32_t e = lane >> 4, g = lane & 15u;
+    const uint32_t rest     = blockIdx.x * kNttTileCols + 2u * warp + e;
+    const uint32_t low_mask = (1u << lo) - 1u;
+    const uint32_t col_base = ((rest >> lo) << hi) | (rest & low_mask); // position of row 0 of this column
     Fr             v[8];
-#pragma unroll 1
-    for (int r = 0; r < 3; r++)
+    if (!DIT)
     {
-        int      round = DIT ? 2 - r : r; // DIF: A, B, C ; DIT: C, B, A
-        uint32_t t_rest, sh;
-        int      nst;
-        if (round == 0)
-        {
-            t_rest = g;
-            sh     = 4;
-            nst    = 3;
-        }
-        else if (round == 1)
-        {
-            t_rest = (g >> 1) * 16u + (g & 1u);
-            sh     = 1;
-            nst    = 3;
-        }
-        else
-        {
-            t_rest = g * 8u;
-            sh     = 0;
-            nst    = 1;
-        }
 #pragma unroll
         for (int q = 0; q < 8; q++)
-            ntt_sm_load(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
-        ntt_round<DIT>(v, twT, t_rest & ((1u << sh) - 1u), sh, nst);
+            v[q] = x[col_base | (ntt_row1(g, q) << lo)];
+        ntt_dif_rounds(v, wsm, twp, g, e);
 #pragma unroll
         for (int q = 0; q < 8; q++)
-            ntt_sm_store(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
-        __syncthreads();
-    }
-
-    // ---- store (coalesced), boundary twiddle for DIF, optional pointwise post-multiplier
-#pragma unroll
-    for (int q = 0; q < 8; q++)
-    {
-        uint32_t e = tid + (uint32_t)kNttThreads * q;
-        uint32_t t, cc;
-        if (lo == 0)
         {
-            cc = e >> 7;
-            t  = e & 127u;
-        }
-        else
-        {
-            t  = e >> kNttColBits;
-            cc = e & (uint32_t)(kNttTileCols - 1);
-        }
-        uint32_t pos = pos_of(t, cc);
-        Fr       val;
-        ntt_sm_load(sm, t, cc, val);
-        if (!DIT && lo > 0)
-        {
-            uint32_t m  = pos & low_mask;
-            uint32_t ex = (m * (__brev(t) >> 25)) << (k - hi);
-            if (ex != 0)
+            uint32_t t   = ntt_row3(g, q);
+            uint32_t pos = col_base | (t << lo);
+            if (lo > 0)
             {
-                Fr w;
-                ntt_root(w, tw, ex, k);
-                Fr::mul(val, val, w);
+                uint32_t m  = pos & low_mask;
+                uint32_t ex = (m * (__brev(t) >> 25)) << (k - hi);
+                if (ex != 0)
+                {
+                    Fr w;
+                    ntt_root(w, tw, ex, k);
+                    Fr::mul(v[q], v[q], w);
+                }
+            }
+            if (post)
+                Fr::mul(v[q], v[q], post[pos]);
+            x[pos] = v[q];
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+        {
+            uint32_t pos = col_base | (ntt_row3(g, q) << lo);
+            v[q]         = x[pos];
+            if (lo > 0)
+            {
+                uint32_t upper = pos >> lo;
+                uint32_t brv   = __brev(upper) >> (32 - (k - lo));
+                uint32_t kt    = (pos >> plo) & ((1u << (lo - plo)) - 1u);
+                uint32_t ex    = (brv * kt) << plo;
+                if (ex != 0)
+                {
+                    Fr w;
+                    ntt_root(w, tw, ex, k);
+                    Fr::mul(v[q], v[q], w);
+                }
             }
         }
-        if (!DIT && post)
-            Fr::mul(val, val, post[pos]);
-        x[pos] = val;
+        ntt_dit_rounds(v, wsm, twp, g, e);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            x[col_base | (ntt_row1(g, q) << lo)] = v[q];
     }
 }
 
-
 // Fused middle of the prover's ifft -> coset shift -> fft chain when k is a multiple of 7: the inverse transform's
 // last level and the forward transform's first level both act on the same 128 contiguous elements (lo = 0), so one
-// CTA runs DIF rounds A, B, C, multiplies by post[pos] (= w_2n^bitrev(pos) / n: ifft scaling + coset shift), and
-// continues with DIT rounds C, B, A. Round C of both directions uses the same thread -> element map, so the hand-over
-// happens in registers. Saves one full read + write of the vector and four shared-memory passes per chain.
+// warp runs the DIF rounds, multiplies by post[pos] (= w_2n^bitrev(pos) / n: ifft scaling + coset shift) and
+// continues with the DIT rounds. R3 is the last DIF round and the first DIT round, so the hand-over happens in
+// registers. Saves one full read + write of the vector and a shared-memory pass per chain.
 __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
     k_ntt_mid(NttBatch batch, const Fr* __restrict__ tw_inv, const Fr* __restrict__ tw_fwd, uint32_t k,
               const Fr* __restrict__ post)
 {
     Fr* __restrict__        x = batch.x[blockIdx.y];
     extern __shared__ uint4 ntt_smem[];
-    uint4*                  sm   = ntt_smem;
-    Fr*                     twI  = reinterpret_cast<Fr*>(ntt_smem + 2 * kNttTileElems);
-    Fr*                     twF  = twI + 64;
-    const uint32_t          tid  = threadIdx.x;
+    const uint32_t          tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint4*                  wsm = ntt_smem + warp * (kNttWarpSmem / sizeof(uint4));
+    uint4*                  twI = ntt_smem + (kNttThreads / 32) * (kNttWarpSmem / sizeof(uint4));
+    uint4*                  twF = twI + 128;
     if (tid < 64)
-        twI[tid] = tw_inv[(size_t)tid << (k - kNttTileBits)];
+        ntt_tw_fill(twI, tw_inv, tid, k);
     else if (tid < 128)
-        twF[tid - 64] = tw_fwd[(size_t)(tid - 64) << (k - kNttTileBits)];
-    const uint32_t base = blockIdx.x * (kNttTileCols << kNttTileBits); // 2048 contiguous elements
-#pragma unroll
-    for (int q = 0; q < 8; q++)
-    {
-        uint32_t e = tid + (uint32_t)kNttThreads * q;
-        Fr       val = x[base + e];
-        ntt_sm_store(sm, e & 127u, e >> 7, val);
-    }
+        ntt_tw_fill(twF, tw_fwd, tid - 64, k);
     __syncthreads();
-    const uint32_t c = tid & (uint32_t)(kNttTileCols - 1);
-    const uint32_t g = tid >> kNttColBits;
+    const uint32_t e = lane >> 4, g = lane & 15u;
+    const uint32_t col_base = (blockIdx.x * kNttTileCols + 2u * warp + e) << kNttTileBits; // 128 contiguous elements
     Fr             v[8];
-    // DIF rounds A and B through shared memory
-#pragma unroll 1
-    for (int round = 0; round < 2; round++)
-    {
-        uint32_t t_rest = round == 0 ? g : (g >> 1) * 16u + (g & 1u);
-        uint32_t sh     = round == 0 ? 4u : 1u;
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            ntt_sm_load(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
-        ntt_round<false>(v, twI, t_rest & ((1u << sh) - 1u), sh, 3);
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            ntt_sm_store(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
-        __syncthreads();
-    }
-    // round C of both directions in registers, with the pointwise multiplier in between
-    {
-        uint32_t t_rest = g * 8u;
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            ntt_sm_load(sm, t_rest + (uint32_t)q, c, v[q]);
-        ntt_round<false>(v, twI, 0, 0, 1);
-        const Fr* pp = post + base + c * 128u + t_rest;
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            Fr::mul(v[q], v[q], pp[q]);
-        ntt_round<true>(v, twF, 0, 0, 1);
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            ntt_sm_store(sm, t_rest + (uint32_t)q, c, v[q]);
-        __syncthreads();
-    }
-    // DIT rounds B and A
-#pragma unroll 1
-    for (int round = 1; round >= 0; round--)
-    {
-        uint32_t t_rest = round == 0 ? g : (g >> 1) * 16u + (g & 1u);
-        uint32_t sh     = round == 0 ? 4u : 1u;
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            ntt_sm_load(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
-        ntt_round<true>(v, twF, t_rest & ((1u << sh) - 1u), sh, 3);
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            ntt_sm_store(sm, t_rest + ((uint32_t)q << sh), c, v[q]);
-        __syncthreads();
-    }
 #pragma unroll
     for (int q = 0; q < 8; q++)
-    {
-        uint32_t e = tid + (uint32_t)kNttThreads * q;
-        Fr       val;
-        ntt_sm_load(sm, e & 127u, e >> 7, val);
-        x[base + e] = val;
-    }
+        v[q] = x[col_base + ntt_row1(g, q)];
+    ntt_dif_rounds(v, wsm, twI, g, e);
+    const Fr* pp = post + col_base + ntt_row3(g, 0);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        Fr::mul(v[q], v[q], pp[q]);
+    __syncwarp();
+    ntt_dit_rounds(v, wsm, twF, g, e);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        x[col_base + ntt_row1(g, q)] = v[q];
 }
-
-constexpr size_t kNttMidSmem = 2 * kNttTileElems * sizeof(uint4) + 128 * sizeof(Fr);
-constexpr size_t kNttLevelSmem = 2 * kNttTileElems * sizeof(uint4) + 64 * sizeof(Fr);
 
 } // namespace kzp
