@@ -111,7 +111,7 @@ constexpr uint32_t kMsmHeavyGrid    = 128;  // blocks of the heavy kernel (work 
 constexpr uint32_t kMsmMaxHeavy     = 1024; // heavy buckets handled that way (the rest stay thread-serial)
 constexpr uint32_t kMsmEntryBaseBits = 27;  // sorted entry = base | window << 27 | sign << 31
 constexpr uint32_t kMsmEntryBaseMask = (1u << kMsmEntryBaseBits) - 1u;
-constexpr uint32_t kMsmFoldBlock    = 128;  // buckets per block of the finalise+fold kernel
+constexpr uint32_t kMsmFoldBlock    = 128;  // buckets per block of the bucket-sum kernel
 
 struct MsmSort
 {
@@ -160,8 +160,9 @@ struct MsmScratch
     XY*       heavy_partial = nullptr; // kMsmMaxHeavy x kMsmHeavyBlocks
     XY*       heavy_sum     = nullptr; // kMsmMaxHeavy
     uint32_t* heavy_done    = nullptr; // kMsmMaxHeavy arrival counters (self-resetting)
-    XY*       s0part        = nullptr; // (buckets / kMsmFoldBlock) x 32 : per block, per low digit
-    XY*       s1part        = nullptr; // (buckets / kMsmFoldBlock) x 4  : per block, per warp
+    XY*       bsum          = nullptr; // buckets : the sum of every bucket
+    XY*       s0part        = nullptr; // (buckets / 1024) x 4 x 32 : per plane and quarter of digit 1, per digit 0
+    XY*       s1part        = nullptr; // (buckets / 1024) x 32     : per plane, per digit 1 (sum over digit 0)
     XY*       classes       = nullptr; // levels x 32 weighted class sums
     XY*       result        = nullptr; // 1 (device)
     cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr; // bracket the bucket-accumulation kernel of the last run
@@ -199,7 +200,7 @@ template <class XY>
 void msm_last_accumulate(const MsmSort& sort, const MsmScratch<XY>& s, float* ms, uint64_t* entries);
 // kernels launched by one msm_sort_run / one msm_reduce_batch
 constexpr uint32_t kMsmSortLaunches   = 4; // hist, column sums, bucket scan, scatter  |  count, scan, partition, local sort
-constexpr uint32_t kMsmReduceLaunches = 6;
+constexpr uint32_t kMsmReduceLaunches = 7; // classify, accumulate, heavy, bucket sums, plane fold, class fold, final
 
 extern template struct MsmBases<G1Xyzz>;
 extern template struct MsmBases<G2Xyzz>;

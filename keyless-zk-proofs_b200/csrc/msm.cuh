@@ -36,6 +36,7 @@ struct MsmBatchArgs
     XY*                        heavy_partial[kMsmMaxBatch];
     XY*                        heavy_sum[kMsmMaxBatch];
     uint32_t*                  heavy_done[kMsmMaxBatch];
+    XY*                        bsum[kMsmMaxBatch];
     XY*                        s0part[kMsmMaxBatch];
     XY*                        s1part[kMsmMaxBatch];
     XY*                        classes[kMsmMaxBatch];
@@ -48,8 +49,8 @@ struct MsmBatchArgs
 // the records of bucket b are exactly slots [lo/L + b, (hi-1)/L + b] for its range [lo, hi). Work per
 // thread is therefore independent of the digit distribution (a bit-heavy witness puts ~half of all
 // entries in bucket 1). blockIdx.y selects the MSM of the batch (same sort, different base table).
-template <class XY>
-__global__ void __launch_bounds__(128)
+template <class XY, int MINB>
+__global__ void __launch_bounds__(128, MINB)
     k_msm_accumulate(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
                      MsmBatchArgs<XY> args, uint32_t chunk, uint32_t n, uint32_t nbuckets)
 {
@@ -295,22 +296,18 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// ---- bucket finalisation + first fold -------------------------------------------------------------------
-// Block = kMsmFoldBlock (128) consecutive buckets, thread = bucket: sum its records (or take the heavy sum), then
-// fold inside the block: lane sums over the 4 warps (digit 0 classes) and warp sums (digit 1 class of each warp;
-// higher digits are constant over a block). grid = (buckets / 128, batch).
+// ---- bucket sums ----------------------------------------------------------------------------------------
+// Thread = bucket: sum its records (or take the heavy sum) and store the bucket's point. Every lane does the same
+// kind of work (a bucket of a uniform scalar vector spans one or two chunks). grid = (buckets / 128, batch).
 template <class XY>
 __global__ void __launch_bounds__(kMsmFoldBlock)
-    k_msm_finalize_fold(const uint32_t* __restrict__ offsets, MsmBatchArgs<XY> args, uint32_t chunk)
+    k_msm_bucket_sums(const uint32_t* __restrict__ offsets, MsmBatchArgs<XY> args, uint32_t chunk)
 {
     const uint32_t* __restrict__ heavy_slot = args.heavy_slot;
-    extern __shared__ uint4 smem_raw[];
-    XY*                     sm      = reinterpret_cast<XY*>(smem_raw);
-    const XY* __restrict__  records = args.records[blockIdx.y];
-    uint32_t                tid     = threadIdx.x;
-    uint32_t                b       = blockIdx.x * kMsmFoldBlock + tid + 1;
-    uint32_t                lo = offsets[b], hi = offsets[b + 1];
-    XY                      acc;
+    const XY* __restrict__       records    = args.records[blockIdx.y];
+    uint32_t                     b          = blockIdx.x * kMsmFoldBlock + threadIdx.x + 1;
+    uint32_t                     lo = offsets[b], hi = offsets[b + 1];
+    XY                           acc;
     XY::set_inf(acc);
     if (lo != hi)
     {
@@ -330,71 +327,89 @@ __global__ void __launch_bounds__(kMsmFoldBlock)
             }
         }
     }
-    // Fold inside the block with as few idle lanes as the data allows: warp 0 sums over the 4 warps (digit-0 classes,
-    // 3 additions on 32 lanes) while warps 1 and 2 run the first level of all four warp-sum trees at once (64 lanes);
-    // the remaining 4 levels (32, 16, 8, 4 lanes) run on one warp. 9 warp-wide additions instead of 23.
-    XY* sm2 = sm + kMsmFoldBlock; // 64 entries: [row][16]
-    sm[tid] = acc;
-    __syncthreads();
-    if (tid < 32)
+    args.bsum[blockIdx.y][b - 1] = acc;
+}
+
+// lane exchange of a whole point (for the shuffle trees below)
+template <class XY>
+__device__ __forceinline__ XY shfl_xor_point(const XY& p, int mask)
+{
+    XY              r;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&p);
+    uint32_t*       dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(XY) / 4); i++)
+        dst[i] = __shfl_xor_sync(0xffffffffu, src[i], mask);
+    return r;
+}
+
+// ---- first fold: one plane of 1024 buckets (base-32 digits d1, d0 of the bucket index) per block -----------
+// Threads 0..127 = (row d1, quarter): 8 consecutive buckets each, then a shuffle tree over the 4 quarters -> the
+// row sum s1part[plane][d1] (sum over d0; feeds digit classes 1 and up). Threads 128..255 = (quarter of d1, d0):
+// 8 buckets 32 apart -> s0q[plane][quarter][d0] (partial sums over d1; feed the digit-0 classes). All lanes run the
+// same 7 sequential additions: no idle lanes as in a per-warp tree over 32 buckets. grid = (buckets / 1024, batch).
+template <class XY>
+__global__ void __launch_bounds__(256) k_msm_plane_fold(MsmBatchArgs<XY> args)
+{
+    const XY* __restrict__ bs   = args.bsum[blockIdx.y] + (size_t)blockIdx.x * 1024;
+    const uint32_t         tid  = threadIdx.x;
+    if (tid < 128)
     {
-        XY t = sm[tid];
+        const uint32_t row = tid >> 2, part = tid & 3u;
+        const XY*      src = bs + row * 32 + part * 8;
+        XY             acc = src[0];
 #pragma unroll 1
-        for (uint32_t w = 1; w < kMsmFoldBlock / 32; w++)
+        for (uint32_t k = 1; k < 8; k++)
         {
-            XY u = sm[32 * w + tid];
-            cold_add(t, u);
+            XY r = src[k];
+            cold_add(acc, r);
         }
-        args.s0part[blockIdx.y][(size_t)blockIdx.x * 32 + tid] = t;
-    }
-    else if (tid < 96)
-    {
-        uint32_t i = tid - 32, row = i >> 4, k = i & 15;
-        XY       a = sm[row * 32 + k], c = sm[row * 32 + k + 16];
-        cold_add(a, c);
-        sm2[row * 16 + k] = a;
-    }
-    __syncthreads();
-    if (tid < 32)
-    {
 #pragma unroll 1
-        for (uint32_t width = 8; width > 0; width >>= 1)
+        for (int m = 1; m <= 2; m <<= 1)
         {
-            // 4 rows x `width` lanes: entry k of a row takes entry k + width
-            if (tid < 4 * width)
-            {
-                uint32_t row = tid / width, k = tid % width;
-                XY       a = sm2[row * 16 + k], c = sm2[row * 16 + k + width];
-                cold_add(a, c);
-                sm2[row * 16 + k] = a;
-            }
-            __syncwarp();
+            XY o = shfl_xor_point(acc, m);
+            cold_add(acc, o);
         }
-        if (tid < kMsmFoldBlock / 32)
-            args.s1part[blockIdx.y][(size_t)blockIdx.x * (kMsmFoldBlock / 32) + tid] = sm2[tid * 16];
+        if (part == 0)
+            args.s1part[blockIdx.y][(size_t)blockIdx.x * 32 + row] = acc;
+    }
+    else
+    {
+        const uint32_t t = tid - 128, q4 = t >> 5, d0 = t & 31u;
+        const XY*      src = bs + (q4 * 8) * 32 + d0;
+        XY             acc = src[0];
+#pragma unroll 1
+        for (uint32_t k = 1; k < 8; k++)
+        {
+            XY r = src[k * 32];
+            cold_add(acc, r);
+        }
+        args.s0part[blockIdx.y][((size_t)blockIdx.x * 4 + q4) * 32 + d0] = acc;
     }
 }
 
-// ---- second fold: the levels x 32 class sums -----------------------------------------------------
+// ---- second fold: the levels x 32 class sums ---------------------------------------------------------------
 // Block (l, v) sums every partial of the buckets whose base-32 digit l equals v and scales it by 32^l.
-// grid = (32 * levels, batch), 256 threads.
+//   l = 0: s0part[plane][quarter][v] over all planes and quarters
+//   l = 1: s1part[plane][v] over all planes
+//   l >= 2: digit l of the index is digit l - 2 of the plane number: all 32 rows of the matching planes
+// grid = (32 * levels, batch).
 template <class XY>
 __global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args, uint32_t nbuckets)
 {
     extern __shared__ uint4 smem_raw[];
-    XY*                     sm   = reinterpret_cast<XY*>(smem_raw);
-    const uint32_t          nblk = nbuckets / kMsmFoldBlock;
-    constexpr uint32_t      wpb  = kMsmFoldBlock / 32; // warps (digit-1 classes) per fold block
-    const XY* __restrict__  s0   = args.s0part[blockIdx.y];
-    const XY* __restrict__  s1   = args.s1part[blockIdx.y];
-    uint32_t                tid  = threadIdx.x;
-    uint32_t                l    = blockIdx.x >> 5;
-    uint32_t                v    = blockIdx.x & 31;
+    XY*                     sm     = reinterpret_cast<XY*>(smem_raw);
+    const uint32_t          planes = nbuckets >> 10;
+    const XY* __restrict__  s0     = args.s0part[blockIdx.y];
+    const XY* __restrict__  s1     = args.s1part[blockIdx.y];
+    uint32_t                tid    = threadIdx.x;
+    uint32_t                l      = blockIdx.x >> 5;
+    uint32_t                v      = blockIdx.x & 31;
     XY                      acc;
     XY::set_inf(acc);
     if (l == 0)
     {
-        for (uint32_t t = tid; t < nblk; t += blockDim.x)
+        for (uint32_t t = tid; t < planes * 4; t += blockDim.x)
         {
             XY r = s0[(size_t)t * 32 + v];
             cold_add(acc, r);
@@ -402,29 +417,26 @@ __global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args, uint32
     }
     else if (l == 1)
     {
-        // fold block blk holds digit-1 values wpb * (blk % (32 / wpb)) + w
-        constexpr uint32_t period = 32 / wpb;
-        for (uint32_t t = tid; t < nblk / period; t += blockDim.x)
+        for (uint32_t t = tid; t < planes; t += blockDim.x)
         {
-            XY r = s1[(size_t)(t * period + v / wpb) * wpb + (v % wpb)];
+            XY r = s1[(size_t)t * 32 + v];
             cold_add(acc, r);
         }
     }
     else
     {
-        // digit l of idx = blk * 128 + .. is ((blk >> shift) & 31) with shift = 5 l - 7: whole blocks
-        uint32_t shift = 5 * l - 7;
-        uint32_t span  = 1u << shift;                 // consecutive blocks sharing the digit
-        uint32_t reps  = (nblk + (span << 5) - 1) / (span << 5);
-        uint32_t nterm = reps * span * wpb;
+        // planes p with ((p >> shift) & 31) == v, shift = 5 (l - 2); term t = (matching plane index, row)
+        uint32_t shift = 5 * (l - 2);
+        uint32_t span  = 1u << shift; // consecutive planes sharing the digit
+        uint32_t reps  = (planes + (span << 5) - 1) / (span << 5);
+        uint32_t nterm = reps * span * 32;
         for (uint32_t t = tid; t < nterm; t += blockDim.x)
         {
-            uint32_t w   = t % wpb;
-            uint32_t q   = t / wpb;
-            uint32_t blk = ((q >> shift) << (shift + 5)) | (v << shift) | (q & (span - 1));
-            if (blk < nblk)
+            uint32_t row = t & 31u, q = t >> 5;
+            uint32_t pl  = ((q >> shift) << (shift + 5)) | (v << shift) | (q & (span - 1));
+            if (pl < planes)
             {
-                XY r = s1[(size_t)blk * wpb + w];
+                XY r = s1[(size_t)pl * 32 + row];
                 cold_add(acc, r);
             }
         }
@@ -671,8 +683,6 @@ static void msm_set_smem_attrs()
 {
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_heavy<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(256 * sizeof(XY))));
-    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_finalize_fold<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)((kMsmFoldBlock + 64) * sizeof(XY))));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_fold2<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(256 * sizeof(XY))));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_final<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -685,7 +695,6 @@ void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort, uint32_t chunk)
     msm_set_smem_attrs<XY>(); // function attributes are per device: set on the device that owns the scratch
     s.shape     = sort.shape;
     size_t nb   = (size_t)s.shape.buckets + 2;
-    size_t nblk = s.shape.buckets / kMsmFoldBlock;
     s.chunk     = chunk ? chunk : msm_default_chunk(sort.n);
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_count, 4 * (1 + kMsmMaxBatch))); // [0] heavy buckets, [1..] accumulate tickets
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_ids, kMsmMaxHeavy * 4));
@@ -695,8 +704,10 @@ void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort, uint32_t chunk)
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_sum, (size_t)kMsmMaxHeavy * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_done, (size_t)kMsmMaxHeavy * 4));
     KZP_CUDA_CHECK(cudaMemset(s.heavy_done, 0, (size_t)kMsmMaxHeavy * 4));
-    KZP_CUDA_CHECK(cudaMalloc(&s.s0part, nblk * 32 * sizeof(XY)));
-    KZP_CUDA_CHECK(cudaMalloc(&s.s1part, nblk * (kMsmFoldBlock / 32) * sizeof(XY)));
+    size_t planes = s.shape.buckets >> 10;
+    KZP_CUDA_CHECK(cudaMalloc(&s.bsum, (size_t)s.shape.buckets * sizeof(XY)));
+    KZP_CUDA_CHECK(cudaMalloc(&s.s0part, planes * 4 * 32 * sizeof(XY)));
+    KZP_CUDA_CHECK(cudaMalloc(&s.s1part, planes * 32 * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.classes, (size_t)kMsmMaxLevels * 32 * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.result, sizeof(XY)));
     KZP_CUDA_CHECK(cudaEventCreate(&s.ev_acc0));
@@ -713,6 +724,7 @@ void msm_scratch_destroy(MsmScratch<XY>& s)
     cudaFree(s.heavy_partial);
     cudaFree(s.heavy_sum);
     cudaFree(s.heavy_done);
+    cudaFree(s.bsum);
     cudaFree(s.s0part);
     cudaFree(s.s1part);
     cudaFree(s.classes);
@@ -725,7 +737,7 @@ void msm_scratch_destroy(MsmScratch<XY>& s)
 }
 
 // CTAs of the accumulate kernel that are resident at once on the current device (occupancy x SMs)
-template <class XY>
+template <class XY, int MINB>
 static unsigned int msm_resident_blocks()
 {
     static thread_local int cached_dev = -1;
@@ -735,7 +747,7 @@ static unsigned int msm_resident_blocks()
     if (dev != cached_dev)
     {
         int per_sm = 0, sms = 0;
-        KZP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msm_accumulate<XY>, 128, 0));
+        KZP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_msm_accumulate<XY, MINB>, 128, 0));
         KZP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         cached     = (unsigned int)std::max(1, per_sm * sms);
         cached_dev = dev;
@@ -761,6 +773,7 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
         a.heavy_partial[k] = scr[j]->heavy_partial;
         a.heavy_sum[k]     = scr[j]->heavy_sum;
         a.heavy_done[k]    = scr[j]->heavy_done;
+        a.bsum[k]          = scr[j]->bsum;
         a.s0part[k]        = scr[j]->s0part;
         a.s1part[k]        = scr[j]->s1part;
         a.classes[k]       = scr[j]->classes;
@@ -784,11 +797,23 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     if (sort.n > 0)
     {
         uint64_t threads = ((uint64_t)sort.cap_entries + chunk - 1) / chunk;
-        by.x             = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY>());
-        static const int acc_smem = getenv("KZP_ACC_SMEM") ? atoi(getenv("KZP_ACC_SMEM")) : 0; // experiment: cap occupancy
-        if (acc_smem > 48 * 1024)
-            KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_accumulate<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize, acc_smem));
-        k_msm_accumulate<XY><<<by, 128, (size_t)(nb == 1 && sizeof(XY) == 128 ? acc_smem : 0), st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
+        // resident CTAs per SM the kernel is compiled for (register cap): KZP_ACC_OCC = 4 | 5 | 6 (G1 only)
+        static const int occ = getenv("KZP_ACC_OCC") ? atoi(getenv("KZP_ACC_OCC")) : 4;
+        if (sizeof(XY) == 128 && occ == 5)
+        {
+            by.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 5>());
+            k_msm_accumulate<XY, 5><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
+        }
+        else if (sizeof(XY) == 128 && occ == 6)
+        {
+            by.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 6>());
+            k_msm_accumulate<XY, 6><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
+        }
+        else
+        {
+            by.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 1>());
+            k_msm_accumulate<XY, 1><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
+        }
         KZP_CUDA_CHECK(cudaGetLastError());
     }
     KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc1, st));
@@ -805,7 +830,10 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     k_msm_heavy<XY><<<by, heavy_t, heavy_t * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = nbuckets / kMsmFoldBlock;
-    k_msm_finalize_fold<XY><<<by, kMsmFoldBlock, (kMsmFoldBlock + 64) * sizeof(XY), st>>>(sort.offsets, a, chunk);
+    k_msm_bucket_sums<XY><<<by, kMsmFoldBlock, 0, st>>>(sort.offsets, a, chunk);
+    KZP_CUDA_CHECK(cudaGetLastError());
+    by.x = nbuckets >> 10;
+    k_msm_plane_fold<XY><<<by, 256, 0, st>>>(a);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = 32 * sort.shape.levels;
     k_msm_fold2<XY><<<by, fold2_t, fold2_t * sizeof(XY), st>>>(a, nbuckets);
