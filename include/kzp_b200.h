@@ -65,6 +65,16 @@ typedef struct kzp_prover kzp_prover;
 kzp_prover* kzp_prover_new(const char* zkey_path, int device, int* state_out);
 /* MSM base ranges of shard `rank` of `world` only; used one process per GPU. */
 kzp_prover* kzp_prover_new_sharded(const char* zkey_path, int device, int rank, int world, int* state_out);
+/* ONE proof over n_devices GPUs of this process (1..8): shard r on devices[r] holds base range r of
+ * every MSM section and computes one of the three coset-NTT chains (the reference runs them as three std::async tasks,
+ * groth16.cpp:172-262); the chain outputs cross NVLink as peer stores fused into the chain's last level (peer copies
+ * when peer access is unavailable or $KZP_GROUP_SCATTER=0), the 768-byte partial results are summed on the host.
+ * The handle behaves like any other: kzp_prover_prove / _prove_mem / _prove_resident / _upload_witness* / _run_gpu /
+ * _timings (per-stage maximum over the shards) / _get_h / _get_msm_results; kzp_prover_keep_ab is not available.
+ * devices == NULL: $KZP_SHARD_DEVICES ("0,1,2,3"). kzp_prover_new(path, -1, ..) — and therefore the reference-shaped
+ * FullProver::FullProver(zkeyPath) — builds a group whenever $KZP_SHARD_DEVICES is set. */
+kzp_prover* kzp_prover_new_group(const char* zkey_path, const int* devices, int n_devices, int* state_out);
+int         kzp_prover_group_info(kzp_prover* p, int* shards, int* fused_exchange); /* 1 shard = single-GPU prover */
 void        kzp_prover_free(kzp_prover* p); /* FullProver::~FullProver */
 
 /* FullProver::prove(const char* wtnsPath) — fullprover.cpp:114-125,204-250.

@@ -100,6 +100,8 @@ def lib() -> ctypes.CDLL:
         "kzp_free": (None, [vp]),
         "kzp_prover_new": (vp, [c.c_char_p, c.c_int, i32p]),
         "kzp_prover_new_sharded": (vp, [c.c_char_p, c.c_int, c.c_int, c.c_int, i32p]),
+        "kzp_prover_new_group": (vp, [c.c_char_p, c.POINTER(c.c_int), c.c_int, i32p]),
+        "kzp_prover_group_info": (c.c_int, [vp, i32p, i32p]),
         "kzp_prover_free": (None, [vp]),
         "kzp_prover_prove": (c.c_int, [vp, c.c_char_p, u8p, u8p, c.POINTER(vp), i32p, i32p]),
         "kzp_prover_prove_mem": (c.c_int, [vp, u8p, c.c_uint64, u8p, u8p, c.POINTER(vp), i32p, i32p]),
@@ -194,10 +196,16 @@ class FullProver:
     ``metrics["prover_time"]`` is in milliseconds, and raises the ProverError variants of the Rust binding.
     """
 
-    def __init__(self, zkey_path: str, device: int = -1, shard: Optional[Tuple[int, int]] = None):
+    def __init__(self, zkey_path: str, device: int = -1, shard: Optional[Tuple[int, int]] = None,
+                 devices: Optional[Sequence[int]] = None):
+        """``devices=[0, 1, ...]``: one proof sharded over those GPUs inside every prove call (kzp_prover_new_group);
+        ``shard=(rank, world)``: one shard of the one-process-per-GPU mode; neither: one GPU (or $KZP_SHARD_DEVICES)."""
         L = lib()
         st = ctypes.c_int(0)
-        if shard is None:
+        if devices is not None:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            self._h = L.kzp_prover_new_group(os.fsencode(zkey_path), arr, len(devices), ctypes.byref(st))
+        elif shard is None:
             self._h = L.kzp_prover_new(os.fsencode(zkey_path), device, ctypes.byref(st))
         else:
             self._h = L.kzp_prover_new_sharded(os.fsencode(zkey_path), device, shard[0], shard[1], ctypes.byref(st))
@@ -215,6 +223,12 @@ class FullProver:
                                  ctypes.byref(dev)))
         self.n_vars, self.n_public, self.domain_size = nv.value, npub.value, dom.value
         self.n_coefs, self.device = nc.value, dev.value
+
+    def group_info(self) -> Tuple[int, bool]:
+        """(number of shards, whether the slices travel as fused peer stores)"""
+        n, f = ctypes.c_int(), ctypes.c_int()
+        _check(lib().kzp_prover_group_info(self._h, ctypes.byref(n), ctypes.byref(f)))
+        return n.value, bool(f.value)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -107,7 +107,8 @@ static bool device_is_dead()
     return e != cudaSuccess && e != cudaErrorMemoryAllocation;
 }
 
-kzp_prover* kzp_prover_new_sharded(const char* zkey_path, int device, int rank, int world, int* state_out)
+template <class Make>
+static kzp_prover* new_prover_handle(Make&& make, int* state_out)
 {
     kzp_prover* h = new (std::nothrow) kzp_prover();
     if (!h)
@@ -116,7 +117,7 @@ kzp_prover* kzp_prover_new_sharded(const char* zkey_path, int device, int rank, 
     {
         if (kzp_device_count() == 0)
             throw CudaError("no CUDA device available (this library has no CPU fallback)");
-        h->prover = new DeviceProver(zkey_path ? zkey_path : "", pick_device(device), rank, world);
+        h->prover = make();
         h->state  = KZP_STATE_OK;
     }
     catch (const LoadError& e)
@@ -147,9 +148,73 @@ kzp_prover* kzp_prover_new_sharded(const char* zkey_path, int device, int rank, 
     return h;
 }
 
+kzp_prover* kzp_prover_new_sharded(const char* zkey_path, int device, int rank, int world, int* state_out)
+{
+    return new_prover_handle([&] { return new DeviceProver(zkey_path ? zkey_path : "", pick_device(device), rank, world); },
+                             state_out);
+}
+
+// "0,1,2,3" -> {0, 1, 2, 3}; anything that is not a list of small non-negative integers -> empty
+static std::vector<int> parse_device_list(const char* text)
+{
+    std::vector<int> out;
+    if (!text)
+        return out;
+    const char* p = text;
+    while (*p)
+    {
+        while (*p == ' ' || *p == ',')
+            p++;
+        if (!*p)
+            break;
+        if (*p < '0' || *p > '9')
+            return {};
+        int v = 0;
+        while (*p >= '0' && *p <= '9' && v < 100000)
+            v = v * 10 + (*p++ - '0');
+        out.push_back(v);
+    }
+    return out;
+}
+
+kzp_prover* kzp_prover_new_group(const char* zkey_path, const int* devices, int n_devices, int* state_out)
+{
+    std::vector<int> devs;
+    if (devices && n_devices > 0)
+        devs.assign(devices, devices + n_devices);
+    else
+        devs = parse_device_list(getenv("KZP_SHARD_DEVICES"));
+    return new_prover_handle(
+        [&]() -> DeviceProver* {
+            if (devs.empty())
+                throw FormatError("no devices listed for the prover group (argument or $KZP_SHARD_DEVICES)");
+            return new DeviceProver(zkey_path ? zkey_path : "", devs);
+        },
+        state_out);
+}
+
 kzp_prover* kzp_prover_new(const char* zkey_path, int device, int* state_out)
 {
+    // $KZP_SHARD_DEVICES="0,1,..." turns every prover made through the reference-shaped constructor (device < 0:
+    // "you choose") into one proof sharded over those GPUs — FullProver::FullProver(zkeyPath) has no other knob
+    if (device < 0)
+    {
+        const char* sd = getenv("KZP_SHARD_DEVICES");
+        if (sd && *sd)
+            return kzp_prover_new_group(zkey_path, nullptr, 0, state_out);
+    }
     return kzp_prover_new_sharded(zkey_path, device, 0, 1, state_out);
+}
+
+int kzp_prover_group_info(kzp_prover* p, int* shards, int* fused_exchange)
+{
+    if (!p || !p->prover)
+        return KZP_ERR_STATE;
+    if (shards)
+        *shards = p->prover->group_size();
+    if (fused_exchange)
+        *fused_exchange = p->prover->group_fused_exchange() ? 1 : 0;
+    return KZP_OK;
 }
 
 void kzp_prover_free(kzp_prover* p)

@@ -51,9 +51,21 @@ void ntt_domain_destroy(NttDomain& d);
 void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st);
 void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st);
 uint32_t ntt_launches(uint32_t log_n); // kernels per transform
+// Where the last level of a chain stores its natural-order output when one proof is sharded over several GPUs
+// (SURVEY.md 8(e)): position pos of vector i goes to dst[i][r] + pos for the shard r with bound[r] <= pos < bound[r+1]
+// — a peer-mapped pointer over NVLink, or the launching device's own buffer. Every element is written exactly once.
+constexpr int kNttMaxShards = 8;
+struct NttScatter
+{
+    Fr*      dst[3][kNttMaxShards];
+    uint32_t bound[kNttMaxShards + 1];
+    int      world;
+};
+// the batched path of ntt_coset_chain (which is the only one that can scatter) applies to this size
+bool ntt_chain_is_batched(uint32_t log_n);
 // ifft -> coset shift -> fft (groth16.cpp:172-262) on `count` <= 3 vectors, all of them through each launch together;
-// returns the number of kernels launched
-uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st);
+// returns the number of kernels launched. scatter (optional, batched path only): see NttScatter.
+uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st, const NttScatter* scatter = nullptr);
 // natural <-> bit-reversed permutation (only used by the component-level entry points that expose
 // the reference's natural-in/natural-out FFT::fft / FFT::ifft contract, fft.cpp:192-246)
 void ntt_bitrev_permute(Fr* x, uint32_t log_n, cudaStream_t st);
@@ -68,8 +80,8 @@ struct CoefCsr
     uint32_t* wire    = nullptr; // nnz
     Fr*       coef    = nullptr; // nnz, value * R^2 mod r exactly as stored in zkey section 4
 };
-// a = A.w, b = B.w (Montgomery), c = a o b. w: raw canonical witness values.
-void spmv_abc(const CoefCsr& m, const Fr* w, Fr* a, Fr* b, Fr* c, cudaStream_t st);
+// a = A.w, b = B.w (Montgomery), c = a o b. w: raw canonical witness values. which: bit 0 / 1 / 2 = write a / b / c.
+void spmv_abc(const CoefCsr& m, const Fr* w, Fr* a, Fr* b, Fr* c, cudaStream_t st, uint32_t which = 7);
 // h[i] = fromMontgomery(a[i]*b[i] - c[i])  (groth16.cpp:266-275)
 void h_pointwise(const Fr* a, const Fr* b, const Fr* c, Fr* h, uint64_t n, cudaStream_t st);
 

@@ -22,41 +22,51 @@ static inline unsigned int div_up(uint64_t a, uint64_t b) { return (unsigned int
 // =====================================================================================================
 // SpMV + pointwise
 // =====================================================================================================
+// which: bit 0 = write a, bit 1 = write b, bit 2 = write c (= a o b). A shard of a multi-GPU proof that owns only one
+// of the three vectors computes only the row sums that vector needs and leaves the other buffers alone (peers write
+// their slices into them).
 __global__ void __launch_bounds__(256)
     k_spmv_abc(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ wire,
                const Fr* __restrict__ coef, const Fr* __restrict__ w, Fr* __restrict__ a,
-               Fr* __restrict__ b, Fr* __restrict__ c, uint32_t n_rows)
+               Fr* __restrict__ b, Fr* __restrict__ c, uint32_t n_rows, uint32_t which)
 {
     uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_rows)
         return;
     uint32_t e0 = row_ptr[2 * row], e1 = row_ptr[2 * row + 1], e2 = row_ptr[2 * row + 2];
     Fr       sa = Fr::zero(), sb = Fr::zero(), t;
-    for (uint32_t e = e0; e < e1; e++)
+    if (which & 5u)
+        for (uint32_t e = e0; e < e1; e++)
+        {
+            Fr ws = w[wire[e]];
+            if (Fr::is_zero(ws))
+                continue;
+            Fr::mul(t, ws, coef[e]);
+            Fr::add(sa, sa, t);
+        }
+    if (which & 6u)
+        for (uint32_t e = e1; e < e2; e++)
+        {
+            Fr ws = w[wire[e]];
+            if (Fr::is_zero(ws))
+                continue;
+            Fr::mul(t, ws, coef[e]);
+            Fr::add(sb, sb, t);
+        }
+    if (which & 1u)
+        a[row] = sa;
+    if (which & 2u)
+        b[row] = sb;
+    if (which & 4u)
     {
-        Fr ws = w[wire[e]];
-        if (Fr::is_zero(ws))
-            continue;
-        Fr::mul(t, ws, coef[e]);
-        Fr::add(sa, sa, t);
+        Fr::mul(t, sa, sb);
+        c[row] = t;
     }
-    for (uint32_t e = e1; e < e2; e++)
-    {
-        Fr ws = w[wire[e]];
-        if (Fr::is_zero(ws))
-            continue;
-        Fr::mul(t, ws, coef[e]);
-        Fr::add(sb, sb, t);
-    }
-    a[row] = sa;
-    b[row] = sb;
-    Fr::mul(t, sa, sb);
-    c[row] = t;
 }
 
-void spmv_abc(const CoefCsr& m, const Fr* w, Fr* a, Fr* b, Fr* c, cudaStream_t st)
+void spmv_abc(const CoefCsr& m, const Fr* w, Fr* a, Fr* b, Fr* c, cudaStream_t st, uint32_t which)
 {
-    k_spmv_abc<<<div_up(m.n_rows, 256), 256, 0, st>>>(m.row_ptr, m.wire, m.coef, w, a, b, c, m.n_rows);
+    k_spmv_abc<<<div_up(m.n_rows, 256), 256, 0, st>>>(m.row_ptr, m.wire, m.coef, w, a, b, c, m.n_rows, which);
     KZP_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -173,6 +183,7 @@ static void ntt_level_attrs()
     // per device; cheap enough to repeat
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttMidSmem));
 }
 
@@ -216,7 +227,7 @@ void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st)
         while (hi >= (uint32_t)kNttTileBits)
         {
             uint32_t lo = hi - kNttTileBits;
-            k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_inv, log_n, lo, 0, lo == 0 ? post : nullptr);
+            k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_inv, log_n, lo, 0, lo == 0 ? post : nullptr, NttScatter());
             KZP_CUDA_CHECK(cudaGetLastError());
             hi = lo;
         }
@@ -251,7 +262,7 @@ void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st)
     uint32_t     plo   = 0;
     for (uint32_t lo = r; lo + kNttTileBits <= log_n; lo += kNttTileBits)
     {
-        k_ntt_level<true><<<lgrid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_fwd, log_n, lo, plo, nullptr);
+        k_ntt_level<true><<<lgrid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_fwd, log_n, lo, plo, nullptr, NttScatter());
         KZP_CUDA_CHECK(cudaGetLastError());
         plo = lo;
     }
@@ -259,13 +270,17 @@ void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st)
 
 // The prover's H chain on `count` <= 3 vectors at once: ifft, multiply by w_2n^i, fft (groth16.cpp:172-262), all
 // vectors through each launch together. When log_n is a multiple of 7 the middle two levels run fused (k_ntt_mid).
-uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st)
+bool ntt_chain_is_batched(uint32_t log_n) { return ntt_use_levels(log_n) && log_n % kNttTileBits == 0; }
+
+uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st, const NttScatter* scatter)
 {
     uint32_t log_n = d.log_n;
     if (count < 1 || count > kNttMaxBatch)
         throw CudaError("NTT batch size out of range");
-    if (!ntt_use_levels(log_n) || log_n % kNttTileBits != 0)
+    if (!ntt_chain_is_batched(log_n))
     {
+        if (scatter)
+            throw CudaError("the scattering NTT chain needs a batched domain size");
         for (int i = 0; i < count; i++)
         {
             ntt_inverse_dif(d, xs[i], d.coset_br, st);
@@ -281,7 +296,7 @@ uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStrea
     uint32_t launches = 0;
     for (uint32_t lo = log_n - kNttTileBits; lo > 0; lo -= kNttTileBits)
     {
-        k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, nullptr);
+        k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, nullptr, NttScatter());
         KZP_CUDA_CHECK(cudaGetLastError());
         launches++;
     }
@@ -291,7 +306,10 @@ uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStrea
     uint32_t plo = 0;
     for (uint32_t lo = kNttTileBits; lo + kNttTileBits <= log_n; lo += kNttTileBits)
     {
-        k_ntt_level<true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr);
+        if (scatter && lo + kNttTileBits == log_n)
+            k_ntt_level<true, true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, *scatter);
+        else
+            k_ntt_level<true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, NttScatter());
         KZP_CUDA_CHECK(cudaGetLastError());
         plo = lo;
         launches++;

@@ -201,10 +201,12 @@ constexpr size_t kNttMidSmem   = (kNttThreads / 32) * kNttWarpSmem + 4 * 64 * si
 
 // One level on bits [lo, lo+7) of a size-2^k transform. tw: w^i (forward) or w^-i (inverse), i < 2^(k-1).
 // post (DIF only, may be null): element at position pos is multiplied by post[pos] on the way out.
-template <bool DIT>
+// SCATTER (DIT only): the level's output goes to the shard that owns each position (NttScatter), i.e. the exchange of
+// a multi-GPU proof is fused into the last level as peer stores.
+template <bool DIT, bool SCATTER = false>
 __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
     k_ntt_level(NttBatch batch, const Fr* __restrict__ tw, uint32_t k, uint32_t lo, uint32_t plo,
-                const Fr* __restrict__ post)
+                const Fr* __restrict__ post, const NttScatter sc)
 {
     Fr* __restrict__        x = batch.x[blockIdx.y];
     extern __shared__ uint4 ntt_smem[];
@@ -270,9 +272,25 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
             }
         }
         ntt_dit_rounds(v, wsm, twp, g, e);
+        if (SCATTER)
+        {
+            const int world = sc.world;
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-            x[col_base | (ntt_row1(g, q) << lo)] = v[q];
+            for (int q = 0; q < 8; q++)
+            {
+                uint32_t pos = col_base | (ntt_row1(g, q) << lo);
+                int      r   = 0;
+                while (r + 1 < world && pos >= sc.bound[r + 1])
+                    r++;
+                sc.dst[blockIdx.y][r][pos] = v[q];
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                x[col_base | (ntt_row1(g, q) << lo)] = v[q];
+        }
     }
 }
 

@@ -464,6 +464,30 @@ __global__ void __launch_bounds__(1024) k_witness_expand(const uint8_t* __restri
     }
 }
 
+// The two sources of witness values (see WitnessPacker::begin): the caller's memory, or an open .wtns file
+inline auto witness_reader_mem(const uint8_t* values)
+{
+    return [values](uint8_t*, uint64_t first, uint32_t) -> const uint8_t* { return values + first * 32; };
+}
+inline auto witness_reader_fd(int fd, uint64_t file_offset)
+{
+    return [fd, file_offset](uint8_t* bounce, uint64_t first, uint32_t count) -> const uint8_t* {
+        uint8_t* dst = bounce;
+        size_t   len = (size_t)count * 32;
+        off_t    off = (off_t)(file_offset + first * 32);
+        while (len > 0)
+        {
+            ssize_t got = ::pread(fd, dst, len, off);
+            if (got <= 0)
+                return nullptr;
+            dst += got;
+            off += got;
+            len -= (size_t)got;
+        }
+        return bounce;
+    };
+}
+
 // Persistent staging workers (spawning threads per proof costs more than the copy they do).
 class SlicePool
 {
@@ -542,6 +566,186 @@ public:
     size_t size() const { return threads_.size(); }
 };
 
+// Host half of the packed witness transfer: a pinned buffer of n_slices x kPackStride bytes and the workers that
+// classify and pack slices into it. One per prover; a group of shards (one proof over several GPUs) shares one, so
+// the witness is read and packed once and every GPU copies the same pinned bytes over its own PCIe link.
+struct PackState
+{
+    std::vector<std::atomic<int>> ready;
+    std::vector<uint32_t>         n_full;
+    std::atomic<int>              failed{0};
+    explicit PackState(size_t n_slices)
+        : ready(n_slices)
+        , n_full(n_slices, 0)
+    {
+        for (auto& r : ready)
+            r.store(0, std::memory_order_relaxed);
+    }
+    void wait_all()
+    {
+        for (auto& r : ready)
+            while (!r.load(std::memory_order_acquire))
+                std::this_thread::yield();
+    }
+};
+
+class WitnessPacker
+{
+public:
+    uint8_t*                   pinned   = nullptr; // packed slices (kPackStride each)
+    size_t                     n_slices = 0;
+    uint32_t                   n_vars   = 0;
+    std::unique_ptr<SlicePool> pool;
+    std::function<void(size_t)> job_; // kept alive until the next begin()
+
+    // the calling thread must have a current CUDA device (the allocation is portable: valid for every device)
+    void create(uint32_t n_vars_)
+    {
+        n_vars   = n_vars_;
+        n_slices = ((size_t)n_vars + kPackWires - 1) / kPackWires;
+        KZP_CUDA_CHECK(cudaHostAlloc(&pinned, std::max<size_t>(1, n_slices) * kPackStride, cudaHostAllocPortable));
+        const char* te = getenv("KZP_UPLOAD_THREADS");
+        int         nt = te ? atoi(te) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        pool.reset(new SlicePool(std::max(nt, 0)));
+    }
+    void destroy()
+    {
+        pool.reset();
+        if (pinned)
+            cudaFreeHost(pinned);
+        pinned = nullptr;
+    }
+
+    // read(bounce, value_index, count) returns a pointer to `count` plain 32-byte values starting at wire
+    // `value_index` (either `bounce`, filled by the call, or the caller's own memory), nullptr on failure.
+    // Returns at once when there are workers; `read` and `st` must stay valid until every ready[k] is set.
+    template <class Read>
+    void begin(Read& read, PackState& st)
+    {
+        job_ = [this, &read, &st](size_t k) {
+            constexpr uint32_t          kChunk = 4096; // values per read: 128 KiB, stays in the reading core's cache
+            static thread_local uint8_t bounce[(size_t)kChunk * 32] __attribute__((aligned(64)));
+            uint32_t first_wire = (uint32_t)(k * kPackWires);
+            uint32_t in_slice   = std::min<uint32_t>(kPackWires, n_vars - first_wire);
+            uint8_t* slice      = pinned + k * kPackStride;
+            uint32_t nf         = 0;
+            for (uint32_t done = 0; done < in_slice && !st.failed.load(std::memory_order_relaxed); done += kChunk)
+            {
+                uint32_t cnt = std::min(kChunk, in_slice - done);
+                const uint8_t* src = read(bounce, (uint64_t)first_wire + done, cnt);
+                if (!src)
+                {
+                    st.failed.store(1);
+                    break;
+                }
+                uint32_t padded = (cnt + kPackGroup - 1) / kPackGroup * kPackGroup;
+                if (padded != cnt)
+                {
+                    if (src != bounce)
+                        memcpy(bounce, src, (size_t)cnt * 32);
+                    memset(bounce + (size_t)cnt * 32, 0, (size_t)(padded - cnt) * 32);
+                    src = bounce;
+                }
+                pack_values(slice, done, src, padded, &nf);
+            }
+            st.n_full[k] = nf;
+            st.ready[k].store(1, std::memory_order_release);
+        };
+        if (pool && pool->size() > 0 && n_slices > 1)
+            pool->start(n_slices, job_);
+        else
+            for (size_t k = 0; k < n_slices; k++)
+                job_(k);
+    }
+};
+
+// A fixed crew of host threads, one per shard of a multi-GPU proof: run(fn) calls fn(r) on thread r for every r and
+// returns when all are done (kernel launches of different devices must not queue behind one another on one thread).
+class Crew
+{
+    std::vector<std::thread>  threads_;
+    std::mutex                mu_;
+    std::condition_variable   cv_;
+    std::function<void(int)>  fn_;
+    uint64_t                  generation_ = 0;
+    int                       pending_    = 0;
+    bool                      stop_       = false;
+    std::atomic<uint32_t>     bar_count_{0};
+    std::atomic<uint32_t>     bar_gen_{0};
+
+    void loop(int r)
+    {
+        uint64_t seen = 0;
+        for (;;)
+        {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_)
+                    return;
+                seen = generation_;
+            }
+            fn_(r);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                pending_--;
+            }
+            cv_.notify_all();
+        }
+    }
+
+public:
+    explicit Crew(int n)
+    {
+        for (int r = 0; r < n; r++)
+            threads_.emplace_back([this, r] { loop(r); });
+    }
+    ~Crew()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_)
+            t.join();
+    }
+    int size() const { return (int)threads_.size(); }
+    // fn must not throw
+    void run(std::function<void(int)> fn)
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        fn_      = std::move(fn);
+        pending_ = (int)threads_.size();
+        generation_++;
+        cv_.notify_all();
+        cv_.wait(lk, [&] { return pending_ == 0; });
+    }
+    // to be called by every crew thread from inside fn: returns when all have arrived (they are all busy launching,
+    // so the wait is short: spin)
+    void barrier()
+    {
+        uint32_t gen = bar_gen_.load(std::memory_order_acquire);
+        if (bar_count_.fetch_add(1, std::memory_order_acq_rel) + 1 == (uint32_t)threads_.size())
+        {
+            bar_count_.store(0, std::memory_order_relaxed);
+            bar_gen_.store(gen + 1, std::memory_order_release);
+        }
+        else
+            while (bar_gen_.load(std::memory_order_acquire) == gen)
+                std::this_thread::yield();
+    }
+};
+
+class DeviceProverImpl;
+// What a shard of a multi-GPU proof knows about the others (set by ProverGroup once every shard is built).
+struct GroupLinks
+{
+    std::vector<DeviceProverImpl*> shard;
+    int  owner_of[3]   = {0, 0, 0}; // shard that computes a, b, c (SpMV + coset-NTT chain)
+    bool fused_scatter = false;     // the chain's last level stores every shard's slice straight into that shard's buffer
+};
+
 class DeviceProverImpl
 {
 public:
@@ -559,7 +763,7 @@ public:
     cudaStream_t st_h = nullptr, st_w = nullptr, st_w2 = nullptr, st_copy = nullptr;
     enum
     {
-        EV_H2D0, EV_H2D1, EV_H0, EV_SPMV, EV_NTT, EV_HMSM, EV_W0, EV_WSORT, EV_WG1, EV_WG2_0, EV_WG2, EV_COUNT
+        EV_H2D0, EV_H2D1, EV_H0, EV_SPMV, EV_NTT, EV_HMSM, EV_W0, EV_WSORT, EV_WG1, EV_WG2_0, EV_WG2, EV_XCHG, EV_COUNT
     };
     cudaEvent_t ev[EV_COUNT] = {};
 
@@ -568,9 +772,15 @@ public:
     Fr *      d_w = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_h = nullptr;
     Fr *      d_keep_a = nullptr, *d_keep_b = nullptr;
     bool      keep_ab  = false;
-    uint8_t*  pinned_w = nullptr; // packed slices (kPackStride each)
+    WitnessPacker  own_packer;        // single-GPU prover: its own pinned staging buffer and workers
+    WitnessPacker* packer = nullptr;  // the one in use (a group's shards share the group's)
     uint8_t*  d_pack   = nullptr; // device image of the packed slices
     size_t    n_pack_slices = 0;
+    // one proof over several GPUs (ProverGroup): which of a, b, c this shard computes (bit 0 / 1 / 2), its slice of
+    // the H domain, and the other shards
+    uint32_t          own_mask = 7;
+    uint64_t          h0 = 0, h1 = 0;
+    const GroupLinks* links = nullptr;
     uint64_t  h2d_bytes = 0;     // bytes the last upload moved over PCIe
     uint8_t*  pinned_out = nullptr; // 5 result points
 
@@ -581,7 +791,6 @@ public:
     MsmScratch<G2Xyzz> sc_b2;
 
     HostVk vk;
-    std::unique_ptr<SlicePool> pool; // witness staging workers
 
     ShardPartials parts;
     ShardPartials sums;       // the five MSM results of the last assemble(), summed over shards
@@ -655,10 +864,15 @@ public:
         msm_bases_create<XY>(b, cols.data(), last - first, false, st_h, window_bits);
     }
 
-    DeviceProverImpl(const std::string& path, int dev, int rank_, int world_)
+    // own_mask_: 7 for a self-contained prover (also the one-process-per-GPU shards, which recompute a, b, c);
+    // shared_packer: the staging buffer of the group this shard belongs to (nullptr: make one)
+    DeviceProverImpl(const std::string& path, int dev, int rank_, int world_, uint32_t own_mask_ = 7,
+                     WitnessPacker* shared_packer = nullptr)
         : device(dev)
         , rank(rank_)
         , world(world_)
+        , packer(shared_packer)
+        , own_mask(own_mask_)
     {
         if (world < 1 || rank < 0 || rank >= world)
             throw FormatError("invalid shard rank/world");
@@ -714,8 +928,11 @@ public:
         memcpy(vk.beta2, zh.beta2, 128);
         memcpy(vk.delta2, zh.delta2, 128);
 
-        build_csr(zh);
-        ntt_domain_create(ntt, log_domain);
+        if (own_mask) // a shard that computes none of a, b, c needs neither the matrices nor the twiddles
+        {
+            build_csr(zh);
+            ntt_domain_create(ntt, log_domain);
+        }
         size_t vec = (size_t)domain * 32;
         KZP_CUDA_CHECK(cudaMalloc(&d_w, (size_t)n_vars * 32));
         KZP_CUDA_CHECK(cudaMalloc(&d_a, vec));
@@ -723,18 +940,18 @@ public:
         KZP_CUDA_CHECK(cudaMalloc(&d_c, vec));
         KZP_CUDA_CHECK(cudaMalloc(&d_h, vec));
         n_pack_slices = ((size_t)n_vars + kPackWires - 1) / kPackWires;
-        KZP_CUDA_CHECK(cudaMallocHost(&pinned_w, std::max<size_t>(1, n_pack_slices) * kPackStride));
+        if (!packer)
+        {
+            own_packer.create(n_vars);
+            packer = &own_packer;
+        }
         KZP_CUDA_CHECK(cudaMalloc(&d_pack, std::max<size_t>(1, n_pack_slices) * kPackStride));
         KZP_CUDA_CHECK(cudaMallocHost(&pinned_out, sizeof(ShardPartials)));
-        {
-            const char* te = getenv("KZP_UPLOAD_THREADS");
-            int         nt = te ? atoi(te) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-            pool.reset(new SlicePool(std::max(nt, 0)));
-        }
 
         // this shard's base ranges: wires [w0, w1) of sections 5-8, points [h0, h1) of section 9
         uint64_t w0 = (uint64_t)rank * n_vars / (uint64_t)world, w1 = (uint64_t)(rank + 1) * n_vars / (uint64_t)world;
-        uint64_t h0 = (uint64_t)rank * domain / (uint64_t)world, h1 = (uint64_t)(rank + 1) * domain / (uint64_t)world;
+        h0 = (uint64_t)rank * domain / (uint64_t)world;
+        h1 = (uint64_t)(rank + 1) * domain / (uint64_t)world;
         make_bases(bases_a, zh.points_a, n_vars, 0, w0, w1);
         make_bases(bases_b1, zh.points_b1, n_vars, 0, w0, w1);
         make_bases(bases_b2, zh.points_b2, n_vars, 0, w0, w1);
@@ -764,13 +981,14 @@ public:
 
     void teardown()
     {
-        pool.reset();
         if (cudaSetDevice(device) != cudaSuccess)
         {
             cudaGetLastError();
+            own_packer.pool.reset();
             return; // no such device: nothing was allocated
         }
         cudaDeviceSynchronize();
+        own_packer.destroy();
         msm_bases_destroy(bases_a);
         msm_bases_destroy(bases_b1);
         msm_bases_destroy(bases_b2);
@@ -795,7 +1013,6 @@ public:
         cudaFree(d_h);
         cudaFree(d_keep_a);
         cudaFree(d_keep_b);
-        cudaFreeHost(pinned_w);
         cudaFreeHost(pinned_out);
         for (auto& e : ev)
             if (e)
@@ -812,67 +1029,27 @@ public:
     // k_witness_expand then rebuilds the plain vector in HBM.   KZP_UPLOAD_THREADS (default min(16, cores)).
     // Measured on the B200 host (16 cores), 43 MB keyless witness: plain copy 1.15 ms (DMA-bound at ~38 GB/s);
     // packed: 3.7 MB over the bus, 0.5 ms with 16 workers (pread-bound), end to end 13.6 -> 13.0 ms.
-    // read(bounce, value_index, count) returns a pointer to `count` plain 32-byte values starting at wire
-    // `value_index` (either `bounce`, filled by the call, or the caller's own memory), nullptr on failure.
-    template <class Read>
-    void upload_with(Read&& read)
+
+    // Device half: copies every slice of packer->pinned as soon as it is packed, then expands. Safe to run for several
+    // shards at once on different threads (they read the same pinned bytes).
+    void enqueue_packed(PackState& ps)
     {
         set_device();
         const size_t n_slices = n_pack_slices;
-        std::vector<std::atomic<int>> ready(n_slices);
-        std::vector<uint32_t>         n_full(n_slices, 0);
-        for (auto& r : ready)
-            r.store(0, std::memory_order_relaxed);
-        std::atomic<int> failed{0};
-        auto             job = [&](size_t k) {
-            constexpr uint32_t          kChunk = 4096; // values per read: 128 KiB, stays in the reading core's cache
-            static thread_local uint8_t bounce[(size_t)kChunk * 32] __attribute__((aligned(64)));
-            uint32_t first_wire = (uint32_t)(k * kPackWires);
-            uint32_t in_slice   = std::min<uint32_t>(kPackWires, n_vars - first_wire);
-            uint8_t* slice      = pinned_w + k * kPackStride;
-            uint32_t nf         = 0;
-            for (uint32_t done = 0; done < in_slice && !failed.load(std::memory_order_relaxed); done += kChunk)
-            {
-                uint32_t cnt = std::min(kChunk, in_slice - done);
-                const uint8_t* src = read(bounce, (uint64_t)first_wire + done, cnt);
-                if (!src)
-                {
-                    failed.store(1);
-                    break;
-                }
-                uint32_t padded = (cnt + kPackGroup - 1) / kPackGroup * kPackGroup;
-                if (padded != cnt)
-                {
-                    if (src != bounce)
-                        memcpy(bounce, src, (size_t)cnt * 32);
-                    memset(bounce + (size_t)cnt * 32, 0, (size_t)(padded - cnt) * 32);
-                    src = bounce;
-                }
-                pack_values(slice, done, src, padded, &nf);
-            }
-            n_full[k] = nf;
-            ready[k].store(1, std::memory_order_release);
-        };
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H2D0], st_copy));
-        double dbg_t0 = now_ms();
-        if (pool && pool->size() > 0 && n_slices > 1)
-            pool->start(n_slices, job);
-        else
-            for (size_t k = 0; k < n_slices; k++)
-                job(k);
         cudaError_t err   = cudaSuccess;
         uint64_t    moved = 0;
         for (size_t k = 0; k < n_slices; k++)
         {
-            while (!ready[k].load(std::memory_order_acquire))
+            while (!ps.ready[k].load(std::memory_order_acquire))
                 std::this_thread::yield();
-            size_t len = kPackHead + (size_t)n_full[k] * 32;
-            if (err == cudaSuccess && !failed.load())
-                err = cudaMemcpyAsync(d_pack + k * kPackStride, pinned_w + k * kPackStride, len, cudaMemcpyHostToDevice, st_copy);
+            size_t len = kPackHead + (size_t)ps.n_full[k] * 32;
+            if (err == cudaSuccess && !ps.failed.load())
+                err = cudaMemcpyAsync(d_pack + k * kPackStride, packer->pinned + k * kPackStride, len, cudaMemcpyHostToDevice, st_copy);
             moved += len;
         }
         KZP_CUDA_CHECK(err);
-        if (failed.load())
+        if (ps.failed.load())
             throw LoadError("reading the witness failed");
         if (n_slices > 0)
         {
@@ -880,47 +1057,63 @@ public:
             KZP_CUDA_CHECK(cudaGetLastError());
         }
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H2D1], st_copy));
-        h2d_bytes = moved;
+        h2d_bytes        = moved;
+        witness_resident = true;
+    }
+
+    template <class Read>
+    void upload_with(Read&& read)
+    {
+        set_device();
+        PackState ps(n_pack_slices);
+        double    dbg_t0 = now_ms();
+        packer->begin(read, ps);
+        try
+        {
+            enqueue_packed(ps);
+        }
+        catch (...)
+        {
+            ps.wait_all(); // the workers still use `read` and `ps`
+            throw;
+        }
         if (getenv("KZP_DEBUG_UPLOAD"))
         {
             double t1 = now_ms();
             cudaStreamSynchronize(st_copy);
             fprintf(stderr, "[kzp upload] staged+enqueued %.3f ms, DMA+expand drained +%.3f ms, %zu slices, %zu workers, %.2f MB moved\n",
-                    t1 - dbg_t0, now_ms() - t1, n_slices, pool ? pool->size() : 0, moved / 1e6);
+                    t1 - dbg_t0, now_ms() - t1, n_pack_slices, packer->pool ? packer->pool->size() : 0, h2d_bytes / 1e6);
         }
-        witness_resident = true;
     }
 
     void upload(const uint8_t* values, uint64_t n)
     {
         if (n < n_vars)
             throw FormatError("witness has fewer values than the zkey has variables");
-        upload_with([&](uint8_t*, uint64_t first, uint32_t) -> const uint8_t* { return values + first * 32; });
+        upload_with(witness_reader_mem(values));
     }
 
     void upload_fd(int fd, uint64_t file_offset, uint64_t n)
     {
         if (n < n_vars)
             throw FormatError("witness has fewer values than the zkey has variables");
-        upload_with([&](uint8_t* bounce, uint64_t first, uint32_t count) -> const uint8_t* {
-            uint8_t* dst = bounce;
-            size_t   len = (size_t)count * 32;
-            off_t    off = (off_t)(file_offset + first * 32);
-            while (len > 0)
-            {
-                ssize_t got = ::pread(fd, dst, len, off);
-                if (got <= 0)
-                    return nullptr;
-                dst += got;
-                off += got;
-                len -= (size_t)got;
-            }
-            return bounce;
-        });
+        upload_with(witness_reader_fd(fd, file_offset));
     }
+
+    Fr* vec_ptr(int i) const { return i == 0 ? d_a : (i == 1 ? d_b : d_c); }
 
     // Enqueues the whole GPU part of one proof (no host synchronisation).
     void launch_gpu()
+    {
+        launch_prefix();
+        launch_h();
+    }
+
+    // SpMV, the coset-NTT chains of the vectors this prover owns, and everything on the witness streams.
+    // In a group (links != nullptr) the chain output is handed to the other shards: either the chain's last level
+    // stores each shard's slice [h0, h1) of the H domain straight into that shard's buffer over NVLink (fused_scatter),
+    // or the finished vector is cut up with peer copies.
+    void launch_prefix()
     {
         if (!witness_resident)
             throw FormatError("no witness uploaded");
@@ -931,25 +1124,60 @@ public:
 
         // ---- stream H: SpMV -> 3 x (iNTT, coset, NTT) -> pointwise -> MSM H
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H0], st_h));
-        spmv_abc(csr, d_w, d_a, d_b, d_c, st_h);
-        if (keep_ab)
+        uint32_t ntt_kernels = 0;
+        if (own_mask)
         {
-            KZP_CUDA_CHECK(cudaMemcpyAsync(d_keep_a, d_a, (size_t)domain * 32, cudaMemcpyDeviceToDevice, st_h));
-            KZP_CUDA_CHECK(cudaMemcpyAsync(d_keep_b, d_b, (size_t)domain * 32, cudaMemcpyDeviceToDevice, st_h));
+            spmv_abc(csr, d_w, d_a, d_b, d_c, st_h, own_mask);
+            if (keep_ab)
+            {
+                KZP_CUDA_CHECK(cudaMemcpyAsync(d_keep_a, d_a, (size_t)domain * 32, cudaMemcpyDeviceToDevice, st_h));
+                KZP_CUDA_CHECK(cudaMemcpyAsync(d_keep_b, d_b, (size_t)domain * 32, cudaMemcpyDeviceToDevice, st_h));
+            }
         }
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_SPMV], st_h));
-        Fr*      vecs[3]      = {d_a, d_b, d_c};
-        uint32_t ntt_kernels = ntt_coset_chain(ntt, vecs, 3, st_h);
-        h_pointwise(d_a, d_b, d_c, d_h, domain, st_h);
-        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_NTT], st_h));
+        if (own_mask)
         {
-            const MsmBases<G1Xyzz>* b[1] = {&bases_h};
-            MsmScratch<G1Xyzz>*     s[1] = {&sc_h};
-            msm_sort_run(sort_h, reinterpret_cast<const uint32_t*>(d_h), st_h);
-            msm_reduce_batch<G1Xyzz>(sort_h, b, s, 1, st_h);
+            Fr* vecs[3];
+            int owned[3], cnt = 0;
+            for (int i = 0; i < 3; i++)
+                if (own_mask & (1u << i))
+                {
+                    owned[cnt]  = i;
+                    vecs[cnt++] = vec_ptr(i);
+                }
+            if (links && links->fused_scatter)
+            {
+                NttScatter sc = {};
+                sc.world      = (int)links->shard.size();
+                for (int r = 0; r < sc.world; r++)
+                {
+                    sc.bound[r] = (uint32_t)links->shard[r]->h0;
+                    for (int i = 0; i < cnt; i++)
+                        sc.dst[i][r] = links->shard[r]->vec_ptr(owned[i]);
+                }
+                sc.bound[sc.world] = domain;
+                ntt_kernels        = ntt_coset_chain(ntt, vecs, cnt, st_h, &sc);
+            }
+            else
+            {
+                ntt_kernels = ntt_coset_chain(ntt, vecs, cnt, st_h);
+                if (links)
+                    for (size_t r = 0; r < links->shard.size(); r++)
+                    {
+                        const DeviceProverImpl* peer = links->shard[r];
+                        if (peer == this || peer->h1 == peer->h0)
+                            continue;
+                        for (int i = 0; i < cnt; i++)
+                            KZP_CUDA_CHECK(cudaMemcpyPeerAsync(peer->vec_ptr(owned[i]) + peer->h0, peer->device,
+                                                               vecs[i] + peer->h0, device, (size_t)(peer->h1 - peer->h0) * 32, st_h));
+                    }
+            }
         }
-        KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 384, sc_h.result, 128, cudaMemcpyDeviceToHost, st_h));
-        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_HMSM], st_h));
+        if (links)
+            KZP_CUDA_CHECK(cudaEventRecord(ev[EV_XCHG], st_h)); // this shard's vectors have reached every other shard
+        else
+            h_pointwise(d_a, d_b, d_c, d_h, domain, st_h);
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_NTT], st_h));
 
         // ---- stream W: one digit sort of the witness, then A, B1, C as one G1 batch; B2 on its own stream
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_W0], st_w));
@@ -981,7 +1209,38 @@ public:
             KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 256, sc_c.result, 128, cudaMemcpyDeviceToHost, st_w));
             KZP_CUDA_CHECK(cudaEventRecord(ev[EV_WG1], st_w));
         }
-        launches_     = 1 + ntt_kernels + 1 + 2 * kMsmSortLaunches + 3 * kMsmReduceLaunches; // + 1 per upload (expand)
+        launches_ = (own_mask ? 1 : 0) + ntt_kernels + 2 * kMsmSortLaunches + 3 * kMsmReduceLaunches; // + 1 per upload (expand)
+    }
+
+    // The H MSM. In a group: first wait until the owners of a, b, c have delivered this shard's slices (their EV_XCHG
+    // must have been recorded for THIS proof before this call: ProverGroup puts a host barrier between the two
+    // halves), then the pointwise step on the slice only.
+    void launch_h()
+    {
+        set_device();
+        if (links)
+        {
+            for (int i = 0; i < 3; i++)
+            {
+                const DeviceProverImpl* o = links->shard[links->owner_of[i]];
+                bool seen = o == this;
+                for (int j = 0; j < i; j++)
+                    seen = seen || links->shard[links->owner_of[j]] == o;
+                if (!seen)
+                    KZP_CUDA_CHECK(cudaStreamWaitEvent(st_h, o->ev[EV_XCHG], 0));
+            }
+            if (h1 > h0)
+                h_pointwise(d_a + h0, d_b + h0, d_c + h0, d_h + h0, h1 - h0, st_h);
+        }
+        {
+            const MsmBases<G1Xyzz>* b[1] = {&bases_h};
+            MsmScratch<G1Xyzz>*     s[1] = {&sc_h};
+            msm_sort_run(sort_h, reinterpret_cast<const uint32_t*>(d_h), st_h);
+            msm_reduce_batch<G1Xyzz>(sort_h, b, s, 1, st_h);
+        }
+        KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 384, sc_h.result, 128, cudaMemcpyDeviceToHost, st_h));
+        KZP_CUDA_CHECK(cudaEventRecord(ev[EV_HMSM], st_h));
+        launches_ += 1; // pointwise
         gpu_in_flight = true;
     }
 
@@ -1084,60 +1343,465 @@ public:
     }
 };
 
+// ------------------------------------------------------------------ one proof over several GPUs, one process
+// the reference's only entry is FullProver::prove under one mutex (prover-service/src/request_handler/
+// prover_handler.rs:266-269), so a drop-in has to shard INSIDE that call. Shard r lives on devices[r] and holds base
+// range r of every MSM section. The three coset-NTT chains are independent (the reference runs them as three
+// std::async tasks, groth16.cpp:172-262): each is computed by one shard and its output is delivered slice by slice to
+// the shards that need it for their part of the H MSM (peer stores fused into the chain's last level, or peer copies).
+// The 768-byte partial results meet on the host, which sums them: no communicator, no collective library.
+class ProverGroup
+{
+public:
+    std::vector<std::unique_ptr<DeviceProverImpl>> sh;
+    std::vector<int>      devices;
+    GroupLinks            links;
+    WitnessPacker         packer;
+    std::unique_ptr<Crew> crew;
+    ShardPartials         parts; // sum over the shards, in one shard's format
+    ShardPartials         sums;
+    bool                  art_valid = false;
+    MsmArtefacts          art;
+    ProveTimings          tm;
+    bool                  gpu_in_flight = false;
+
+    static void owners_for(int world, int (&owner_of)[3])
+    {
+        if (world == 1)
+            owner_of[0] = owner_of[1] = owner_of[2] = 0;
+        else if (world == 2)
+            owner_of[0] = 0, owner_of[1] = owner_of[2] = 1; // c = a o b needs both row sums anyway: b rides along
+        else
+            owner_of[0] = 0, owner_of[1] = 1, owner_of[2] = 2;
+    }
+
+    ProverGroup(const std::string& path, const std::vector<int>& devs)
+        : devices(devs)
+    {
+        const int world = (int)devices.size();
+        if (world < 1 || world > kNttMaxShards)
+            throw FormatError("a prover group has 1 to 8 shards");
+        int n_dev = 0;
+        KZP_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+        for (int d : devices)
+            if (d < 0 || d >= n_dev)
+                throw CudaError("CUDA device " + std::to_string(d) + " not present");
+        uint32_t n_vars = 0;
+        {
+            MappedFile file(path);
+            BinView    bin(file.data(), file.size(), "zkey", 1);
+            n_vars = parse_zkey(bin).n_vars;
+        }
+        owners_for(world, links.owner_of);
+        try
+        {
+            KZP_CUDA_CHECK(cudaSetDevice(devices[0]));
+            packer.create(n_vars);
+            crew.reset(new Crew(world));
+            sh.resize(world);
+            std::vector<std::exception_ptr> err(world);
+            crew->run([&](int r) {
+                try
+                {
+                    uint32_t mask = 0;
+                    for (int i = 0; i < 3; i++)
+                        if (links.owner_of[i] == r)
+                            mask |= 1u << i;
+                    sh[r].reset(new DeviceProverImpl(path, devices[r], r, world, mask, &packer));
+                }
+                catch (...)
+                {
+                    err[r] = std::current_exception();
+                }
+            });
+            for (auto& e : err)
+                if (e)
+                    std::rethrow_exception(e);
+            // peer mappings for the slice exchange
+            bool all_peers = true;
+            for (int i = 0; i < world; i++)
+                for (int j = 0; j < world; j++)
+                {
+                    if (devices[i] == devices[j])
+                        continue;
+                    int can = 0;
+                    KZP_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, devices[i], devices[j]));
+                    if (!can)
+                    {
+                        all_peers = false;
+                        continue;
+                    }
+                    KZP_CUDA_CHECK(cudaSetDevice(devices[i]));
+                    cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled)
+                        cudaGetLastError();
+                    else
+                        KZP_CUDA_CHECK(e);
+                }
+            for (auto& p : sh)
+                links.shard.push_back(p.get());
+            const char* se      = getenv("KZP_GROUP_SCATTER");
+            links.fused_scatter = (se ? atoi(se) != 0 : true) && all_peers && ntt_chain_is_batched(sh[0]->log_domain);
+            for (auto& p : sh)
+                p->links = &links;
+        }
+        catch (...)
+        {
+            destroy();
+            throw;
+        }
+    }
+
+    ~ProverGroup() { destroy(); }
+
+    void destroy()
+    {
+        sh.clear(); // each shard synchronises its device first
+        crew.reset();
+        if (!devices.empty() && cudaSetDevice(devices[0]) == cudaSuccess)
+            packer.destroy();
+        else
+            packer.pool.reset();
+        cudaGetLastError();
+    }
+
+    int world() const { return (int)sh.size(); }
+
+    // One wake-up of the crew per proof: thread r copies + expands the witness on its GPU (when ps != nullptr), launches
+    // its prefix, meets the others (every EV_XCHG of this proof is recorded), launches its H MSM.
+    void run_crew(PackState* ps)
+    {
+        const int                       n = world();
+        std::vector<std::exception_ptr> err(n);
+        std::atomic<int>                failed{0};
+        crew->run([&](int r) {
+            try
+            {
+                if (ps)
+                    sh[r]->enqueue_packed(*ps);
+                sh[r]->launch_prefix();
+            }
+            catch (...)
+            {
+                err[r] = std::current_exception();
+                failed.store(1);
+            }
+            crew->barrier();
+            if (failed.load())
+                return;
+            try
+            {
+                sh[r]->launch_h();
+            }
+            catch (...)
+            {
+                err[r] = std::current_exception();
+            }
+        });
+        if (ps)
+            ps->wait_all();
+        for (auto& e : err)
+            if (e)
+            {
+                for (auto& p : sh) // leave no work in flight behind a failed proof
+                    if (cudaSetDevice(p->device) == cudaSuccess)
+                        cudaDeviceSynchronize();
+                for (auto& p : sh)
+                    p->gpu_in_flight = false;
+                std::rethrow_exception(e);
+            }
+        gpu_in_flight = true;
+    }
+
+    template <class Read>
+    void upload_with(Read&& read)
+    {
+        PackState ps(packer.n_slices);
+        packer.begin(read, ps);
+        std::vector<std::exception_ptr> err(world());
+        crew->run([&](int r) {
+            try
+            {
+                sh[r]->enqueue_packed(ps);
+            }
+            catch (...)
+            {
+                err[r] = std::current_exception();
+            }
+        });
+        ps.wait_all();
+        for (auto& e : err)
+            if (e)
+                std::rethrow_exception(e);
+    }
+    void check_n(uint64_t n) const
+    {
+        if (n < sh[0]->n_vars)
+            throw FormatError("witness has fewer values than the zkey has variables");
+    }
+
+    void wait_witness_msms(HG1& A, HG1& B1, HG1& C, HG2& B2)
+    {
+        if (!gpu_in_flight)
+            throw FormatError("no proof in flight");
+        HG1::set_inf(A);
+        HG1::set_inf(B1);
+        HG1::set_inf(C);
+        HG2::set_inf(B2);
+        for (auto& p : sh)
+        {
+            p->wait_witness_msms();
+            HG1 t;
+            HG2 t2;
+            memcpy(&t, p->pinned_out + 0, 128);
+            HG1::add(A, t);
+            memcpy(&t, p->pinned_out + 128, 128);
+            HG1::add(B1, t);
+            memcpy(&t, p->pinned_out + 256, 128);
+            HG1::add(C, t);
+            memcpy(&t2, p->pinned_out + 512, 256);
+            HG2::add(B2, t2);
+        }
+    }
+
+    // all shards done; parts = the sums
+    void wait_gpu()
+    {
+        if (!gpu_in_flight)
+            throw FormatError("no proof in flight");
+        gpu_in_flight = false;
+        HG1 A, B1, C, H;
+        HG2 B2;
+        HG1::set_inf(A);
+        HG1::set_inf(B1);
+        HG1::set_inf(C);
+        HG1::set_inf(H);
+        HG2::set_inf(B2);
+        ProveTimings t;
+        for (auto& p : sh)
+        {
+            p->wait_gpu();
+            HG1 g;
+            HG2 g2;
+            memcpy(&g, p->parts.bytes + 0, 128);
+            HG1::add(A, g);
+            memcpy(&g, p->parts.bytes + 128, 128);
+            HG1::add(B1, g);
+            memcpy(&g, p->parts.bytes + 256, 128);
+            HG1::add(C, g);
+            memcpy(&g, p->parts.bytes + 384, 128);
+            HG1::add(H, g);
+            memcpy(&g2, p->parts.bytes + 512, 256);
+            HG2::add(B2, g2);
+            const ProveTimings& q = p->tm;
+            t.h2d_ms       = std::max(t.h2d_ms, q.h2d_ms);
+            t.spmv_ms      = std::max(t.spmv_ms, q.spmv_ms);
+            t.ntt_ms       = std::max(t.ntt_ms, q.ntt_ms);
+            t.msm_h_ms     = std::max(t.msm_h_ms, q.msm_h_ms);
+            t.msm_wsort_ms = std::max(t.msm_wsort_ms, q.msm_wsort_ms);
+            t.msm_wg1_ms   = std::max(t.msm_wg1_ms, q.msm_wg1_ms);
+            t.msm_wg2_ms   = std::max(t.msm_wg2_ms, q.msm_wg2_ms);
+            t.gpu_ms       = std::max(t.gpu_ms, q.gpu_ms);
+            t.h2d_mbytes += q.h2d_mbytes;
+            t.kernel_launches += q.kernel_launches;
+        }
+        memcpy(parts.bytes + 0, &A, 128);
+        memcpy(parts.bytes + 128, &B1, 128);
+        memcpy(parts.bytes + 256, &C, 128);
+        memcpy(parts.bytes + 384, &H, 128);
+        memcpy(parts.bytes + 512, &B2, 256);
+        t.assemble_host_ms = tm.assemble_host_ms;
+        t.total_host_ms    = tm.total_host_ms;
+        tm                 = t;
+    }
+
+    void run_gpu()
+    {
+        run_crew(nullptr);
+        wait_gpu();
+    }
+
+    std::string assemble(const ShardPartials* ps, int count, const uint8_t* r32, const uint8_t* s32)
+    {
+        double     t0 = now_ms();
+        BlindTerms bt;
+        compute_blind_terms(sh[0]->vk, r32, s32, bt);
+        std::string j       = assemble_with_terms(sh[0]->vk, ps, count, bt, &sums);
+        art_valid           = false;
+        tm.assemble_host_ms = (float)(now_ms() - t0);
+        return j;
+    }
+
+    // same overlap of host work with the GPUs as DeviceProverImpl::prove_with
+    template <class Start>
+    std::string prove_with(Start&& start, const uint8_t* r32, const uint8_t* s32)
+    {
+        double t0 = now_ms();
+        start();
+        BlindTerms bt;
+        compute_blind_terms(sh[0]->vk, r32, s32, bt);
+        EarlyProof ep;
+        {
+            HG1 A, B1, C;
+            HG2 B2;
+            wait_witness_msms(A, B1, C, B2);
+            assemble_early(sh[0]->vk, bt, A, B1, C, B2, ep);
+        }
+        wait_gpu();
+        double t1 = now_ms();
+        HG1    H;
+        memcpy(&H, parts.bytes + 384, 128);
+        std::string j       = assemble_final(ep, H, &sums);
+        art_valid           = false;
+        tm.assemble_host_ms = (float)(now_ms() - t1);
+        tm.total_host_ms    = (float)(now_ms() - t0);
+        return j;
+    }
+
+    template <class Read>
+    std::string prove_upload(Read&& read, const uint8_t* r32, const uint8_t* s32)
+    {
+        PackState ps(packer.n_slices);
+        return prove_with(
+            [&] {
+                packer.begin(read, ps);
+                try
+                {
+                    run_crew(&ps);
+                }
+                catch (...)
+                {
+                    ps.wait_all();
+                    throw;
+                }
+            },
+            r32, s32);
+    }
+
+    const MsmArtefacts& artefacts()
+    {
+        if (!art_valid)
+        {
+            artefacts_from_sums(sums, art);
+            art_valid = true;
+        }
+        return art;
+    }
+
+    // every shard holds its own slice of the H coefficients
+    void copy_h(uint8_t* out) const
+    {
+        for (auto& p : sh)
+        {
+            p->set_device();
+            if (p->h1 > p->h0)
+                KZP_CUDA_CHECK(cudaMemcpy(out + p->h0 * 32, p->d_h + p->h0, (size_t)(p->h1 - p->h0) * 32, cudaMemcpyDeviceToHost));
+        }
+    }
+};
+
 // ------------------------------------------------------------------ facade
 DeviceProver::DeviceProver(const std::string& zkey_path, int device, int shard_rank, int shard_world)
     : impl_(new DeviceProverImpl(zkey_path, device, shard_rank, shard_world))
 {
 }
+DeviceProver::DeviceProver(const std::string& zkey_path, const std::vector<int>& devices)
+    : group_(new ProverGroup(zkey_path, devices))
+{
+}
 DeviceProver::~DeviceProver() {}
-uint32_t DeviceProver::n_vars() const { return impl_->n_vars; }
-uint32_t DeviceProver::n_public() const { return impl_->n_public; }
-uint32_t DeviceProver::domain_size() const { return impl_->domain; }
-uint64_t DeviceProver::n_coefs() const { return impl_->n_coefs; }
-int      DeviceProver::device() const { return impl_->device; }
-void     DeviceProver::upload_witness(const uint8_t* values, uint64_t n) { impl_->upload(values, n); }
-void     DeviceProver::run_gpu() { impl_->run_gpu(); }
+DeviceProverImpl& DeviceProver::first() const { return group_ ? *group_->sh[0] : *impl_; }
+uint32_t DeviceProver::n_vars() const { return first().n_vars; }
+uint32_t DeviceProver::n_public() const { return first().n_public; }
+uint32_t DeviceProver::domain_size() const { return first().domain; }
+uint64_t DeviceProver::n_coefs() const { return first().n_coefs; }
+int      DeviceProver::device() const { return first().device; }
+int      DeviceProver::group_size() const { return group_ ? group_->world() : 1; }
+bool     DeviceProver::group_fused_exchange() const { return group_ && group_->links.fused_scatter; }
+void     DeviceProver::upload_witness(const uint8_t* values, uint64_t n)
+{
+    if (group_)
+    {
+        group_->check_n(n);
+        group_->upload_with(witness_reader_mem(values));
+    }
+    else
+        impl_->upload(values, n);
+}
+void DeviceProver::upload_witness_fd(int fd, uint64_t file_offset, uint64_t n)
+{
+    if (group_)
+    {
+        group_->check_n(n);
+        group_->upload_with(witness_reader_fd(fd, file_offset));
+    }
+    else
+        impl_->upload_fd(fd, file_offset, n);
+}
+void DeviceProver::run_gpu()
+{
+    if (group_)
+        group_->run_gpu();
+    else
+        impl_->run_gpu();
+}
 std::string DeviceProver::prove_resident(const uint8_t* r32, const uint8_t* s32)
 {
+    if (group_)
+        return group_->prove_with([&] { group_->run_crew(nullptr); }, r32, s32);
     return impl_->prove_with([] {}, r32, s32);
 }
-const ShardPartials& DeviceProver::partials() const { return impl_->parts; }
+const ShardPartials& DeviceProver::partials() const { return group_ ? group_->parts : impl_->parts; }
 std::string DeviceProver::assemble(const ShardPartials* parts, int count, const uint8_t* r32,
                                    const uint8_t* s32)
 {
-    return impl_->assemble(parts, count, r32, s32);
+    return group_ ? group_->assemble(parts, count, r32, s32) : impl_->assemble(parts, count, r32, s32);
 }
 std::string DeviceProver::prove(const uint8_t* values, uint64_t n, const uint8_t* r32, const uint8_t* s32)
 {
+    if (group_)
+    {
+        group_->check_n(n);
+        return group_->prove_upload(witness_reader_mem(values), r32, s32);
+    }
     return impl_->prove_with([&] { impl_->upload(values, n); }, r32, s32);
 }
 std::string DeviceProver::prove_fd(int fd, uint64_t file_offset, uint64_t n, const uint8_t* r32, const uint8_t* s32)
 {
+    if (group_)
+    {
+        group_->check_n(n);
+        return group_->prove_upload(witness_reader_fd(fd, file_offset), r32, s32);
+    }
     return impl_->prove_with([&] { impl_->upload_fd(fd, file_offset, n); }, r32, s32);
 }
-void DeviceProver::upload_witness_fd(int fd, uint64_t file_offset, uint64_t n) { impl_->upload_fd(fd, file_offset, n); }
-const ProveTimings& DeviceProver::timings() const { return impl_->tm; }
+const ProveTimings& DeviceProver::timings() const { return group_ ? group_->tm : impl_->tm; }
 void DeviceProver::msm_profile(int which, float* ms, uint64_t* entries) const
 {
-    impl_->set_device();
+    DeviceProverImpl& p = first();
+    p.set_device();
     switch (which)
     {
     case 0: // A, B1 and C run as one batched launch over the shared witness sort
     case 1:
-    case 3: msm_last_accumulate(impl_->sort_w, impl_->sc_a, ms, entries); break;
-    case 2: msm_last_accumulate(impl_->sort_w, impl_->sc_b2, ms, entries); break;
-    case 4: msm_last_accumulate(impl_->sort_h, impl_->sc_h, ms, entries); break;
+    case 3: msm_last_accumulate(p.sort_w, p.sc_a, ms, entries); break;
+    case 2: msm_last_accumulate(p.sort_w, p.sc_b2, ms, entries); break;
+    case 4: msm_last_accumulate(p.sort_h, p.sc_h, ms, entries); break;
     default: throw FormatError("msm index out of range");
     }
 }
-const MsmArtefacts& DeviceProver::msm_artefacts() const { return impl_->artefacts(); }
+const MsmArtefacts& DeviceProver::msm_artefacts() const { return group_ ? group_->artefacts() : impl_->artefacts(); }
 void DeviceProver::copy_h(uint8_t* out) const
 {
+    if (group_)
+        return group_->copy_h(out);
     impl_->set_device();
     KZP_CUDA_CHECK(cudaMemcpy(out, impl_->d_h, (size_t)impl_->domain * 32, cudaMemcpyDeviceToHost));
 }
 void DeviceProver::set_keep_ab(bool on)
 {
+    if (group_)
+        throw FormatError("keep_ab is not available on a prover group (a and b live on different GPUs)");
     impl_->set_device();
     if (on && !impl_->d_keep_a)
     {
@@ -1148,7 +1812,7 @@ void DeviceProver::set_keep_ab(bool on)
 }
 void DeviceProver::copy_ab(uint8_t* out) const
 {
-    if (!impl_->d_keep_a)
+    if (group_ || !impl_->d_keep_a)
         throw FormatError("set_keep_ab(true) was not called before the proof");
     impl_->set_device();
     size_t vec = (size_t)impl_->domain * 32;

@@ -61,17 +61,27 @@ size_t pack_slice_capacity();
 size_t pack_witness_slice(const uint8_t* values, uint32_t count, uint8_t* out, uint32_t* n_full);
 
 class DeviceProverImpl;
+class ProverGroup;
 
 class DeviceProver
 {
-    std::unique_ptr<DeviceProverImpl> impl_;
+    std::unique_ptr<DeviceProverImpl> impl_;  // one GPU ...
+    std::unique_ptr<ProverGroup>      group_; // ... or one proof over several (exactly one of the two is set)
+    DeviceProverImpl&                 first() const;
 
 public:
     // Throws kzp::LoadError / kzp::FormatError / kzp::CudaError.
     // shard_rank/shard_world: this instance holds only base range [rank*n/world, (rank+1)*n/world) of every
     // MSM section; world == 1 is the ordinary single-GPU prover.
     DeviceProver(const std::string& zkey_path, int device, int shard_rank = 0, int shard_world = 1);
+    // One proof over devices.size() GPUs of this process (1..8; a device may be listed more than once): shard r on
+    // devices[r] holds base range r of every MSM section and computes one of the three coset-NTT chains (when there
+    // are fewer shards than chains, shard 1 computes two); the chain outputs cross NVLink slice by slice, the
+    // 768-byte partial results are summed on the host. Every prove*/upload*/run_gpu call below then drives all of them.
+    DeviceProver(const std::string& zkey_path, const std::vector<int>& devices);
     ~DeviceProver();
+    int  group_size() const;           // 1 for a single-GPU prover
+    bool group_fused_exchange() const; // the slices travel as peer stores of the chain's last level (else peer copies)
 
     uint32_t n_vars() const;
     uint32_t n_public() const;

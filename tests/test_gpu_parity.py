@@ -343,14 +343,16 @@ def test_msm_reference_kats(gpu, kzp, oracle):
 
 
 # ---------------------------------------------------------------- whole proofs
-def _check_against_expected(o, p, zkey, wtns, exp):
+def _check_against_expected(o, p, zkey, wtns, exp, ab=True):
     r, s = bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"])
-    p.keep_ab(True)
+    if ab:
+        p.keep_ab(True)
     js, metrics = p.prove(wtns, r, s)
     assert js == exp["proof"]                      # final proof bytes
     assert p.h_coefficients().hex() == exp["h"]    # H coefficients, natural order, canonical
     assert p.msm_results().hex() == exp["msm"]     # A, B1, B2, C, H affine canonical
-    assert p.ab().hex() == exp["ab"]               # a, b after the SpMV (Montgomery)
+    if ab:
+        assert p.ab().hex() == exp["ab"]           # a, b after the SpMV (Montgomery)
     assert metrics["prover_time"] >= 0
 
 
@@ -423,6 +425,83 @@ def test_proof_matches_reference_generated(gpu, kzp, oracle, ref, port, workdir,
     zk_vk = oracle.read_zkey(z) if n_vars < 5000 else None
     if zk_vk is not None:
         assert oracle.groth16_verify(oracle.vk_from_zkey(zk_vk), [info["public_input"]], pa, pb, pc)
+
+
+# ---------------------------------------------------------------- one proof over several GPUs, inside the prove call
+def _group_devices(gpu, shards):
+    """shard r -> device r mod (visible GPUs): on a one-GPU box every shard shares device 0 (the exchange then runs
+    as same-device stores/copies), on a multi-GPU box the slices really cross NVLink"""
+    return [i % gpu for i in range(shards)]
+
+
+@pytest.mark.parametrize("shards,scatter", [(1, 1), (2, 1), (2, 0), (3, 1), (4, 0), (5, 1), (8, 1)])
+def test_group_proof_matches_reference(gpu, kzp, oracle, ref, port, workdir, monkeypatch, shards, scatter):
+    """SURVEY.md §8(e) as a product feature: kzp_prover_new_group shards ONE proof inside kzp_prover_prove — MSM base
+    ranges split, one coset-NTT chain per shard, slices exchanged as fused peer stores (scatter=1; domain 2^14 takes
+    the batched chain) or peer copies (scatter=0). Proof bytes, H coefficients and the five MSM results equal the
+    reference's, through the file, in-memory and resident entry points."""
+    z = os.path.join(workdir, "grp.zkey")
+    w = os.path.join(workdir, "grp.wtns")
+    info = port.make_setup(12000, 11000, 5, z, w)
+    assert info["domain"] == 1 << 14
+    rnd = random.Random(77)
+    r, s = oracle.le32(rnd.randrange(oracle.R_MOD >> 2)), oracle.le32(rnd.randrange(oracle.R_MOD >> 2))
+    rj, _ = ref.prove(z, w, r, s)
+    _, rh, rm = ref.dump(z, w, info["domain"])
+    monkeypatch.setenv("KZP_GROUP_SCATTER", str(scatter))
+    with kzp.FullProver(z, devices=_group_devices(gpu, shards)) as p:
+        assert p.group_info() == (shards, bool(scatter))
+        for _ in range(2):  # the second proof reuses buffers the first one's peers wrote into
+            js, _ = p.prove(w, r, s)
+            assert js == rj
+            assert p.h_coefficients() == rh
+            assert p.msm_results() == rm
+        values = open(w, "rb").read()[-p.n_vars * 32:]
+        js, _ = p.prove_mem(values, r, s)
+        assert js == rj
+        js, _ = p.prove_resident(r, s)
+        assert js == rj
+        p.run_gpu()
+        assert p.assemble([p.partials()], r, s) == rj
+        assert int(p.timings()["kernel_launches"]) > 20 * shards
+        js2, _ = p.prove(w)
+        assert js2 != rj
+        with pytest.raises(kzp.InvalidInput):
+            p.prove("/nonexistent.wtns")
+        with pytest.raises(kzp.InvalidInput):
+            p.prove_mem(bytes(64))
+        js, _ = p.prove(w, r, s)  # still usable
+        assert js == rj
+
+
+@pytest.mark.parametrize("name,zkey,wtns", [("toy", "toy_1.zkey", "toy.wtns"), ("syn256", "syn256.zkey", "syn256.wtns")])
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_group_proof_small_circuits(gpu, kzp, oracle, name, zkey, wtns, shards):
+    """Domains too small for the batched chain (8 and 512 points: the exchange falls back to peer copies) and shards
+    whose base ranges are nearly or entirely empty, against the committed golden fixtures."""
+    d = os.path.join(GOLDEN, name)
+    exp = json.load(open(os.path.join(d, "expected.json")))
+    with kzp.FullProver(os.path.join(d, zkey), devices=_group_devices(gpu, shards)) as p:
+        assert p.group_info() == (shards, False)
+        _check_against_expected(oracle, p, os.path.join(d, zkey), os.path.join(d, wtns), exp, ab=False)
+        with pytest.raises(kzp.KzpError):
+            p.keep_ab(True)  # a and b live on different GPUs
+
+
+def test_group_through_reference_shaped_constructor(gpu, kzp, oracle, monkeypatch):
+    """FullProver::FullProver(zkeyPath) has no device argument: $KZP_SHARD_DEVICES turns it into a sharded prover."""
+    d = os.path.join(GOLDEN, "syn256")
+    exp = json.load(open(os.path.join(d, "expected.json")))
+    monkeypatch.setenv("KZP_SHARD_DEVICES", ",".join(str(x) for x in _group_devices(gpu, 4)))
+    with kzp.FullProver(os.path.join(d, "syn256.zkey")) as p:
+        assert p.group_info()[0] == 4
+        js, _ = p.prove(os.path.join(d, "syn256.wtns"), bytes.fromhex(exp["r"]), bytes.fromhex(exp["s"]))
+        assert js == exp["proof"]
+    monkeypatch.setenv("KZP_SHARD_DEVICES", "0,x")
+    with pytest.raises(kzp.ProverInitError):
+        kzp.FullProver(os.path.join(d, "syn256.zkey"))
+    with pytest.raises(kzp.ProverInitError):
+        kzp.FullProver(os.path.join(d, "syn256.zkey"), devices=[0, 99])
 
 
 # ---------------------------------------------------------------- boundary behaviour (RS/fullprover.cpp:80-125,204-250)
@@ -513,6 +592,12 @@ def test_keyless_shape_full_size(gpu, kzp, oracle, ref, port, workdir):
     assert js == rj
     _, rh, rm = ref.dump(z, w, info["domain"])
     assert gh == rh and gm == rm
+    # the same proof sharded inside the call: domain 2^21 takes the fused-scatter chain
+    for shards in (2, 4):
+        with kzp.FullProver(z, devices=_group_devices(gpu, shards)) as p:
+            assert p.group_info() == (shards, True)
+            js, _ = p.prove(w, r, s)
+            assert js == rj and p.h_coefficients() == rh and p.msm_results() == rm
     pa, pb, pc = oracle.proof_from_json(js)
     # VK from the zkey header + IC section only (reading 1.3M points in Python would be slow)
     sec = oracle.read_binfile(z, b"zkey", 1)
