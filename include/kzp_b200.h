@@ -66,15 +66,18 @@ kzp_prover* kzp_prover_new(const char* zkey_path, int device, int* state_out);
 /* MSM base ranges of shard `rank` of `world` only; used one process per GPU. */
 kzp_prover* kzp_prover_new_sharded(const char* zkey_path, int device, int rank, int world, int* state_out);
 /* ONE proof over n_devices GPUs of this process (1..8): shard r on devices[r] holds base range r of
- * every MSM section and computes one of the three coset-NTT chains (the reference runs them as three std::async tasks,
- * groth16.cpp:172-262); the chain outputs cross NVLink as peer stores fused into the chain's last level (peer copies
- * when peer access is unavailable or $KZP_GROUP_SCATTER=0), the 768-byte partial results are summed on the host.
+ * every MSM section. With 2, 4 or 8 shards every coset-NTT chain is spread over all of them: each GPU runs 1/N of every
+ * level of a, b and c, and the two transposes between the level partitions plus the delivery of the H slices are peer
+ * stores over NVLink fused into the level kernels ($KZP_GROUP_NTT=chain turns this off). Otherwise each chain is
+ * computed by one shard (the reference runs them as three std::async tasks, groth16.cpp:172-262) and its output crosses
+ * NVLink as peer stores of the chain's last level (peer copies when peer access is unavailable, the domain is too small
+ * for the batched chain, or $KZP_GROUP_SCATTER=0). The 768-byte partial results are summed on the host.
  * The handle behaves like any other: kzp_prover_prove / _prove_mem / _prove_resident / _upload_witness* / _run_gpu /
  * _timings (per-stage maximum over the shards) / _get_h / _get_msm_results; kzp_prover_keep_ab is not available.
  * devices == NULL: $KZP_SHARD_DEVICES ("0,1,2,3"). kzp_prover_new(path, -1, ..) — and therefore the reference-shaped
  * FullProver::FullProver(zkeyPath) — builds a group whenever $KZP_SHARD_DEVICES is set. */
 kzp_prover* kzp_prover_new_group(const char* zkey_path, const int* devices, int n_devices, int* state_out);
-int         kzp_prover_group_info(kzp_prover* p, int* shards, int* fused_exchange); /* 1 shard = single-GPU prover */
+int         kzp_prover_group_info(kzp_prover* p, int* shards, int* fused_exchange, int* distributed_ntt); /* 1 shard = single-GPU prover */
 void        kzp_prover_free(kzp_prover* p); /* FullProver::~FullProver */
 
 /* FullProver::prove(const char* wtnsPath) — fullprover.cpp:114-125,204-250.
@@ -114,6 +117,8 @@ int kzp_prover_info(kzp_prover* p, uint32_t* n_vars, uint32_t* n_public, uint32_
 /* last proof: floats {h2d, spmv, ntt, msm_h, msm_witness_sort, msm_witness_g1 (A,B1,C batched), msm_witness_g2 (B2),
  * h2d_megabytes (what the upload moved over PCIe), gpu, assemble_host, total_host, kernel_launches}; returns the number of values written (<= cap) */
 int kzp_prover_timings(kzp_prover* p, float* out, int cap);
+/* the same values for one shard of a group (kzp_prover_new_group): where the time of a sharded proof goes */
+int kzp_prover_group_shard_timings(kzp_prover* p, int shard, float* out, int cap);
 /* bucket-accumulation kernel (the dominant kernel) of MSM `which` (0 A, 1 B1, 2 B2, 3 C, 4 H) in the last proof:
  * its duration from CUDA events on its stream and the number of (point, bucket) entries it summed. A, B1 and C
  * share one batched launch over one digit sort: 0, 1 and 3 return that launch and the shared entry count. */

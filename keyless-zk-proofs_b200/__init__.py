@@ -101,7 +101,7 @@ def lib() -> ctypes.CDLL:
         "kzp_prover_new": (vp, [c.c_char_p, c.c_int, i32p]),
         "kzp_prover_new_sharded": (vp, [c.c_char_p, c.c_int, c.c_int, c.c_int, i32p]),
         "kzp_prover_new_group": (vp, [c.c_char_p, c.POINTER(c.c_int), c.c_int, i32p]),
-        "kzp_prover_group_info": (c.c_int, [vp, i32p, i32p]),
+        "kzp_prover_group_info": (c.c_int, [vp, i32p, i32p, i32p]),
         "kzp_prover_free": (None, [vp]),
         "kzp_prover_prove": (c.c_int, [vp, c.c_char_p, u8p, u8p, c.POINTER(vp), i32p, i32p]),
         "kzp_prover_prove_mem": (c.c_int, [vp, u8p, c.c_uint64, u8p, u8p, c.POINTER(vp), i32p, i32p]),
@@ -114,6 +114,7 @@ def lib() -> ctypes.CDLL:
         "kzp_prover_info": (c.c_int, [vp, c.POINTER(c.c_uint32), c.POINTER(c.c_uint32), c.POINTER(c.c_uint32),
                                       c.POINTER(c.c_uint64), i32p]),
         "kzp_prover_timings": (c.c_int, [vp, c.POINTER(c.c_float), c.c_int]),
+        "kzp_prover_group_shard_timings": (c.c_int, [vp, c.c_int, c.POINTER(c.c_float), c.c_int]),
         "kzp_prover_msm_profile": (c.c_int, [vp, c.c_int, c.POINTER(c.c_float), c.POINTER(c.c_uint64)]),
         "kzp_prover_get_h": (c.c_int, [vp, u8p, c.c_uint64]),
         "kzp_prover_keep_ab": (c.c_int, [vp, c.c_int]),
@@ -224,11 +225,12 @@ class FullProver:
         self.n_vars, self.n_public, self.domain_size = nv.value, npub.value, dom.value
         self.n_coefs, self.device = nc.value, dev.value
 
-    def group_info(self) -> Tuple[int, bool]:
-        """(number of shards, whether the slices travel as fused peer stores)"""
-        n, f = ctypes.c_int(), ctypes.c_int()
-        _check(lib().kzp_prover_group_info(self._h, ctypes.byref(n), ctypes.byref(f)))
-        return n.value, bool(f.value)
+    def group_info(self) -> Tuple[int, bool, bool]:
+        """(number of shards, whether the slices travel as fused peer stores, whether every NTT chain is spread over
+        all shards)"""
+        n, f, d = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _check(lib().kzp_prover_group_info(self._h, ctypes.byref(n), ctypes.byref(f), ctypes.byref(d)))
+        return n.value, bool(f.value), bool(d.value)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -305,6 +307,11 @@ class FullProver:
     def timings(self) -> dict:
         arr = (ctypes.c_float * 12)()
         n = lib().kzp_prover_timings(self._h, arr, 12)
+        return {k: float(arr[i]) for i, k in enumerate(TIMING_KEYS[:n])}
+
+    def shard_timings(self, shard: int) -> dict:
+        arr = (ctypes.c_float * 12)()
+        n = lib().kzp_prover_group_shard_timings(self._h, shard, arr, 12)
         return {k: float(arr[i]) for i, k in enumerate(TIMING_KEYS[:n])}
 
     def msm_profile(self, which: int):

@@ -206,7 +206,7 @@ kzp_prover* kzp_prover_new(const char* zkey_path, int device, int* state_out)
     return kzp_prover_new_sharded(zkey_path, device, 0, 1, state_out);
 }
 
-int kzp_prover_group_info(kzp_prover* p, int* shards, int* fused_exchange)
+int kzp_prover_group_info(kzp_prover* p, int* shards, int* fused_exchange, int* distributed_ntt)
 {
     if (!p || !p->prover)
         return KZP_ERR_STATE;
@@ -214,6 +214,8 @@ int kzp_prover_group_info(kzp_prover* p, int* shards, int* fused_exchange)
         *shards = p->prover->group_size();
     if (fused_exchange)
         *fused_exchange = p->prover->group_fused_exchange() ? 1 : 0;
+    if (distributed_ntt)
+        *distributed_ntt = p->prover->group_distributed_ntt() ? 1 : 0;
     return KZP_OK;
 }
 
@@ -453,11 +455,24 @@ int kzp_prover_info(kzp_prover* p, uint32_t* n_vars, uint32_t* n_public, uint32_
     return KZP_OK;
 }
 
+static int timings_out(const ProveTimings& t, float* out, int cap);
+
+int kzp_prover_group_shard_timings(kzp_prover* p, int shard, float* out, int cap)
+{
+    if (!p || !p->prover || !out || shard < 0 || shard >= p->prover->group_size())
+        return 0;
+    return timings_out(p->prover->shard_timings(shard), out, cap);
+}
+
 int kzp_prover_timings(kzp_prover* p, float* out, int cap)
 {
     if (!p || !p->prover || !out)
         return 0;
-    const ProveTimings& t = p->prover->timings();
+    return timings_out(p->prover->timings(), out, cap);
+}
+
+static int timings_out(const ProveTimings& t, float* out, int cap)
+{
     float v[12] = {t.h2d_ms,     t.spmv_ms,     t.ntt_ms, t.msm_h_ms,         t.msm_wsort_ms,  t.msm_wg1_ms,
                    t.msm_wg2_ms, t.h2d_mbytes, t.gpu_ms, t.assemble_host_ms, t.total_host_ms,
                    (float)t.kernel_launches};
@@ -683,7 +698,8 @@ kzp_msm* kzp_msm_new_ex(int group, const uint8_t* bases, uint64_t n, int device,
         {
             msm_bases_create<G1Xyzz>(m->b1, bases, n, true, 0, c);
             msm_sort_create(m->sort, m->b1.n, m->b1.scalar_idx, 0, c, two_level != 0);
-            msm_scratch_create<G1Xyzz>(m->s1, m->sort, 0);
+            const char* ce = getenv("KZP_MSM_CHUNK"); // entries per accumulate thread (0 / unset: msm_default_chunk)
+            msm_scratch_create<G1Xyzz>(m->s1, m->sort, ce ? (uint32_t)atoi(ce) : 0);
         }
         else
         {

@@ -51,21 +51,40 @@ void ntt_domain_destroy(NttDomain& d);
 void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st);
 void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st);
 uint32_t ntt_launches(uint32_t log_n); // kernels per transform
-// Where the last level of a chain stores its natural-order output when one proof is sharded over several GPUs
-// (SURVEY.md 8(e)): position pos of vector i goes to dst[i][r] + pos for the shard r with bound[r] <= pos < bound[r+1]
-// — a peer-mapped pointer over NVLink, or the launching device's own buffer. Every element is written exactly once.
+// How an NTT kernel of a multi-GPU proof is routed. Every field zero = an ordinary local launch.
+//  * blocks: which tiles this GPU runs. kNttBlocksLow: the tiles whose columns have index bits [7-k, 7) equal to g
+//    (a partition by LOW position bits: valid for every level with lo >= 7); kNttBlocksTop: the g-th contiguous
+//    1/2^k of the tiles (a partition by the TOP position bits: valid for the fused middle level).
+//  * stores: where outputs go. kNttStoreBounds: position pos of vector i goes to dst[i][r] + pos for the shard r
+//    with bound[r] <= pos < bound[r+1]; kNttStoreBits: r = (pos >> shift) & mask. dst[i][r] is shard r's buffer of
+//    vector i (peer-mapped over NVLink, or the launching device's own): the transposes between the two partitions
+//    and the final delivery of every shard's H slice are peer stores fused into the butterflies' last round.
 constexpr int kNttMaxShards = 8;
-struct NttScatter
+enum : int { kNttBlocksAll = 0, kNttBlocksLow = 1, kNttBlocksTop = 2 };
+enum : int { kNttStoreLocal = 0, kNttStoreBounds = 1, kNttStoreBits = 2 };
+struct NttRoute
 {
     Fr*      dst[3][kNttMaxShards];
     uint32_t bound[kNttMaxShards + 1];
     int      world;
+    int      store;
+    uint32_t shift, mask;
+    int      blocks;
+    uint32_t k, g; // log2(shards), this shard
 };
-// the batched path of ntt_coset_chain (which is the only one that can scatter) applies to this size
+// the batched path of ntt_coset_chain (the only one that can be routed) applies to this size
 bool ntt_chain_is_batched(uint32_t log_n);
 // ifft -> coset shift -> fft (groth16.cpp:172-262) on `count` <= 3 vectors, all of them through each launch together;
-// returns the number of kernels launched. scatter (optional, batched path only): see NttScatter.
-uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st, const NttScatter* scatter = nullptr);
+// returns the number of kernels launched. last_store (optional, batched path only): routing of the last level's
+// stores (kNttStoreBounds: one whole chain per GPU, every shard's slice delivered by the last level).
+uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st, const NttRoute* last_store = nullptr);
+// The same chain spread over 2^k GPUs, in three phases with a cross-GPU hand-over after each (the caller orders
+// them with events): phase 0 = inverse levels down to lo = 7 under the low-bit partition, the last one storing by top
+// bits; phase 1 = fused middle level under the top-bit partition, storing by low bits; phase 2 = forward levels
+// under the low-bit partition, the last one storing every position to the shard that owns it (top bits again).
+// dst[i][r] = vector i on shard r for all r < 2^k. Returns the number of kernels launched.
+uint32_t ntt_coset_chain_phase(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st, int phase, uint32_t k,
+                               uint32_t g, Fr* const (*dst)[kNttMaxShards]);
 // natural <-> bit-reversed permutation (only used by the component-level entry points that expose
 // the reference's natural-in/natural-out FFT::fft / FFT::ifft contract, fft.cpp:192-246)
 void ntt_bitrev_permute(Fr* x, uint32_t log_n, cudaStream_t st);
@@ -81,7 +100,9 @@ struct CoefCsr
     Fr*       coef    = nullptr; // nnz, value * R^2 mod r exactly as stored in zkey section 4
 };
 // a = A.w, b = B.w (Montgomery), c = a o b. w: raw canonical witness values. which: bit 0 / 1 / 2 = write a / b / c.
-void spmv_abc(const CoefCsr& m, const Fr* w, Fr* a, Fr* b, Fr* c, cudaStream_t st, uint32_t which = 7);
+// part_k / part_g: only the rows whose index bits [7 - part_k, 7) equal part_g (the low-bit partition of NttRoute).
+void spmv_abc(const CoefCsr& m, const Fr* w, Fr* a, Fr* b, Fr* c, cudaStream_t st, uint32_t which = 7, uint32_t part_k = 0,
+              uint32_t part_g = 0);
 // h[i] = fromMontgomery(a[i]*b[i] - c[i])  (groth16.cpp:266-275)
 void h_pointwise(const Fr* a, const Fr* b, const Fr* c, Fr* h, uint64_t n, cudaStream_t st);
 

@@ -28,9 +28,15 @@ static inline unsigned int div_up(uint64_t a, uint64_t b) { return (unsigned int
 __global__ void __launch_bounds__(256)
     k_spmv_abc(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ wire,
                const Fr* __restrict__ coef, const Fr* __restrict__ w, Fr* __restrict__ a,
-               Fr* __restrict__ b, Fr* __restrict__ c, uint32_t n_rows, uint32_t which)
+               Fr* __restrict__ b, Fr* __restrict__ c, uint32_t n_rows, uint32_t which, uint32_t part_k, uint32_t part_g)
 {
     uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (part_k)
+    {
+        // this GPU's rows of a multi-GPU proof: index bits [7 - part_k, 7) equal part_g (NttRoute's low-bit partition)
+        const uint32_t low = 7u - part_k;
+        row = ((row >> low) << 7) | (part_g << low) | (row & ((1u << low) - 1u));
+    }
     if (row >= n_rows)
         return;
     uint32_t e0 = row_ptr[2 * row], e1 = row_ptr[2 * row + 1], e2 = row_ptr[2 * row + 2];
@@ -64,9 +70,10 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-void spmv_abc(const CoefCsr& m, const Fr* w, Fr* a, Fr* b, Fr* c, cudaStream_t st, uint32_t which)
+void spmv_abc(const CoefCsr& m, const Fr* w, Fr* a, Fr* b, Fr* c, cudaStream_t st, uint32_t which, uint32_t part_k, uint32_t part_g)
 {
-    k_spmv_abc<<<div_up(m.n_rows, 256), 256, 0, st>>>(m.row_ptr, m.wire, m.coef, w, a, b, c, m.n_rows, which);
+    k_spmv_abc<<<div_up(div_up(m.n_rows, 1u << part_k), 256), 256, 0, st>>>(m.row_ptr, m.wire, m.coef, w, a, b, c, m.n_rows, which, part_k,
+                                                                              part_g);
     KZP_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -184,7 +191,9 @@ static void ntt_level_attrs()
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
-    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttMidSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_mid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttMidSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_mid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttMidSmem));
 }
 
 static NttBatch ntt_batch1(Fr* x)
@@ -227,7 +236,7 @@ void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st)
         while (hi >= (uint32_t)kNttTileBits)
         {
             uint32_t lo = hi - kNttTileBits;
-            k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_inv, log_n, lo, 0, lo == 0 ? post : nullptr, NttScatter());
+            k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_inv, log_n, lo, 0, lo == 0 ? post : nullptr, NttRoute());
             KZP_CUDA_CHECK(cudaGetLastError());
             hi = lo;
         }
@@ -262,7 +271,7 @@ void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st)
     uint32_t     plo   = 0;
     for (uint32_t lo = r; lo + kNttTileBits <= log_n; lo += kNttTileBits)
     {
-        k_ntt_level<true><<<lgrid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_fwd, log_n, lo, plo, nullptr, NttScatter());
+        k_ntt_level<true><<<lgrid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_fwd, log_n, lo, plo, nullptr, NttRoute());
         KZP_CUDA_CHECK(cudaGetLastError());
         plo = lo;
     }
@@ -272,15 +281,15 @@ void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st)
 // vectors through each launch together. When log_n is a multiple of 7 the middle two levels run fused (k_ntt_mid).
 bool ntt_chain_is_batched(uint32_t log_n) { return ntt_use_levels(log_n) && log_n % kNttTileBits == 0; }
 
-uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st, const NttScatter* scatter)
+uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st, const NttRoute* last_store)
 {
     uint32_t log_n = d.log_n;
     if (count < 1 || count > kNttMaxBatch)
         throw CudaError("NTT batch size out of range");
     if (!ntt_chain_is_batched(log_n))
     {
-        if (scatter)
-            throw CudaError("the scattering NTT chain needs a batched domain size");
+        if (last_store)
+            throw CudaError("a routed NTT chain needs a batched domain size");
         for (int i = 0; i < count; i++)
         {
             ntt_inverse_dif(d, xs[i], d.coset_br, st);
@@ -296,23 +305,90 @@ uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStrea
     uint32_t launches = 0;
     for (uint32_t lo = log_n - kNttTileBits; lo > 0; lo -= kNttTileBits)
     {
-        k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, nullptr, NttScatter());
+        k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, nullptr, NttRoute());
         KZP_CUDA_CHECK(cudaGetLastError());
         launches++;
     }
-    k_ntt_mid<<<grid, kNttThreads, kNttMidSmem, st>>>(b, d.tw_inv, d.tw_fwd, log_n, d.coset_br);
+    k_ntt_mid<false><<<grid, kNttThreads, kNttMidSmem, st>>>(b, d.tw_inv, d.tw_fwd, log_n, d.coset_br, NttRoute());
     KZP_CUDA_CHECK(cudaGetLastError());
     launches++;
     uint32_t plo = 0;
     for (uint32_t lo = kNttTileBits; lo + kNttTileBits <= log_n; lo += kNttTileBits)
     {
-        if (scatter && lo + kNttTileBits == log_n)
-            k_ntt_level<true, true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, *scatter);
+        if (last_store && lo + kNttTileBits == log_n)
+            k_ntt_level<true, true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, *last_store);
         else
-            k_ntt_level<true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, NttScatter());
+            k_ntt_level<true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, NttRoute());
         KZP_CUDA_CHECK(cudaGetLastError());
         plo = lo;
         launches++;
+    }
+    return launches;
+}
+
+uint32_t ntt_coset_chain_phase(const NttDomain& d, Fr* const* xs, int count, cudaStream_t st, int phase, uint32_t k,
+                               uint32_t g, Fr* const (*dst)[kNttMaxShards])
+{
+    const uint32_t log_n = d.log_n;
+    if (count < 1 || count > kNttMaxBatch)
+        throw CudaError("NTT batch size out of range");
+    // the low-bit partition lives in tile-index bits [3 - k, 3), the top-bit partition in the top k position bits
+    if (!ntt_chain_is_batched(log_n) || k > (uint32_t)(kNttTileBits - kNttColBits) || g >= (1u << k))
+        throw CudaError("this domain size / shard count cannot run the distributed NTT chain");
+    ntt_level_attrs();
+    NttBatch b;
+    for (int i = 0; i < kNttMaxBatch; i++)
+        b.x[i] = xs[i < count ? i : 0];
+    NttRoute low = {}; // low-bit partition, local stores
+    low.blocks   = kNttBlocksLow;
+    low.k        = k;
+    low.g        = g;
+    low.world    = 1 << k;
+    NttRoute low_to_top = low; // ... storing by the top k position bits
+    low_to_top.store    = kNttStoreBits;
+    low_to_top.shift    = log_n - k;
+    low_to_top.mask     = (1u << k) - 1u;
+    NttRoute top_to_low = low; // top-bit partition, storing by position bits [7 - k, 7)
+    top_to_low.blocks   = kNttBlocksTop;
+    top_to_low.store    = kNttStoreBits;
+    top_to_low.shift    = kNttTileBits - k;
+    top_to_low.mask     = (1u << k) - 1u;
+    for (int i = 0; i < count; i++)
+        for (uint32_t r = 0; r < (1u << k); r++)
+            low_to_top.dst[i][r] = top_to_low.dst[i][r] = dst[i][r];
+    dim3     grid((1u << (log_n - kNttTileBits - kNttColBits)) >> k, (unsigned int)count, 1);
+    uint32_t launches = 0;
+    if (phase == 0)
+    {
+        for (uint32_t lo = log_n - kNttTileBits; lo > 0; lo -= kNttTileBits)
+        {
+            if (lo == (uint32_t)kNttTileBits)
+                k_ntt_level<false, true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, nullptr, low_to_top);
+            else
+                k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, nullptr, low);
+            KZP_CUDA_CHECK(cudaGetLastError());
+            launches++;
+        }
+    }
+    else if (phase == 1)
+    {
+        k_ntt_mid<true><<<grid, kNttThreads, kNttMidSmem, st>>>(b, d.tw_inv, d.tw_fwd, log_n, d.coset_br, top_to_low);
+        KZP_CUDA_CHECK(cudaGetLastError());
+        launches++;
+    }
+    else
+    {
+        uint32_t plo = 0;
+        for (uint32_t lo = kNttTileBits; lo + kNttTileBits <= log_n; lo += kNttTileBits)
+        {
+            if (lo + kNttTileBits == log_n)
+                k_ntt_level<true, true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, low_to_top);
+            else
+                k_ntt_level<true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, low);
+            KZP_CUDA_CHECK(cudaGetLastError());
+            plo = lo;
+            launches++;
+        }
     }
     return launches;
 }

@@ -199,14 +199,43 @@ constexpr size_t kNttWarpSmem  = 2 * 256 * sizeof(uint4);                       
 constexpr size_t kNttLevelSmem = (kNttThreads / 32) * kNttWarpSmem + 2 * 64 * sizeof(uint4); // + one twiddle table
 constexpr size_t kNttMidSmem   = (kNttThreads / 32) * kNttWarpSmem + 4 * 64 * sizeof(uint4); // + two twiddle tables
 
+// Tile index of this CTA under the route's block partition (device.hpp NttRoute).
+__device__ __forceinline__ uint32_t ntt_route_block(const NttRoute& rt)
+{
+    uint32_t b = blockIdx.x;
+    if (rt.blocks == kNttBlocksLow)
+    {
+        // column index bits [7-k, 7) = tile index bits [3-k, 3) (a tile is 16 columns): insert g there
+        const uint32_t low = (uint32_t)(7 - kNttColBits) - rt.k;
+        return ((b >> low) << (7 - kNttColBits)) | (rt.g << low) | (b & ((1u << low) - 1u));
+    }
+    if (rt.blocks == kNttBlocksTop)
+        return rt.g * gridDim.x + b;
+    return b;
+}
+
+// Destination of position pos of vector blockIdx.y under the route's store mode
+template <bool ROUTED>
+__device__ __forceinline__ Fr* ntt_route_dst(const NttRoute& rt, Fr* local, uint32_t pos)
+{
+    if (!ROUTED)
+        return local + pos;
+    int r = 0;
+    if (rt.store == kNttStoreBits)
+        r = (int)((pos >> rt.shift) & rt.mask);
+    else
+        while (r + 1 < rt.world && pos >= rt.bound[r + 1])
+            r++;
+    return rt.dst[blockIdx.y][r] + pos;
+}
+
 // One level on bits [lo, lo+7) of a size-2^k transform. tw: w^i (forward) or w^-i (inverse), i < 2^(k-1).
 // post (DIF only, may be null): element at position pos is multiplied by post[pos] on the way out.
-// SCATTER (DIT only): the level's output goes to the shard that owns each position (NttScatter), i.e. the exchange of
-// a multi-GPU proof is fused into the last level as peer stores.
-template <bool DIT, bool SCATTER = false>
+// ROUTED: the outputs are stored where rt says (peer stores); the tile selection of rt applies either way.
+template <bool DIT, bool ROUTED = false>
 __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
     k_ntt_level(NttBatch batch, const Fr* __restrict__ tw, uint32_t k, uint32_t lo, uint32_t plo,
-                const Fr* __restrict__ post, const NttScatter sc)
+                const Fr* __restrict__ post, const NttRoute rt)
 {
     Fr* __restrict__        x = batch.x[blockIdx.y];
     extern __shared__ uint4 ntt_smem[];
@@ -219,7 +248,7 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
     __syncthreads();
 
     const uint32_t e = lane >> 4, g = lane & 15u;
-    const uint32_t rest     = blockIdx.x * kNttTileCols + 2u * warp + e;
+    const uint32_t rest     = ntt_route_block(rt) * kNttTileCols + 2u * warp + e;
     const uint32_t low_mask = (1u << lo) - 1u;
     const uint32_t col_base = ((rest >> lo) << hi) | (rest & low_mask); // position of row 0 of this column
     Fr             v[8];
@@ -247,7 +276,7 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
             }
             if (post)
                 Fr::mul(v[q], v[q], post[pos]);
-            x[pos] = v[q];
+            *ntt_route_dst<ROUTED>(rt, x, pos) = v[q];
         }
     }
     else
@@ -272,25 +301,9 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
             }
         }
         ntt_dit_rounds(v, wsm, twp, g, e);
-        if (SCATTER)
-        {
-            const int world = sc.world;
 #pragma unroll
-            for (int q = 0; q < 8; q++)
-            {
-                uint32_t pos = col_base | (ntt_row1(g, q) << lo);
-                int      r   = 0;
-                while (r + 1 < world && pos >= sc.bound[r + 1])
-                    r++;
-                sc.dst[blockIdx.y][r][pos] = v[q];
-            }
-        }
-        else
-        {
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-                x[col_base | (ntt_row1(g, q) << lo)] = v[q];
-        }
+        for (int q = 0; q < 8; q++)
+            *ntt_route_dst<ROUTED>(rt, x, col_base | (ntt_row1(g, q) << lo)) = v[q];
     }
 }
 
@@ -299,9 +312,10 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
 // warp runs the DIF rounds, multiplies by post[pos] (= w_2n^bitrev(pos) / n: ifft scaling + coset shift) and
 // continues with the DIT rounds. R3 is the last DIF round and the first DIT round, so the hand-over happens in
 // registers. Saves one full read + write of the vector and a shared-memory pass per chain.
+template <bool ROUTED = false>
 __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
     k_ntt_mid(NttBatch batch, const Fr* __restrict__ tw_inv, const Fr* __restrict__ tw_fwd, uint32_t k,
-              const Fr* __restrict__ post)
+              const Fr* __restrict__ post, const NttRoute rt)
 {
     Fr* __restrict__        x = batch.x[blockIdx.y];
     extern __shared__ uint4 ntt_smem[];
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
         ntt_tw_fill(twF, tw_fwd, tid - 64, k);
     __syncthreads();
     const uint32_t e = lane >> 4, g = lane & 15u;
-    const uint32_t col_base = (blockIdx.x * kNttTileCols + 2u * warp + e) << kNttTileBits; // 128 contiguous elements
+    const uint32_t col_base = (ntt_route_block(rt) * kNttTileCols + 2u * warp + e) << kNttTileBits; // 128 contiguous elements
     Fr             v[8];
 #pragma unroll
     for (int q = 0; q < 8; q++)
@@ -329,7 +343,7 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
     ntt_dit_rounds(v, wsm, twF, g, e);
 #pragma unroll
     for (int q = 0; q < 8; q++)
-        x[col_base + ntt_row1(g, q)] = v[q];
+        *ntt_route_dst<ROUTED>(rt, x, col_base + ntt_row1(g, q)) = v[q];
 }
 
 } // namespace kzp

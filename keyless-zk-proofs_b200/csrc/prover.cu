@@ -200,8 +200,9 @@ static void artefacts_from_sums(const ShardPartials& sums, MsmArtefacts& art)
     put1(art.bytes + 320, H);
 }
 
-// Proof assembly in two steps so that everything that does not need the H MSM result runs while the GPU is still
-// busy with it (the witness MSMs finish first): early = pi_a, pi_b and pi_c without its H term; final = + H.
+// Proof assembly in three steps, each as soon as its inputs are on the host, so that everything that does not need
+// the H MSM result runs while the GPU is still busy with it: g1 = pi_a and pi_c without its H term (needs A, B1, C:
+// two 254-bit scalar multiplications), g2 = pi_b (needs B2), final = + H.
 // pi_c = C + H + s*pi_a + r*pib1 - rs*delta1 (groth16.cpp:340-352) is a sum in an abelian group, so adding H last
 // gives the same affine point.
 struct EarlyProof
@@ -209,35 +210,24 @@ struct EarlyProof
     HG1         A, B1, C;
     HG2         B2;
     HG1         pi_c_partial; // C + s*pi_a + r*pib1 - rs*delta1
-    std::string head;         // JSON up to and including "pi_c":[
+    std::string pi_a, pi_b;   // their JSON fragments
 };
 
-static void assemble_early(const HostVk& vk, const BlindTerms& bt, const HG1& A, const HG1& B1, const HG1& C,
-                           const HG2& B2, EarlyProof& ep)
+static void assemble_early_g1(const HostVk& vk, const BlindTerms& bt, const HG1& A, const HG1& B1, const HG1& C, EarlyProof& ep)
 {
     HG1Affine alpha1, beta1;
-    HG2Affine beta2;
     memcpy(&alpha1, vk.alpha1, 64);
     memcpy(&beta1, vk.beta1, 64);
-    memcpy(&beta2, vk.beta2, 128);
     ep.A  = A;
     ep.B1 = B1;
     ep.C  = C;
-    ep.B2 = B2;
     HG1 al, be1;
-    HG2 be2;
     HG1::from_affine(al, alpha1);
     HG1::from_affine(be1, beta1);
-    HG2::from_affine(be2, beta2);
-
     // pi_a = A + alpha1 + r*delta1            (groth16.cpp:328-330)
     HG1 pi_a = A;
     HG1::add(pi_a, al);
     HG1::add(pi_a, bt.r_delta1);
-    // pi_b = B2 + beta2 + s*delta2            (:332-334)
-    HG2 pi_b = B2;
-    HG2::add(pi_b, be2);
-    HG2::add(pi_b, bt.s_delta2);
     // pib1 = B1 + beta1 + s*delta1            (:336-338)
     HG1 pib1 = B1;
     HG1::add(pib1, be1);
@@ -252,21 +242,31 @@ static void assemble_early(const HostVk& vk, const BlindTerms& bt, const HG1& A,
     HG1::neg(np1, bt.rs_delta1);
     HG1::add(pc, np1);
     ep.pi_c_partial = pc;
-
     HG1Affine a_aff;
-    HG2Affine b_aff;
     HG1::to_affine(a_aff, pi_a);
-    HG2::to_affine(b_aff, pi_b);
-    // compact JSON, keys in sorted order, exactly what nlohmann::json::dump() prints for
-    // Proof::toJson (groth16.cpp:379-410, fullprover.cpp:246)
-    std::string& j = ep.head;
+    std::string& j = ep.pi_a;
     j.clear();
-    j.reserve(900);
-    j += "{\"pi_a\":[";
     append_decimal(j, a_aff.x);
     j += ',';
     append_decimal(j, a_aff.y);
-    j += ",\"1\"],\"pi_b\":[[";
+}
+
+static void assemble_early_g2(const HostVk& vk, const BlindTerms& bt, const HG2& B2, EarlyProof& ep)
+{
+    HG2Affine beta2;
+    memcpy(&beta2, vk.beta2, 128);
+    ep.B2 = B2;
+    HG2 be2;
+    HG2::from_affine(be2, beta2);
+    // pi_b = B2 + beta2 + s*delta2            (:332-334)
+    HG2 pi_b = B2;
+    HG2::add(pi_b, be2);
+    HG2::add(pi_b, bt.s_delta2);
+    HG2Affine b_aff;
+    HG2::to_affine(b_aff, pi_b);
+    std::string& j = ep.pi_b;
+    j.clear();
+    j += '[';
     append_decimal(j, b_aff.x.a);
     j += ',';
     append_decimal(j, b_aff.x.b);
@@ -274,7 +274,14 @@ static void assemble_early(const HostVk& vk, const BlindTerms& bt, const HG1& A,
     append_decimal(j, b_aff.y.a);
     j += ',';
     append_decimal(j, b_aff.y.b);
-    j += "],[\"1\",\"0\"]],\"pi_c\":[";
+    j += ']';
+}
+
+static void assemble_early(const HostVk& vk, const BlindTerms& bt, const HG1& A, const HG1& B1, const HG1& C,
+                           const HG2& B2, EarlyProof& ep)
+{
+    assemble_early_g1(vk, bt, A, B1, C, ep);
+    assemble_early_g2(vk, bt, B2, ep);
 }
 
 // sums_out (optional) receives the five summed MSM results (XYZZ) for the parity artefacts.
@@ -292,7 +299,15 @@ static std::string assemble_final(const EarlyProof& ep, const HG1& H, ShardParti
     }
     HG1Affine c_aff;
     HG1::to_affine(c_aff, pi_c);
-    std::string j = ep.head;
+    // compact JSON, keys in sorted order, exactly what nlohmann::json::dump() prints for
+    // Proof::toJson (groth16.cpp:379-410, fullprover.cpp:246)
+    std::string j;
+    j.reserve(900);
+    j += "{\"pi_a\":[";
+    j += ep.pi_a;
+    j += ",\"1\"],\"pi_b\":[";
+    j += ep.pi_b;
+    j += ",[\"1\",\"0\"]],\"pi_c\":[";
     append_decimal(j, c_aff.x);
     j += ',';
     append_decimal(j, c_aff.y);
@@ -742,8 +757,13 @@ class DeviceProverImpl;
 struct GroupLinks
 {
     std::vector<DeviceProverImpl*> shard;
-    int  owner_of[3]   = {0, 0, 0}; // shard that computes a, b, c (SpMV + coset-NTT chain)
+    int  owner_of[3]   = {0, 0, 0}; // shard that computes a, b, c (SpMV + coset-NTT chain) when !dist_ntt
     bool fused_scatter = false;     // the chain's last level stores every shard's slice straight into that shard's buffer
+    // Every chain spread over all 2^dist_k shards (ntt_coset_chain_phase): each shard runs 1/2^k of every level of
+    // a, b and c; the two transposes between the low-bit and the top-bit partition and the delivery of the H slices
+    // are peer stores of the level kernels. Needs a power-of-two shard count, a batched domain size and peer access.
+    bool     dist_ntt = false;
+    uint32_t dist_k   = 0;
 };
 
 class DeviceProverImpl
@@ -763,7 +783,7 @@ public:
     cudaStream_t st_h = nullptr, st_w = nullptr, st_w2 = nullptr, st_copy = nullptr;
     enum
     {
-        EV_H2D0, EV_H2D1, EV_H0, EV_SPMV, EV_NTT, EV_HMSM, EV_W0, EV_WSORT, EV_WG1, EV_WG2_0, EV_WG2, EV_XCHG, EV_COUNT
+        EV_H2D0, EV_H2D1, EV_H0, EV_SPMV, EV_NTT, EV_HMSM, EV_W0, EV_WSORT, EV_WG1, EV_WG2_0, EV_WG2, EV_XCHG, EV_X1, EV_X2, EV_COUNT
     };
     cudaEvent_t ev[EV_COUNT] = {};
 
@@ -799,6 +819,7 @@ public:
     ProveTimings  tm;
     bool          witness_resident = false;
     bool          gpu_in_flight    = false;
+    bool          tm_pending       = false;
     uint32_t      launches_        = 0;
 
     void set_device() const { KZP_CUDA_CHECK(cudaSetDevice(device)); }
@@ -911,8 +932,10 @@ public:
         // with them whatever the priority.
         int prio_lo = 0, prio_hi = 0;
         KZP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        // A shard of a multi-GPU proof runs the witness streams at high priority: its share of the H MSM no longer
+        // hides them (2 GPUs, same box: 6.52 -> 6.25 ms per proof), and the host needs A, B1, C early for its part.
         const char* pe   = getenv("KZP_PRIO");
-        int         mode = pe ? atoi(pe) : 0;
+        int         mode = pe ? atoi(pe) : (packer != nullptr ? 1 : 0);
         int         ph   = mode == 1 ? prio_lo : (mode == -1 ? prio_hi : prio_lo);
         int         pw   = mode == 1 ? prio_hi : (mode == -1 ? prio_lo : prio_lo);
         KZP_CUDA_CHECK(cudaStreamCreateWithPriority(&st_h, cudaStreamNonBlocking, ph));
@@ -960,7 +983,10 @@ public:
         // scalar instead of 16 (and 2^19 buckets, about 52 entries each at 2^21). Small domains keep c = 16: their
         // cost is the bucket reduction, not the accumulation.   KZP_H_WINDOW overrides (16..22).
         auto envu = [](const char* n, uint32_t d) { const char* e = getenv(n); return e ? (uint32_t)atoi(e) : d; };
-        const uint32_t h_window = envu("KZP_H_WINDOW", (h1 - h0) >= (1u << 18) ? 20u : 16u);
+        // Measured alone (scripts/window_sweep.py, uniform scalars; c = 16 / 17 / 20): 2^18 points 1.11 / 1.16 / 1.39 ms,
+        // 2^19 1.77 / 1.76 / 1.95 ms, 2^20 3.12 / 3.02 / 3.01 ms: the wide window pays from 2^20 points (the slices of
+        // a proof sharded over 4 or 8 GPUs stay at c = 16).
+        const uint32_t h_window = envu("KZP_H_WINDOW", (h1 - h0) >= (1u << 20) ? 20u : 16u);
         make_bases(bases_h, zh.points_h, domain, 0, h0, h1, h_window);
         msm_sort_create(sort_w, (uint32_t)(w1 - w0), nullptr, (uint32_t)w0);
         msm_sort_create(sort_h, (uint32_t)(h1 - h0), nullptr, (uint32_t)h0, h_window);
@@ -968,7 +994,7 @@ public:
         // bytes): small chunks keep enough threads in flight; G2 additions are 3x as long, so smaller still.
         // measured under the final schedule (same box): G1 32 -> 64 and G2 8 -> 16 take the proof from 12.05 to 11.80 ms
         // H with wide windows: about 52 entries per bucket, 64-entry chunks (measured 128 / 64 / 32: 10.90 / 10.70 / 10.89 ms per proof)
-        const uint32_t ch_g1 = envu("KZP_CHUNK_G1", 64), ch_g2 = envu("KZP_CHUNK_G2", 16), ch_h = envu("KZP_CHUNK_H", h_window >= 19 ? 64 : 0);
+        const uint32_t ch_g1 = envu("KZP_CHUNK_G1", 64), ch_g2 = envu("KZP_CHUNK_G2", 16), ch_h = envu("KZP_CHUNK_H", h_window >= 19 ? ((h1 - h0) >= (1u << 21) ? 64 : 32) : 0);
         msm_scratch_create(sc_a, sort_w, ch_g1);
         msm_scratch_create(sc_b1, sort_w, ch_g1);
         msm_scratch_create(sc_c, sort_w, ch_g1);
@@ -1105,25 +1131,29 @@ public:
     // Enqueues the whole GPU part of one proof (no host synchronisation).
     void launch_gpu()
     {
-        launch_prefix();
+        launch_front();
+        launch_witness();
         launch_h();
     }
 
-    // SpMV, the coset-NTT chains of the vectors this prover owns, and everything on the witness streams.
-    // In a group (links != nullptr) the chain output is handed to the other shards: either the chain's last level
-    // stores each shard's slice [h0, h1) of the H domain straight into that shard's buffer over NVLink (fused_scatter),
-    // or the finished vector is cut up with peer copies.
-    void launch_prefix()
+    void begin_proof()
     {
         if (!witness_resident)
             throw FormatError("no witness uploaded");
         set_device();
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(d_w);
         KZP_CUDA_CHECK(cudaStreamWaitEvent(st_h, ev[EV_H2D1], 0));
         KZP_CUDA_CHECK(cudaStreamWaitEvent(st_w, ev[EV_H2D1], 0));
-
-        // ---- stream H: SpMV -> 3 x (iNTT, coset, NTT) -> pointwise -> MSM H
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_H0], st_h));
+        launches_ = 0;
+    }
+
+    // SpMV and the coset-NTT chains of the vectors this prover owns (stream H, up to EV_NTT).
+    // In a group (links != nullptr) the chain output is handed to the other shards: either the chain's last level
+    // stores each shard's slice [h0, h1) of the H domain straight into that shard's buffer over NVLink (fused_scatter),
+    // or the finished vector is cut up with peer copies.
+    void launch_front()
+    {
+        begin_proof();
         uint32_t ntt_kernels = 0;
         if (own_mask)
         {
@@ -1147,16 +1177,17 @@ public:
                 }
             if (links && links->fused_scatter)
             {
-                NttScatter sc = {};
-                sc.world      = (int)links->shard.size();
-                for (int r = 0; r < sc.world; r++)
+                NttRoute rt = {};
+                rt.store    = kNttStoreBounds;
+                rt.world    = (int)links->shard.size();
+                for (int r = 0; r < rt.world; r++)
                 {
-                    sc.bound[r] = (uint32_t)links->shard[r]->h0;
+                    rt.bound[r] = (uint32_t)links->shard[r]->h0;
                     for (int i = 0; i < cnt; i++)
-                        sc.dst[i][r] = links->shard[r]->vec_ptr(owned[i]);
+                        rt.dst[i][r] = links->shard[r]->vec_ptr(owned[i]);
                 }
-                sc.bound[sc.world] = domain;
-                ntt_kernels        = ntt_coset_chain(ntt, vecs, cnt, st_h, &sc);
+                rt.bound[rt.world] = domain;
+                ntt_kernels        = ntt_coset_chain(ntt, vecs, cnt, st_h, &rt);
             }
             else
             {
@@ -1178,8 +1209,47 @@ public:
         else
             h_pointwise(d_a, d_b, d_c, d_h, domain, st_h);
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_NTT], st_h));
+        launches_ += (own_mask ? 1 : 0) + ntt_kernels;
+    }
 
-        // ---- stream W: one digit sort of the witness, then A, B1, C as one G1 batch; B2 on its own stream
+    // The distributed front (links->dist_ntt): phase 0 = this shard's rows of the SpMV + the inverse levels, phase 1 =
+    // the fused middle level, phase 2 = the forward levels. Every phase ends in peer stores into the other shards'
+    // buffers and an event; the next phase waits for ALL shards' events, which ProverGroup guarantees to have been
+    // recorded for this proof (host barrier between the phases).
+    void launch_dist(int phase)
+    {
+        const uint32_t k = links->dist_k;
+        Fr* const      vecs[3] = {d_a, d_b, d_c};
+        Fr*            dst[3][kNttMaxShards] = {};
+        for (size_t r = 0; r < links->shard.size(); r++)
+            for (int i = 0; i < 3; i++)
+                dst[i][r] = links->shard[r]->vec_ptr(i);
+        if (phase == 0)
+        {
+            begin_proof();
+            spmv_abc(csr, d_w, d_a, d_b, d_c, st_h, 7, k, (uint32_t)rank);
+            KZP_CUDA_CHECK(cudaEventRecord(ev[EV_SPMV], st_h));
+            launches_ += 1;
+        }
+        else
+        {
+            set_device();
+            for (const DeviceProverImpl* peer : links->shard)
+                if (peer != this)
+                    KZP_CUDA_CHECK(cudaStreamWaitEvent(st_h, peer->ev[phase == 1 ? EV_X1 : EV_X2], 0));
+        }
+        launches_ += ntt_coset_chain_phase(ntt, vecs, 3, st_h, phase, k, (uint32_t)rank, dst);
+        KZP_CUDA_CHECK(cudaEventRecord(ev[phase == 0 ? EV_X1 : (phase == 1 ? EV_X2 : EV_XCHG)], st_h));
+        if (phase == 2)
+            KZP_CUDA_CHECK(cudaEventRecord(ev[EV_NTT], st_h));
+    }
+
+    // Everything on the witness streams: one digit sort of the witness, then A, B1, C as one G1 batch; B2 on its own
+    // stream. Call after EV_NTT has been recorded for this proof.
+    void launch_witness()
+    {
+        set_device();
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(d_w);
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_W0], st_w));
         msm_sort_run(sort_w, w, st_w);
         KZP_CUDA_CHECK(cudaEventRecord(ev[EV_WSORT], st_w));
@@ -1209,7 +1279,7 @@ public:
             KZP_CUDA_CHECK(cudaMemcpyAsync(pinned_out + 256, sc_c.result, 128, cudaMemcpyDeviceToHost, st_w));
             KZP_CUDA_CHECK(cudaEventRecord(ev[EV_WG1], st_w));
         }
-        launches_ = (own_mask ? 1 : 0) + ntt_kernels + 2 * kMsmSortLaunches + 3 * kMsmReduceLaunches; // + 1 per upload (expand)
+        launches_ += 2 * kMsmSortLaunches + 3 * kMsmReduceLaunches; // + 1 per upload (expand)
     }
 
     // The H MSM. In a group: first wait until the owners of a, b, c have delivered this shard's slices (their EV_XCHG
@@ -1220,15 +1290,22 @@ public:
         set_device();
         if (links)
         {
-            for (int i = 0; i < 3; i++)
+            if (links->dist_ntt)
             {
-                const DeviceProverImpl* o = links->shard[links->owner_of[i]];
-                bool seen = o == this;
-                for (int j = 0; j < i; j++)
-                    seen = seen || links->shard[links->owner_of[j]] == o;
-                if (!seen)
-                    KZP_CUDA_CHECK(cudaStreamWaitEvent(st_h, o->ev[EV_XCHG], 0));
+                for (const DeviceProverImpl* peer : links->shard)
+                    if (peer != this)
+                        KZP_CUDA_CHECK(cudaStreamWaitEvent(st_h, peer->ev[EV_XCHG], 0));
             }
+            else
+                for (int i = 0; i < 3; i++)
+                {
+                    const DeviceProverImpl* o = links->shard[links->owner_of[i]];
+                    bool seen = o == this;
+                    for (int j = 0; j < i; j++)
+                        seen = seen || links->shard[links->owner_of[j]] == o;
+                    if (!seen)
+                        KZP_CUDA_CHECK(cudaStreamWaitEvent(st_h, o->ev[EV_XCHG], 0));
+                }
             if (h1 > h0)
                 h_pointwise(d_a + h0, d_b + h0, d_c + h0, d_h + h0, h1 - h0, st_h);
         }
@@ -1244,13 +1321,19 @@ public:
         gpu_in_flight = true;
     }
 
-    // witness-side MSM results (A, B1, C, B2) are on the host after this; the H stream may still be running
-    void wait_witness_msms()
+    // witness-side MSM results are on the host after these (A, B1, C / B2); the H stream may still be running
+    void wait_witness_g1()
     {
         if (!gpu_in_flight)
             throw FormatError("no proof in flight");
         set_device();
         KZP_CUDA_CHECK(cudaStreamSynchronize(st_w));
+    }
+    void wait_witness_g2()
+    {
+        if (!gpu_in_flight)
+            throw FormatError("no proof in flight");
+        set_device();
         KZP_CUDA_CHECK(cudaStreamSynchronize(st_w2));
     }
 
@@ -1264,7 +1347,15 @@ public:
         KZP_CUDA_CHECK(cudaStreamSynchronize(st_w2));
         KZP_CUDA_CHECK(cudaStreamSynchronize(st_h));
         memcpy(parts.bytes, pinned_out, sizeof(parts.bytes));
+        tm_pending = true; // the event queries cost a few microseconds each: made when somebody asks (timings())
+    }
 
+    const ProveTimings& timings()
+    {
+        if (!tm_pending)
+            return tm;
+        tm_pending = false;
+        set_device();
         auto el = [&](int a, int b) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ev[a], ev[b]);
@@ -1280,6 +1371,7 @@ public:
         tm.msm_wg2_ms   = el(EV_WG2_0, EV_WG2);
         tm.gpu_ms       = std::max(std::max(el(EV_H0, EV_HMSM), el(EV_H0, EV_WG1)), el(EV_H0, EV_WG2));
         tm.kernel_launches = launches_;
+        return tm;
     }
 
     void run_gpu()
@@ -1305,22 +1397,31 @@ public:
     template <class Upload>
     std::string prove_with(Upload&& do_upload, const uint8_t* r32, const uint8_t* s32)
     {
+        static const bool timeline = getenv("KZP_DEBUG_TIMELINE") != nullptr;
         double t0 = now_ms();
         do_upload();
         launch_gpu();
+        double     ta = now_ms();
         BlindTerms bt;
         compute_blind_terms(vk, r32, s32, bt);
-        wait_witness_msms();
+        double tb = now_ms();
         EarlyProof ep;
+        wait_witness_g1();
+        double tc = now_ms();
         {
             HG1 A, B1, C;
-            HG2 B2;
             memcpy(&A, pinned_out + 0, 128);
             memcpy(&B1, pinned_out + 128, 128);
             memcpy(&C, pinned_out + 256, 128);
-            memcpy(&B2, pinned_out + 512, 256);
-            assemble_early(vk, bt, A, B1, C, B2, ep);
+            assemble_early_g1(vk, bt, A, B1, C, ep);
         }
+        wait_witness_g2();
+        {
+            HG2 B2;
+            memcpy(&B2, pinned_out + 512, 256);
+            assemble_early_g2(vk, bt, B2, ep);
+        }
+        double td = now_ms();
         wait_gpu();
         double t1 = now_ms();
         HG1    H;
@@ -1329,6 +1430,10 @@ public:
         art_valid           = false;
         tm.assemble_host_ms = (float)(now_ms() - t1);
         tm.total_host_ms    = (float)(now_ms() - t0);
+        if (timeline)
+            fprintf(stderr, "[kzp timeline] upload+launch %.3f | blind terms +%.3f | A, B1, C waited +%.3f | early assembly (incl. waiting for B2) +%.3f | "
+                            "H waited +%.3f | final +%.3f = %.3f ms\n",
+                    ta - t0, tb - ta, tc - tb, td - tc, t1 - td, now_ms() - t1, now_ms() - t0);
         return j;
     }
 
@@ -1364,6 +1469,7 @@ public:
     MsmArtefacts          art;
     ProveTimings          tm;
     bool                  gpu_in_flight = false;
+    bool                  tm_pending    = false;
 
     static void owners_for(int world, int (&owner_of)[3])
     {
@@ -1393,6 +1499,9 @@ public:
             n_vars = parse_zkey(bin).n_vars;
         }
         owners_for(world, links.owner_of);
+        // KZP_GROUP_NTT=dist (default when possible) | chain: every chain spread over all shards, or one chain per shard
+        const char* ne       = getenv("KZP_GROUP_NTT");
+        const bool  want_dist = !(ne && strcmp(ne, "chain") == 0) && world >= 2 && (world & (world - 1)) == 0;
         try
         {
             KZP_CUDA_CHECK(cudaSetDevice(devices[0]));
@@ -1403,7 +1512,9 @@ public:
             crew->run([&](int r) {
                 try
                 {
-                    uint32_t mask = 0;
+                    // which vectors this shard must be able to compute: all three when the chains may be spread over
+                    // the shards (decided below, once the domain size and the peer topology are known)
+                    uint32_t mask = want_dist ? 7u : 0u;
                     for (int i = 0; i < 3; i++)
                         if (links.owner_of[i] == r)
                             mask |= 1u << i;
@@ -1442,6 +1553,22 @@ public:
                 links.shard.push_back(p.get());
             const char* se      = getenv("KZP_GROUP_SCATTER");
             links.fused_scatter = (se ? atoi(se) != 0 : true) && all_peers && ntt_chain_is_batched(sh[0]->log_domain);
+            uint32_t k = 0;
+            while ((1 << k) < world)
+                k++;
+            // the top-bit partition must coincide with the H slices: 2^k | domain, and every slice at least one tile
+            links.dist_ntt = want_dist && all_peers && ntt_chain_is_batched(sh[0]->log_domain) && k <= 3 &&
+                             sh[0]->log_domain >= 11 + k;
+            links.dist_k = k;
+            if (!links.dist_ntt)
+                for (int r = 0; r < world; r++) // back to one chain per owner
+                {
+                    uint32_t mask = 0;
+                    for (int i = 0; i < 3; i++)
+                        if (links.owner_of[i] == r)
+                            mask |= 1u << i;
+                    sh[r]->own_mask = mask;
+                }
             for (auto& p : sh)
                 p->links = &links;
         }
@@ -1479,23 +1606,41 @@ public:
             {
                 if (ps)
                     sh[r]->enqueue_packed(*ps);
-                sh[r]->launch_prefix();
+                if (links.dist_ntt)
+                    sh[r]->launch_dist(0);
+                else
+                {
+                    sh[r]->launch_front();
+                    sh[r]->launch_witness();
+                }
             }
             catch (...)
             {
                 err[r] = std::current_exception();
                 failed.store(1);
             }
-            crew->barrier();
-            if (failed.load())
-                return;
-            try
+            // every barrier: the events the next stage waits on have been recorded by all shards for this proof
+            for (int stage = 1; stage <= (links.dist_ntt ? 3 : 1); stage++)
             {
-                sh[r]->launch_h();
-            }
-            catch (...)
-            {
-                err[r] = std::current_exception();
+                crew->barrier();
+                if (failed.load())
+                    return;
+                try
+                {
+                    if (!links.dist_ntt || stage == 3)
+                        sh[r]->launch_h();
+                    else
+                    {
+                        sh[r]->launch_dist(stage);
+                        if (stage == 2)
+                            sh[r]->launch_witness();
+                    }
+                }
+                catch (...)
+                {
+                    err[r] = std::current_exception();
+                    failed.store(1);
+                }
             }
         });
         if (ps)
@@ -1540,25 +1685,32 @@ public:
             throw FormatError("witness has fewer values than the zkey has variables");
     }
 
-    void wait_witness_msms(HG1& A, HG1& B1, HG1& C, HG2& B2)
+    void wait_witness_g1(HG1& A, HG1& B1, HG1& C)
     {
         if (!gpu_in_flight)
             throw FormatError("no proof in flight");
         HG1::set_inf(A);
         HG1::set_inf(B1);
         HG1::set_inf(C);
-        HG2::set_inf(B2);
         for (auto& p : sh)
         {
-            p->wait_witness_msms();
+            p->wait_witness_g1();
             HG1 t;
-            HG2 t2;
             memcpy(&t, p->pinned_out + 0, 128);
             HG1::add(A, t);
             memcpy(&t, p->pinned_out + 128, 128);
             HG1::add(B1, t);
             memcpy(&t, p->pinned_out + 256, 128);
             HG1::add(C, t);
+        }
+    }
+    void wait_witness_g2(HG2& B2)
+    {
+        HG2::set_inf(B2);
+        for (auto& p : sh)
+        {
+            p->wait_witness_g2();
+            HG2 t2;
             memcpy(&t2, p->pinned_out + 512, 256);
             HG2::add(B2, t2);
         }
@@ -1577,7 +1729,6 @@ public:
         HG1::set_inf(C);
         HG1::set_inf(H);
         HG2::set_inf(B2);
-        ProveTimings t;
         for (auto& p : sh)
         {
             p->wait_gpu();
@@ -1593,7 +1744,24 @@ public:
             HG1::add(H, g);
             memcpy(&g2, p->parts.bytes + 512, 256);
             HG2::add(B2, g2);
-            const ProveTimings& q = p->tm;
+        }
+        memcpy(parts.bytes + 0, &A, 128);
+        memcpy(parts.bytes + 128, &B1, 128);
+        memcpy(parts.bytes + 256, &C, 128);
+        memcpy(parts.bytes + 384, &H, 128);
+        memcpy(parts.bytes + 512, &B2, 256);
+        tm_pending = true;
+    }
+
+    const ProveTimings& timings()
+    {
+        if (!tm_pending)
+            return tm;
+        tm_pending = false;
+        ProveTimings t;
+        for (auto& p : sh)
+        {
+            const ProveTimings& q = p->timings();
             t.h2d_ms       = std::max(t.h2d_ms, q.h2d_ms);
             t.spmv_ms      = std::max(t.spmv_ms, q.spmv_ms);
             t.ntt_ms       = std::max(t.ntt_ms, q.ntt_ms);
@@ -1605,14 +1773,10 @@ public:
             t.h2d_mbytes += q.h2d_mbytes;
             t.kernel_launches += q.kernel_launches;
         }
-        memcpy(parts.bytes + 0, &A, 128);
-        memcpy(parts.bytes + 128, &B1, 128);
-        memcpy(parts.bytes + 256, &C, 128);
-        memcpy(parts.bytes + 384, &H, 128);
-        memcpy(parts.bytes + 512, &B2, 256);
         t.assemble_host_ms = tm.assemble_host_ms;
         t.total_host_ms    = tm.total_host_ms;
         tm                 = t;
+        return tm;
     }
 
     void run_gpu()
@@ -1636,19 +1800,30 @@ public:
     template <class Start>
     std::string prove_with(Start&& start, const uint8_t* r32, const uint8_t* s32)
     {
+        static const bool timeline = getenv("KZP_DEBUG_TIMELINE") != nullptr;
         double t0 = now_ms();
         start();
+        double     ta = now_ms();
         BlindTerms bt;
         compute_blind_terms(sh[0]->vk, r32, s32, bt);
+        double     tb = now_ms(), tc;
         EarlyProof ep;
         {
             HG1 A, B1, C;
             HG2 B2;
-            wait_witness_msms(A, B1, C, B2);
-            assemble_early(sh[0]->vk, bt, A, B1, C, B2, ep);
+            wait_witness_g1(A, B1, C);
+            tc = now_ms();
+            assemble_early_g1(sh[0]->vk, bt, A, B1, C, ep);
+            wait_witness_g2(B2);
+            assemble_early_g2(sh[0]->vk, bt, B2, ep);
         }
+        double td = now_ms();
         wait_gpu();
         double t1 = now_ms();
+        if (timeline)
+            fprintf(stderr, "[kzp group timeline] upload+launch %.3f | blind terms +%.3f | A, B1, C waited +%.3f | early assembly (incl. waiting for B2) "
+                            "+%.3f | H waited +%.3f\n",
+                    ta - t0, tb - ta, tc - tb, td - tc, t1 - td);
         HG1    H;
         memcpy(&H, parts.bytes + 384, 128);
         std::string j       = assemble_final(ep, H, &sums);
@@ -1717,7 +1892,8 @@ uint32_t DeviceProver::domain_size() const { return first().domain; }
 uint64_t DeviceProver::n_coefs() const { return first().n_coefs; }
 int      DeviceProver::device() const { return first().device; }
 int      DeviceProver::group_size() const { return group_ ? group_->world() : 1; }
-bool     DeviceProver::group_fused_exchange() const { return group_ && group_->links.fused_scatter; }
+bool     DeviceProver::group_fused_exchange() const { return group_ && (group_->links.fused_scatter || group_->links.dist_ntt); }
+bool     DeviceProver::group_distributed_ntt() const { return group_ && group_->links.dist_ntt; }
 void     DeviceProver::upload_witness(const uint8_t* values, uint64_t n)
 {
     if (group_)
@@ -1775,7 +1951,13 @@ std::string DeviceProver::prove_fd(int fd, uint64_t file_offset, uint64_t n, con
     }
     return impl_->prove_with([&] { impl_->upload_fd(fd, file_offset, n); }, r32, s32);
 }
-const ProveTimings& DeviceProver::timings() const { return group_ ? group_->tm : impl_->tm; }
+const ProveTimings& DeviceProver::timings() const { return group_ ? group_->timings() : impl_->timings(); }
+const ProveTimings& DeviceProver::shard_timings(int shard) const
+{
+    if (group_ && shard >= 0 && shard < group_->world())
+        return group_->sh[shard]->timings();
+    return first().timings();
+}
 void DeviceProver::msm_profile(int which, float* ms, uint64_t* entries) const
 {
     DeviceProverImpl& p = first();

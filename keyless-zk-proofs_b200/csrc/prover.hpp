@@ -82,6 +82,7 @@ public:
     ~DeviceProver();
     int  group_size() const;           // 1 for a single-GPU prover
     bool group_fused_exchange() const; // the slices travel as peer stores of the chain's last level (else peer copies)
+    bool group_distributed_ntt() const; // every coset-NTT chain is spread over all shards (else one chain per shard)
 
     uint32_t n_vars() const;
     uint32_t n_public() const;
@@ -108,7 +109,8 @@ public:
     std::string prove(const uint8_t* values, uint64_t n, const uint8_t* r32, const uint8_t* s32);
     std::string prove_fd(int fd, uint64_t file_offset, uint64_t n, const uint8_t* r32, const uint8_t* s32);
 
-    const ProveTimings& timings() const;
+    const ProveTimings& timings() const;                 // a group: per-stage maximum over the shards
+    const ProveTimings& shard_timings(int shard) const;  // one shard of a group (shard 0 of a single prover)
     // bucket-accumulation kernel of MSM `which` (0 A, 1 B1, 2 B2, 3 C, 4 H) in the last proof: duration and entries
     void msm_profile(int which, float* accumulate_ms, uint64_t* entries) const;
     const MsmArtefacts& msm_artefacts() const; // filled by assemble()

@@ -434,11 +434,14 @@ def _group_devices(gpu, shards):
     return [i % gpu for i in range(shards)]
 
 
-@pytest.mark.parametrize("shards,scatter", [(1, 1), (2, 1), (2, 0), (3, 1), (4, 0), (5, 1), (8, 1)])
-def test_group_proof_matches_reference(gpu, kzp, oracle, ref, port, workdir, monkeypatch, shards, scatter):
+@pytest.mark.parametrize("shards,ntt,scatter", [(1, "dist", 1), (2, "dist", 1), (4, "dist", 1), (8, "dist", 1), (2, "chain", 1),
+                                                 (2, "chain", 0), (3, "dist", 1), (4, "chain", 0), (5, "chain", 1),
+                                                 (8, "chain", 1)])
+def test_group_proof_matches_reference(gpu, kzp, oracle, ref, port, workdir, monkeypatch, shards, ntt, scatter):
     """SURVEY.md §8(e) as a product feature: kzp_prover_new_group shards ONE proof inside kzp_prover_prove — MSM base
-    ranges split, one coset-NTT chain per shard, slices exchanged as fused peer stores (scatter=1; domain 2^14 takes
-    the batched chain) or peer copies (scatter=0). Proof bytes, H coefficients and the five MSM results equal the
+    ranges split; the coset-NTT chains either spread over all shards with fused peer-store transposes (ntt=dist: 2, 4,
+    8 shards) or one chain per shard with the slices exchanged as fused peer stores (scatter=1; domain 2^14 takes the
+    batched chain) or peer copies (scatter=0). Proof bytes, H coefficients and the five MSM results equal the
     reference's, through the file, in-memory and resident entry points."""
     z = os.path.join(workdir, "grp.zkey")
     w = os.path.join(workdir, "grp.wtns")
@@ -449,8 +452,10 @@ def test_group_proof_matches_reference(gpu, kzp, oracle, ref, port, workdir, mon
     rj, _ = ref.prove(z, w, r, s)
     _, rh, rm = ref.dump(z, w, info["domain"])
     monkeypatch.setenv("KZP_GROUP_SCATTER", str(scatter))
+    monkeypatch.setenv("KZP_GROUP_NTT", ntt)
     with kzp.FullProver(z, devices=_group_devices(gpu, shards)) as p:
-        assert p.group_info() == (shards, bool(scatter))
+        dist = ntt == "dist" and shards in (2, 4, 8)
+        assert p.group_info() == (shards, bool(scatter) or dist, dist)
         for _ in range(2):  # the second proof reuses buffers the first one's peers wrote into
             js, _ = p.prove(w, r, s)
             assert js == rj
@@ -482,7 +487,7 @@ def test_group_proof_small_circuits(gpu, kzp, oracle, name, zkey, wtns, shards):
     d = os.path.join(GOLDEN, name)
     exp = json.load(open(os.path.join(d, "expected.json")))
     with kzp.FullProver(os.path.join(d, zkey), devices=_group_devices(gpu, shards)) as p:
-        assert p.group_info() == (shards, False)
+        assert p.group_info() == (shards, False, False)
         _check_against_expected(oracle, p, os.path.join(d, zkey), os.path.join(d, wtns), exp, ab=False)
         with pytest.raises(kzp.KzpError):
             p.keep_ab(True)  # a and b live on different GPUs
@@ -595,7 +600,7 @@ def test_keyless_shape_full_size(gpu, kzp, oracle, ref, port, workdir):
     # the same proof sharded inside the call: domain 2^21 takes the fused-scatter chain
     for shards in (2, 4):
         with kzp.FullProver(z, devices=_group_devices(gpu, shards)) as p:
-            assert p.group_info() == (shards, True)
+            assert p.group_info() == (shards, True, True)
             js, _ = p.prove(w, r, s)
             assert js == rj and p.h_coefficients() == rh and p.msm_results() == rm
     pa, pb, pc = oracle.proof_from_json(js)
