@@ -11,9 +11,11 @@ tools/setupgen.c (the real keyless zkey cannot be downloaded offline). One "step
   value    proofs/s over all GPUs with the witness already resident in HBM (all kernels + result D2H + host assembly)
   e2e      the same through the reference-facing call FullProver.prove(wtns_path): file mapping, pinned staging,
            H2D of the witness, kernels, D2H, proof JSON — what prover-service would see
-  N > 1    replicas: independent proofs one per GPU, no data-path collective (scaling "weak"); additionally the
-           single-proof latency with the MSM base ranges split across the N GPUs and ONE NCCL all-gather of the
-           768-byte partials is reported as sharded_latency_ms_p50.
+  N > 1    replicas: independent proofs one per GPU, no data-path collective (scaling "weak"); additionally rank 0
+           times ONE proof sharded over all N GPUs inside the library call (kzp_prover_new_group: MSM base ranges
+           split, every coset-NTT chain spread over the GPUs with peer-store transposes over NVLink, partial sums on
+           the host; no Python and no collective library in the loop) while the other ranks idle:
+           sharded_latency_ms_p50 (witness resident) and sharded_e2e_ms_p50.
 
 Only the cpu_baseline leg and --impl reference touch oracle/ (they time the reference's own CPU prover,
 oracle/_ref, or the C port when that library is absent).
@@ -231,6 +233,19 @@ def run_reference_arm(args, zkey, wtns, info, rank):
 METRIC = "keyless Groth16 prove throughput (proofs/s); p50 latency (ms) in latency_ms_p50"
 
 
+def pct(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(round(q * (len(xs) - 1))))]
+
+
+def measured_traffic():
+    """DRAM bytes per launch from the committed ncu capture (scripts/ncu_traffic.sh -> profiles/r02_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception:
+        return None
+
+
 def workload_config(args, info):
     return {"workload": "%s-shaped synthetic circuit (trapdoor setup, tools/setupgen.c seed %d): nVars %d, nPublic %d, "
                         "%d constraints, domain 2^%d, nCoefs %d; witness ~84%% bits / ~12%% bytes / ~4%% full-width"
@@ -281,6 +296,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idle_group = dist.new_group(backend="gloo")  # a barrier that leaves the GPUs alone (NCCL's spins a kernel)
 
     def barrier():
         if distributed:
@@ -334,33 +350,47 @@ def main():
     t_begin = time.perf_counter()
     for _ in range(args.steps):
         t1 = time.perf_counter()
-        prover.prove(wtns)
+        last_proof, _ = prover.prove(wtns)
         e2e_ms.append(1e3 * (time.perf_counter() - t1))
     barrier()
     e2e_elapsed = time.perf_counter() - t_begin
     e2e_stage = prover.timings()
+    # a proof out of the timed loop is checked under the circuit's verifying key (host pairing check, no oracle)
+    proof_ok = kzp.host_verify(zkey, last_proof, [info["public_input"]])
+    if not proof_ok:
+        raise SystemExit("bench.py: a proof produced in the timed region does not verify")
 
-    # ---- sharded single proof (N > 1): MSM base ranges split, one all-gather of the partials ---------------
-    sharded_ms = None
+    # ---- sharded single proof (N > 1): one library call drives all N GPUs; the other ranks keep theirs idle ----
+    sharded = None
     if distributed:
-        sp = kzp.FullProver(zkey, device=local_rank, shard=(rank, world))
-        sp.upload_witness(values)
-        gather = [torch.empty(kzp.PARTIALS_BYTES, dtype=torch.uint8, device="cuda") for _ in range(world)]
-        lat = []
-        for it in range(args.warmup + args.steps):
-            barrier()
-            t1 = time.perf_counter()
-            sp.run_gpu()
-            mine = torch.frombuffer(bytearray(sp.partials()), dtype=torch.uint8).cuda()
-            dist.all_gather(gather, mine)
-            if rank == 0:
-                parts = [g.cpu().numpy().tobytes() for g in gather]
-                sp.assemble(parts)
-            torch.cuda.synchronize()
-            if it >= args.warmup:
-                lat.append(1e3 * (time.perf_counter() - t1))
-        sharded_ms = lat
-        sp.close()
+        barrier()
+        if rank == 0:
+            with kzp.FullProver(zkey, devices=list(range(world))) as sp:
+                shards, fused, dist_ntt = sp.group_info()
+                r32, s32 = (12345).to_bytes(32, "little"), (67890).to_bytes(32, "little")
+                want, _ = prover.prove(wtns, r32, s32)
+                got, _ = sp.prove(wtns, r32, s32)
+                sp.upload_witness(values)
+                for _ in range(args.warmup):
+                    sp.prove_resident()
+                lat, lat_e2e, shard_tm = [], [], []
+                for _ in range(max(args.steps, 10)):
+                    t1 = time.perf_counter()
+                    sp.prove_resident()
+                    lat.append(1e3 * (time.perf_counter() - t1))
+                    shard_tm.append([sp.shard_timings(k) for k in range(shards)])
+                for _ in range(max(args.steps, 10)):
+                    t1 = time.perf_counter()
+                    sp.prove(wtns)
+                    lat_e2e.append(1e3 * (time.perf_counter() - t1))
+                keys = ("spmv_ms", "ntt_ms", "msm_h_ms", "msm_wg1_ms", "msm_wg2_ms", "gpu_ms")
+                sharded = {"latency_ms_p50": statistics.median(lat), "latency_ms_p95": pct(lat, 0.95),
+                           "e2e_ms_p50": statistics.median(lat_e2e), "e2e_ms_p95": pct(lat_e2e, 0.95),
+                           "proof_equals_single_gpu": got == want, "shards": shards, "distributed_ntt": dist_ntt,
+                           "fused_peer_store_exchange": fused,
+                           "slowest_shard_stage_ms_median": {k: max(statistics.median(st[i][k] for st in shard_tm)
+                                                                    for i in range(shards)) for k in keys}}
+        dist.barrier(group=idle_group)
 
     # ---- reduce over ranks: max time ----------------------------------------------------------------------
     def max_over_ranks(x):
@@ -374,7 +404,6 @@ def main():
     e2e_elapsed = max_over_ranks(e2e_elapsed)
     p50 = max_over_ranks(statistics.median(step_ms))
     e2e_p50 = max_over_ranks(statistics.median(e2e_ms))
-    sharded_p50 = max_over_ranks(statistics.median(sharded_ms)) if sharded_ms else None
 
     if rank == 0:
         n = world if distributed else 1
@@ -391,14 +420,21 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tr = measured_traffic() if args.workload == "keyless" else None
+        acc_traffic = tr["h_accumulate"]["bytes_per_launch"] if tr else None
+        ntt_traffic = tr["ntt_chain"]["bytes_per_proof"] if tr else None
+        log_n = int(info["domain"]).bit_length() - 1
+        ntt_muls = 3 * (2 * (info["domain"] // 2) * log_n + info["domain"]) + 2 * info["domain"]  # butterflies + coset scale + pointwise
         line = {
             "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "latency_ms_p50": p50,
+            "latency_ms_p95": pct(step_ms, 0.95),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (254-bit modular integers, 8 x 32-bit Montgomery)", "data": "synthetic",
             "config": workload_config(args, info),
             "clocks": clocks,
             "e2e": {"value": n * args.steps / e2e_elapsed, "unit": "proofs/s", "latency_ms_p50": e2e_p50,
+                    "latency_ms_p95": pct(e2e_ms, 0.95), "proof_verifies": proof_ok,
                     "h2d_bytes_per_step": int(e2e_stage["h2d_mbytes"] * 1e6), "witness_bytes": prover.n_vars * 32, "d2h_bytes_per_step": kzp.PARTIALS_BYTES,
                     "api": "FullProver.prove(wtns_path) via kzp_prover_prove (C ABI): witness file -> classify + pack into pinned "
                            "memory -> H2D of the packed slices -> expansion kernel -> proof kernels -> D2H -> proof JSON", "h2d_ms": e2e_stage["h2d_ms"]},
@@ -416,28 +452,37 @@ def main():
                                "this run; IMAD.WIDE issues at half the 32-bit IMAD rate on sm_100a (profiles/r01_ubench_int_fp64_pipes.txt)",
                 "algorithmic_work": "%d sorted (point,bucket) entries x %d wide multiply-adds per mixed addition (6 products x 128 + 2 squarings x 100 + 1 dual product x 192)" % (entries, IMAD_PER_MIXED_ADD),
                 "launch_ms": acc_t,
-                "launch_note": "timed inside the proof with CUDA events on its stream, while the A/B1/C witness batch shares the "
-                               "SMs (it is scheduled into the H digit sort on purpose); alone the same launch takes 5.43 ms = "
-                               "0.90 of the peak (ncu, profiles/r01_ncu_full_s8.txt)",
-                "traffic": 4.467e9, "traffic_unit": "bytes per launch (dram__bytes_read.sum 4.428 GB + dram__bytes_write.sum 0.039 GB, ncu --set full, "
-                                                   "profiles/r01_ncu_full_s8.txt); algorithmic bytes = entries x (64 B point + 4 B entry) = %.2e; the 2x is the "
-                                                   "128-byte DRAM->L2 fill behind every random 64-byte point gather (DESIGN.md section 4)" % (entries * 68.0),
-                "hbm_view": {"achieved": 4.467e9 / (acc_t * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": 4.467e9 / (acc_t * 1e-3) / 1e9 / hbm_peak}},
+                "launch_note": "timed inside the proof with CUDA events on its stream, while the A/B1/C witness batch and B2 share "
+                               "the SMs (they are scheduled into the H digit sort and MSM on purpose); alone (ncu, serialised) the same "
+                               "launch is faster: profiles/r02_traffic.json ms_under_ncu",
+                "traffic": acc_traffic,
+                "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu "
+                                "capture profiles/r02_traffic.json (scripts/ncu_traffic.sh; null when that file is absent or the "
+                                "workload differs); algorithmic bytes = entries x (64 B point + 4 B entry) = %.2e: every random "
+                                "64-byte point gather costs a 128-byte DRAM->L2 fill (DESIGN.md section 4)" % (entries * 68.0),
+                "hbm_view": None if not acc_traffic else {"achieved": acc_traffic / (acc_t * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                                          "frac": acc_traffic / (acc_t * 1e-3) / 1e9 / hbm_peak}},
             "roofline_ntt": {
-                "kernel": "NTT stage kernels, 3 x (iNTT + coset + NTT) + pointwise, per proof",
+                "kernel": "NTT level kernels, 3 x (iNTT + coset + NTT) + pointwise, per proof",
                 "bound": "hbm", "achieved": ntt_bytes / (ntt_t * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ntt_bytes / (ntt_t * 1e-3) / 1e9 / hbm_peak,
-                "algorithmic_bytes": ntt_bytes, "launch_ms": ntt_t, "traffic": 2.149e9,
-                "traffic_unit": "bytes per proof, summed over the 5 NTT launches (ncu --set full, profiles/r01_ncu_full_s8.txt): "
+                "algorithmic_bytes": ntt_bytes, "launch_ms": ntt_t, "traffic": ntt_traffic,
+                "traffic_unit": "bytes per proof, summed over the NTT launches of one proof (profiles/r02_traffic.json): "
                                 "a 2^21 transform is 3 radix-128 passes (2.5 with the fused middle), each reading and writing a, b, c once",
+                "int_view": {"achieved": ntt_muls * IMAD_PER_FQ_MUL / (ntt_t * 1e-3) / 1e12, "peak": imad_peak / 1e12,
+                             "unit": "T wide-multiply-add/s", "frac": ntt_muls * IMAD_PER_FQ_MUL / (ntt_t * 1e-3) / imad_peak,
+                             "algorithmic_work": "%d Fr products (n/2 log n butterflies per transform x 6, coset scale, pointwise) x 128" % ntt_muls},
                 "note": "algorithmic bytes = 6 transforms x 2 x n x 32 B (SURVEY.md §8(d)); the binding roof for a 254-bit NTT "
-                        "on B200 is the integer pipe"},
+                        "on B200 is the integer pipe (int_view); launch_ms is the in-proof time, with the B2 MSM sharing the SMs"},
             "load_seconds": load_s,
         }
-        if sharded_p50 is not None:
-            line["sharded_latency_ms_p50"] = sharded_p50
-            line["sharded"] = "one proof, MSM base ranges split over %d GPUs, one NCCL all-gather of 768 B/rank" % n
+        if sharded is not None:
+            line["sharded_latency_ms_p50"] = sharded["latency_ms_p50"]
+            line["sharded_e2e_ms_p50"] = sharded["e2e_ms_p50"]
+            line["sharded"] = dict(sharded, what="ONE proof over %d GPUs inside kzp_prover_prove (prover group in libkzp_b200.so, "
+                                                 "driven by rank 0 alone while the other ranks idle): MSM base ranges split, coset-NTT "
+                                                 "chains spread over the GPUs with peer-store transposes over NVLink, 768-byte partials "
+                                                 "summed on the host" % n)
         if not args.no_cpu_baseline and n == 1:
             kind, cores, prove = cpu_reference_prover(zkey)
             prove(wtns)  # first call pages the key in

@@ -185,15 +185,82 @@ void fr_scale(Fr* x, uint64_t n, const Fr& k, cudaStream_t st)
     KZP_CUDA_CHECK(cudaGetLastError());
 }
 
+// persistent grid of the bulk-async kernels: what is resident at once (kNttMinCtas CTAs per SM)
+static unsigned int ntt_persistent_grid(uint32_t units)
+{
+    int dev = 0, sms = 0;
+    KZP_CUDA_CHECK(cudaGetDevice(&dev));
+    KZP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return std::min<unsigned int>(units, (unsigned int)(sms * kNttMinCtas));
+}
+
+// ---- tensor maps for the TMA-staged levels (ntt_tiled.cuh) ----------------------------------------------------------
+// cuTensorMapEncodeTiled is a host-side driver function (it only fills in the 128-byte descriptor); the library links
+// the runtime statically and does not link libcuda, so the entry point is looked up through the runtime.
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiledFn tensor_map_encoder()
+{
+    static TensorMapEncodeTiledFn fn = [] {
+        void*                            p = nullptr;
+        cudaDriverEntryPointQueryResult  q = cudaDriverEntryPointSymbolNotFound;
+        cudaError_t                      e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+        {
+            cudaGetLastError();
+            return (TensorMapEncodeTiledFn) nullptr;
+        }
+        return (TensorMapEncodeTiledFn)p;
+    }();
+    if (!fn)
+        throw CudaError("the CUDA driver does not export cuTensorMapEncodeTiled");
+    return fn;
+}
+
+// x as {2^lo * 4 words, 128 rows, 2^(k - lo - 7) uppers} of 8-byte words; box = one warp's two columns. DIT levels
+// traverse the rows with a stride of 8 (16 rows per copy, see k_ntt_level_tma).
+static void ntt_encode_map(CUtensorMap& m, Fr* x, uint32_t k, uint32_t lo, bool dit)
+{
+    const uint32_t hi         = lo + kNttTileBits;
+    cuuint64_t     gdim[3]    = {(cuuint64_t)4 << lo, 128, (cuuint64_t)1 << (k - hi)};
+    cuuint64_t     gstride[2] = {(cuuint64_t)32 << lo, (cuuint64_t)32 << hi};
+    cuuint32_t     box[3]     = {8, 128, 1};
+    cuuint32_t     estr[3]    = {1, dit ? 8u : 1u, 1};
+    CUresult       r = tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, x, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        throw CudaError("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r) + " (k " + std::to_string(k) + ", lo " +
+                        std::to_string(lo) + ")");
+}
+
 static void ntt_level_attrs()
 {
     // per device; cheap enough to repeat
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
-    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
-    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttLevelSmem));
-    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_mid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttMidSmem));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_mid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttMidSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_mid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttMidSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttTmaSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttTmaSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttTmaSmem));
+    KZP_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_level_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttTmaSmem));
+}
+
+// One TMA-staged level (lo >= 1) over `count` vectors; n_tiles = tiles of 16 columns this launch covers per vector.
+template <bool DIT, bool ROUTED>
+static void ntt_launch_level(const NttBatch& b, int count, const Fr* tw, uint32_t k, uint32_t lo, uint32_t plo, const NttRoute& rt,
+                             uint32_t n_tiles, cudaStream_t st)
+{
+    NttMaps maps;
+    for (int i = 0; i < kNttMaxBatch; i++)
+        if (i < count)
+            ntt_encode_map(maps.m[i], b.x[i], k, lo, DIT);
+        else
+            maps.m[i] = maps.m[0];
+    k_ntt_level_tma<DIT, ROUTED><<<ntt_persistent_grid(n_tiles * (uint32_t)count), kNttThreads, kNttTmaSmem, st>>>(maps, b, tw, k, lo, plo, rt,
+                                                                                                                  n_tiles, (uint32_t)count);
+    KZP_CUDA_CHECK(cudaGetLastError());
 }
 
 static NttBatch ntt_batch1(Fr* x)
@@ -236,8 +303,13 @@ void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st)
         while (hi >= (uint32_t)kNttTileBits)
         {
             uint32_t lo = hi - kNttTileBits;
-            k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_inv, log_n, lo, 0, lo == 0 ? post : nullptr, NttRoute());
-            KZP_CUDA_CHECK(cudaGetLastError());
+            if (lo == 0) // one-element columns: two adjacent columns are not adjacent in memory, plain loads
+            {
+                k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_inv, log_n, lo, 0, post, NttRoute());
+                KZP_CUDA_CHECK(cudaGetLastError());
+            }
+            else
+                ntt_launch_level<false, false>(ntt_batch1(x), 1, d.tw_inv, log_n, lo, 0, NttRoute(), grid, st);
             hi = lo;
         }
         if (hi == 0)
@@ -271,8 +343,13 @@ void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st)
     uint32_t     plo   = 0;
     for (uint32_t lo = r; lo + kNttTileBits <= log_n; lo += kNttTileBits)
     {
-        k_ntt_level<true><<<lgrid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_fwd, log_n, lo, plo, nullptr, NttRoute());
-        KZP_CUDA_CHECK(cudaGetLastError());
+        if (lo == 0)
+        {
+            k_ntt_level<true><<<lgrid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_fwd, log_n, lo, plo, nullptr, NttRoute());
+            KZP_CUDA_CHECK(cudaGetLastError());
+        }
+        else
+            ntt_launch_level<true, false>(ntt_batch1(x), 1, d.tw_fwd, log_n, lo, plo, NttRoute(), lgrid, st);
         plo = lo;
     }
 }
@@ -305,21 +382,20 @@ uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStrea
     uint32_t launches = 0;
     for (uint32_t lo = log_n - kNttTileBits; lo > 0; lo -= kNttTileBits)
     {
-        k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, nullptr, NttRoute());
-        KZP_CUDA_CHECK(cudaGetLastError());
+        ntt_launch_level<false, false>(b, count, d.tw_inv, log_n, lo, 0, NttRoute(), grid.x, st);
         launches++;
     }
-    k_ntt_mid<false><<<grid, kNttThreads, kNttMidSmem, st>>>(b, d.tw_inv, d.tw_fwd, log_n, d.coset_br, NttRoute());
+    k_ntt_mid<false><<<ntt_persistent_grid(grid.x * (uint32_t)count), kNttThreads, kNttMidSmem, st>>>(b, d.tw_inv, d.tw_fwd, log_n, d.coset_br,
+                                                                                                     NttRoute(), grid.x, (uint32_t)count);
     KZP_CUDA_CHECK(cudaGetLastError());
     launches++;
     uint32_t plo = 0;
     for (uint32_t lo = kNttTileBits; lo + kNttTileBits <= log_n; lo += kNttTileBits)
     {
         if (last_store && lo + kNttTileBits == log_n)
-            k_ntt_level<true, true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, *last_store);
+            ntt_launch_level<true, true>(b, count, d.tw_fwd, log_n, lo, plo, *last_store, grid.x, st);
         else
-            k_ntt_level<true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, NttRoute());
-        KZP_CUDA_CHECK(cudaGetLastError());
+            ntt_launch_level<true, false>(b, count, d.tw_fwd, log_n, lo, plo, NttRoute(), grid.x, st);
         plo = lo;
         launches++;
     }
@@ -363,16 +439,16 @@ uint32_t ntt_coset_chain_phase(const NttDomain& d, Fr* const* xs, int count, cud
         for (uint32_t lo = log_n - kNttTileBits; lo > 0; lo -= kNttTileBits)
         {
             if (lo == (uint32_t)kNttTileBits)
-                k_ntt_level<false, true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, nullptr, low_to_top);
+                ntt_launch_level<false, true>(b, count, d.tw_inv, log_n, lo, 0, low_to_top, grid.x, st);
             else
-                k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, nullptr, low);
-            KZP_CUDA_CHECK(cudaGetLastError());
+                ntt_launch_level<false, false>(b, count, d.tw_inv, log_n, lo, 0, low, grid.x, st);
             launches++;
         }
     }
     else if (phase == 1)
     {
-        k_ntt_mid<true><<<grid, kNttThreads, kNttMidSmem, st>>>(b, d.tw_inv, d.tw_fwd, log_n, d.coset_br, top_to_low);
+        k_ntt_mid<true><<<ntt_persistent_grid(grid.x * (uint32_t)count), kNttThreads, kNttMidSmem, st>>>(b, d.tw_inv, d.tw_fwd, log_n, d.coset_br,
+                                                                                                        top_to_low, grid.x, (uint32_t)count);
         KZP_CUDA_CHECK(cudaGetLastError());
         launches++;
     }
@@ -382,10 +458,9 @@ uint32_t ntt_coset_chain_phase(const NttDomain& d, Fr* const* xs, int count, cud
         for (uint32_t lo = kNttTileBits; lo + kNttTileBits <= log_n; lo += kNttTileBits)
         {
             if (lo + kNttTileBits == log_n)
-                k_ntt_level<true, true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, low_to_top);
+                ntt_launch_level<true, true>(b, count, d.tw_fwd, log_n, lo, plo, low_to_top, grid.x, st);
             else
-                k_ntt_level<true><<<grid, kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, low);
-            KZP_CUDA_CHECK(cudaGetLastError());
+                ntt_launch_level<true, false>(b, count, d.tw_fwd, log_n, lo, plo, low, grid.x, st);
             plo = lo;
             launches++;
         }

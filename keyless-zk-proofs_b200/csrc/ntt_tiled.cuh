@@ -26,6 +26,8 @@
 // Replaces FFT<Fr>::fft / ifft (rust-rapidsnark/rapidsnark/src/fft.cpp:192-246) together with kernels.cu.
 #pragma once
 
+#include <cuda.h> // CUtensorMap (the type only: the encoder is looked up in the driver at run time)
+
 #include "device.hpp"
 
 namespace kzp
@@ -91,6 +93,58 @@ __device__ __forceinline__ void ntt_root(Fr& r, const Fr* __restrict__ tw, uint3
     }
 }
 
+// ---- bulk-async staging (sm_90+ async proxy: cp.async.bulk / TMA completing on an mbarrier) ------------------------
+// A warp's next tile is fetched into its own shared-memory buffer by the copy engine while the warp is still in the
+// arithmetic of the current one: one elected lane arms the warp's mbarrier with the byte count and issues the copy,
+// all lanes wait on the barrier's phase before the first round reads. No registers, no LSU issue slots, no address
+// arithmetic are spent on the loads, and their latency sits under the last round's products and stores.
+__device__ __forceinline__ uint32_t ntt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ntt_mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ntt_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ntt_mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void ntt_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ntt_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ntt_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done, addr = ntt_smem_u32(bar), spins = 0;
+    do
+    {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+        if (!done && ++spins > (1u << 24)) // a copy that never lands (bad descriptor) must fail the launch, not hang the GPU
+            asm volatile("trap;");
+    } while (!done);
+}
+// generic-proxy accesses of this thread to shared memory are ordered before later async-proxy (copy engine) accesses
+__device__ __forceinline__ void ntt_fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// contiguous global -> shared copy by the copy engine (SASS: UBLKCP); bytes and both addresses multiples of 16
+__device__ __forceinline__ void ntt_bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ntt_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(ntt_smem_u32(bar))
+                 : "memory");
+}
+
+// 3-D tiled tensor copy global -> shared through a tensor map (SASS: UTMALDG); coordinates innermost first
+__device__ __forceinline__ void ntt_tma_load_3d(void* dst_smem, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     ntt_smem_u32(dst_smem)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(ntt_smem_u32(bar))
+                 : "memory");
+}
+
 // One butterfly stage on v[0..7]: pairs (q, q | 1 << B) for the q with bit B clear. The twiddle of pair q is
 // w_128^idx with idx = (j0 + ((q & mask) << qsh)) << ish where mask = (1 << B) - 1, i.e. j = row mod half-distance.
 // DIF: (a, b) -> (a + b, (a - b) w);  DIT: (a, b) -> (a + w b, a - w b).  KNOWN0: j0 == 0 at compile time, so
@@ -136,8 +190,16 @@ __device__ __forceinline__ uint32_t ntt_row1(uint32_t g, uint32_t q) { return g 
 __device__ __forceinline__ uint32_t ntt_row2(uint32_t g, uint32_t q) { return 32u * (g >> 2) + (g & 3u) + 4u * q; }
 __device__ __forceinline__ uint32_t ntt_row3(uint32_t g, uint32_t q) { return 8u * g + q; }
 
-// The three rounds of a 128-point DIF (R1, R2, R3) between registers: in: rows of R1, out: rows of R3.
-__device__ __forceinline__ void ntt_dif_rounds(Fr (&v)[8], uint4* wsm, const uint4* twp, uint32_t g, uint32_t e)
+struct NttNoHook
+{
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// The three rounds of a 128-point DIF (R1, R2, R3) between registers: in: rows of R1, out: rows of R3. smem_free() runs
+// once the warp's shared-memory buffer is no longer needed (before the last round's products): the place to start the
+// next prefetch.
+template <class Hook = NttNoHook>
+__device__ __forceinline__ void ntt_dif_rounds(Fr (&v)[8], uint4* wsm, const uint4* twp, uint32_t g, uint32_t e, Hook smem_free = Hook())
 {
     // R1: half-distance 64 (q bit 2; j = g + 16 (q & 3)), 32 (q bit 1; j = g + 16 (q & 1), index j * 2)
     ntt_stage<false, 2, false>(v, twp, g, 4, 0);
@@ -161,14 +223,17 @@ __device__ __forceinline__ void ntt_dif_rounds(Fr (&v)[8], uint4* wsm, const uin
     for (int q = 0; q < 8; q++)
         ntt_sm_load(wsm, ntt_row3(g, q), e, v[q]);
     __syncwarp();
+    smem_free();
     // R3: half-distance 4 (j = q & 3, index j * 16), 2 (j = q & 1, index j * 32), 1 (no twiddle)
     ntt_stage<false, 2, true>(v, twp, 0, 0, 4);
     ntt_stage<false, 1, true>(v, twp, 0, 0, 5);
     ntt_stage<false, 0, true>(v, twp, 0, 0, 6);
 }
 
-// The three rounds of a 128-point DIT (R3, R2, R1): in: rows of R3, out: rows of R1.
-__device__ __forceinline__ void ntt_dit_rounds(Fr (&v)[8], uint4* wsm, const uint4* twp, uint32_t g, uint32_t e)
+// The three rounds of a 128-point DIT (R3, R2, R1): in: rows of R3, out: rows of R1. smem_free() runs once the warp's
+// shared-memory buffer is no longer needed (before the last round's products): the place to start the next prefetch.
+template <class Hook = NttNoHook>
+__device__ __forceinline__ void ntt_dit_rounds(Fr (&v)[8], uint4* wsm, const uint4* twp, uint32_t g, uint32_t e, Hook smem_free = Hook())
 {
     ntt_stage<true, 0, true>(v, twp, 0, 0, 6);
     ntt_stage<true, 1, true>(v, twp, 0, 0, 5);
@@ -191,18 +256,18 @@ __device__ __forceinline__ void ntt_dit_rounds(Fr (&v)[8], uint4* wsm, const uin
     for (int q = 0; q < 8; q++)
         ntt_sm_load(wsm, ntt_row1(g, q), e, v[q]);
     __syncwarp();
+    smem_free();
     ntt_stage<true, 1, false>(v, twp, g, 4, 1);
     ntt_stage<true, 2, false>(v, twp, g, 4, 0);
 }
 
 constexpr size_t kNttWarpSmem  = 2 * 256 * sizeof(uint4);                                   // two planes of 256 slots
 constexpr size_t kNttLevelSmem = (kNttThreads / 32) * kNttWarpSmem + 2 * 64 * sizeof(uint4); // + one twiddle table
-constexpr size_t kNttMidSmem   = (kNttThreads / 32) * kNttWarpSmem + 4 * 64 * sizeof(uint4); // + two twiddle tables
+constexpr size_t kNttMidSmem   = (kNttThreads / 32) * kNttWarpSmem + 4 * 64 * sizeof(uint4) + (kNttThreads / 32) * sizeof(uint64_t); // + two twiddle tables + one mbarrier per warp
 
 // Tile index of this CTA under the route's block partition (device.hpp NttRoute).
-__device__ __forceinline__ uint32_t ntt_route_block(const NttRoute& rt)
+__device__ __forceinline__ uint32_t ntt_route_block(const NttRoute& rt, uint32_t b, uint32_t n_tiles)
 {
-    uint32_t b = blockIdx.x;
     if (rt.blocks == kNttBlocksLow)
     {
         // column index bits [7-k, 7) = tile index bits [3-k, 3) (a tile is 16 columns): insert g there
@@ -210,13 +275,13 @@ __device__ __forceinline__ uint32_t ntt_route_block(const NttRoute& rt)
         return ((b >> low) << (7 - kNttColBits)) | (rt.g << low) | (b & ((1u << low) - 1u));
     }
     if (rt.blocks == kNttBlocksTop)
-        return rt.g * gridDim.x + b;
+        return rt.g * n_tiles + b;
     return b;
 }
 
 // Destination of position pos of vector blockIdx.y under the route's store mode
 template <bool ROUTED>
-__device__ __forceinline__ Fr* ntt_route_dst(const NttRoute& rt, Fr* local, uint32_t pos)
+__device__ __forceinline__ Fr* ntt_route_dst(const NttRoute& rt, Fr* local, uint32_t pos, uint32_t vec)
 {
     if (!ROUTED)
         return local + pos;
@@ -226,7 +291,7 @@ __device__ __forceinline__ Fr* ntt_route_dst(const NttRoute& rt, Fr* local, uint
     else
         while (r + 1 < rt.world && pos >= rt.bound[r + 1])
             r++;
-    return rt.dst[blockIdx.y][r] + pos;
+    return rt.dst[vec][r] + pos;
 }
 
 // One level on bits [lo, lo+7) of a size-2^k transform. tw: w^i (forward) or w^-i (inverse), i < 2^(k-1).
@@ -248,7 +313,7 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
     __syncthreads();
 
     const uint32_t e = lane >> 4, g = lane & 15u;
-    const uint32_t rest     = ntt_route_block(rt) * kNttTileCols + 2u * warp + e;
+    const uint32_t rest     = ntt_route_block(rt, blockIdx.x, gridDim.x) * kNttTileCols + 2u * warp + e;
     const uint32_t low_mask = (1u << lo) - 1u;
     const uint32_t col_base = ((rest >> lo) << hi) | (rest & low_mask); // position of row 0 of this column
     Fr             v[8];
@@ -276,7 +341,7 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
             }
             if (post)
                 Fr::mul(v[q], v[q], post[pos]);
-            *ntt_route_dst<ROUTED>(rt, x, pos) = v[q];
+            *ntt_route_dst<ROUTED>(rt, x, pos, blockIdx.y) = v[q];
         }
     }
     else
@@ -303,7 +368,148 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
         ntt_dit_rounds(v, wsm, twp, g, e);
 #pragma unroll
         for (int q = 0; q < 8; q++)
-            *ntt_route_dst<ROUTED>(rt, x, col_base | (ntt_row1(g, q) << lo)) = v[q];
+            *ntt_route_dst<ROUTED>(rt, x, col_base | (ntt_row1(g, q) << lo), blockIdx.y) = v[q];
+    }
+}
+
+// ---- levels with lo >= 1: persistent warps, tiles staged by TMA -----------------------------------------------------
+// The vector is described to the copy engine as a 3-D tensor of 8-byte words (NttMaps, kernels.cu):
+//     dim 0 = 2^lo * 4 words (the contiguous low part of the position), dim 1 = 128 rows t (stride 2^lo elements),
+//     dim 2 = the upper part of the position (stride 2^hi elements), 64-byte swizzle.
+// A warp's two columns are the box {8 words, 128 rows, 1}: 128 rows of 64 bytes, 8 KiB, one tensor copy (DIF). The
+// first round wants lane g to hold rows g + 16 q (DIF) or 8 g + q (DIT); so that the lanes of a quarter-warp always
+// read CONSECUTIVE 64-byte rows of the landed image (with the 64-byte swizzle: eight different bank groups), the DIT
+// kernel fetches the tile as eight copies of 16 rows each with a traversal stride of 8 rows (elementStrides), copy q
+// landing at q * 1 KiB: in both cases virtual row g + 16 q of the image is the element the lane needs as v[q].
+struct alignas(64) NttMaps
+{
+    CUtensorMap m[kNttMaxBatch];
+};
+
+// v[q] <- element (virtual row g + 16 q, column e) of a landed tile (64-byte rows, 64-byte swizzle: the 16-byte chunk
+// index is XORed with bits 1..2 of the row)
+__device__ __forceinline__ void ntt_landed_load(const uint4* wsm, uint32_t g, uint32_t e, Fr (&v)[8])
+{
+    const uint32_t sw = (g >> 1) & 3u; // (row >> 1) & 3 with row = g + 16 q
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+    {
+        const uint4* row = wsm + (g + 16u * q) * 4u;
+        uint4        lo = row[(2u * e) ^ sw], hi = row[(2u * e + 1u) ^ sw];
+        v[q].v[0] = lo.x; v[q].v[1] = lo.y; v[q].v[2] = lo.z; v[q].v[3] = lo.w;
+        v[q].v[4] = hi.x; v[q].v[5] = hi.y; v[q].v[6] = hi.z; v[q].v[7] = hi.w;
+    }
+}
+
+constexpr size_t kNttTmaSmem = kNttLevelSmem + (kNttThreads / 32) * sizeof(uint64_t); // + one mbarrier per warp
+
+// One level on bits [lo, lo+7), lo >= 1. Work unit u < n_tiles * count: vector u % count, tile u / count (16 columns).
+template <bool DIT, bool ROUTED = false>
+__global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
+    k_ntt_level_tma(const __grid_constant__ NttMaps maps, NttBatch batch, const Fr* __restrict__ tw, uint32_t k, uint32_t lo, uint32_t plo,
+                    const NttRoute rt, uint32_t n_tiles, uint32_t count)
+{
+    extern __shared__ __align__(1024) uint4 ntt_smem[];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint4*         wsm = ntt_smem + warp * (kNttWarpSmem / sizeof(uint4));
+    uint4*         twp = ntt_smem + (kNttThreads / 32) * (kNttWarpSmem / sizeof(uint4));
+    uint64_t*      bar = reinterpret_cast<uint64_t*>(twp + 128) + warp;
+    const uint32_t hi  = lo + kNttTileBits;
+    if (tid < 64)
+        ntt_tw_fill(twp, tw, tid, k);
+    if (lane == 0)
+    {
+        ntt_mbar_init(bar, 1);
+        ntt_mbar_init_fence();
+    }
+    __syncthreads();
+
+    const uint32_t e = lane >> 4, g = lane & 15u;
+    const uint32_t low_mask = (1u << lo) - 1u;
+    const uint32_t units    = n_tiles * count;
+    // column index of the warp's first column in work unit u
+    auto pair_rest = [&](uint32_t u) { return ntt_route_block(rt, u / count, n_tiles) * kNttTileCols + 2u * warp; };
+    auto prefetch  = [&](uint32_t u) {
+        const uint32_t     rest = pair_rest(u);
+        const CUtensorMap* map  = &maps.m[u % count];
+        const uint32_t     c0 = (rest & low_mask) * 4u, c2 = rest >> lo;
+        if (lane == 0)
+            ntt_mbar_expect_tx(bar, (uint32_t)kNttWarpSmem);
+        if (!DIT)
+        {
+            if (lane == 0)
+                ntt_tma_load_3d(wsm, map, c0, 0, c2, bar);
+        }
+        else
+        {
+            __syncwarp();
+            if (lane < 8)
+                ntt_tma_load_3d(wsm + lane * 64u, map, c0, lane, c2, bar); // rows lane, lane + 8, ..., lane + 120
+        }
+    };
+    uint32_t u = blockIdx.x, parity = 0;
+    if (u < units)
+        prefetch(u);
+    for (; u < units; u += gridDim.x)
+    {
+        Fr* __restrict__ x        = batch.x[u % count];
+        const uint32_t   rest     = pair_rest(u) + e;
+        const uint32_t   col_base = ((rest >> lo) << hi) | (rest & low_mask); // position of row 0 of this column
+        const uint32_t   next     = u + gridDim.x;
+        auto             smem_free = [&] {
+            if (next < units)
+            {
+                ntt_fence_async_proxy(); // this lane's generic-proxy accesses to the buffer, before the copy engine's
+                __syncwarp();
+                prefetch(next);
+            }
+        };
+        ntt_mbar_wait(bar, parity);
+        parity ^= 1u;
+        Fr v[8];
+        ntt_landed_load(wsm, g, e, v);
+        __syncwarp(); // every lane has its rows before the rounds start to exchange through the same buffer
+        if (!DIT)
+        {
+            ntt_dif_rounds(v, wsm, twp, g, e, smem_free);
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+            {
+                uint32_t t   = ntt_row3(g, q);
+                uint32_t pos = col_base | (t << lo);
+                uint32_t m   = pos & low_mask;
+                uint32_t ex  = (m * (__brev(t) >> 25)) << (k - hi);
+                if (ex != 0)
+                {
+                    Fr w;
+                    ntt_root(w, tw, ex, k);
+                    Fr::mul(v[q], v[q], w);
+                }
+                *ntt_route_dst<ROUTED>(rt, x, pos, u % count) = v[q];
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+            {
+                uint32_t pos   = col_base | (ntt_row3(g, q) << lo);
+                uint32_t upper = pos >> lo;
+                uint32_t brv   = __brev(upper) >> (32 - (k - lo));
+                uint32_t kt    = (pos >> plo) & ((1u << (lo - plo)) - 1u);
+                uint32_t ex    = (brv * kt) << plo;
+                if (ex != 0)
+                {
+                    Fr w;
+                    ntt_root(w, tw, ex, k);
+                    Fr::mul(v[q], v[q], w);
+                }
+            }
+            ntt_dit_rounds(v, wsm, twp, g, e, smem_free);
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                *ntt_route_dst<ROUTED>(rt, x, col_base | (ntt_row1(g, q) << lo), u % count) = v[q];
+        }
     }
 }
 
@@ -312,38 +518,87 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
 // warp runs the DIF rounds, multiplies by post[pos] (= w_2n^bitrev(pos) / n: ifft scaling + coset shift) and
 // continues with the DIT rounds. R3 is the last DIF round and the first DIT round, so the hand-over happens in
 // registers. Saves one full read + write of the vector and a shared-memory pass per chain.
+// Persistent warps with bulk-async staging: a warp's two columns are 8 KiB of CONTIGUOUS global memory, fetched by one
+// cp.async.bulk into the warp's shared-memory buffer (the same buffer the rounds exchange through: it is free again
+// once the last round's rows are in registers, which is when the copy for the warp's next tile is issued).
+// Work unit u < n_tiles * count: vector u % count, tile u / count; CTA c takes u = c, c + gridDim.x, ...
 template <bool ROUTED = false>
 __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
     k_ntt_mid(NttBatch batch, const Fr* __restrict__ tw_inv, const Fr* __restrict__ tw_fwd, uint32_t k,
-              const Fr* __restrict__ post, const NttRoute rt)
+              const Fr* __restrict__ post, const NttRoute rt, uint32_t n_tiles, uint32_t count)
 {
-    Fr* __restrict__        x = batch.x[blockIdx.y];
     extern __shared__ uint4 ntt_smem[];
     const uint32_t          tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint4*                  wsm = ntt_smem + warp * (kNttWarpSmem / sizeof(uint4));
     uint4*                  twI = ntt_smem + (kNttThreads / 32) * (kNttWarpSmem / sizeof(uint4));
     uint4*                  twF = twI + 128;
+    uint64_t*               bar = reinterpret_cast<uint64_t*>(twF + 128) + warp;
     if (tid < 64)
         ntt_tw_fill(twI, tw_inv, tid, k);
     else if (tid < 128)
         ntt_tw_fill(twF, tw_fwd, tid - 64, k);
+    if (lane == 0)
+    {
+        ntt_mbar_init(bar, 1);
+        ntt_mbar_init_fence();
+    }
     __syncthreads();
     const uint32_t e = lane >> 4, g = lane & 15u;
-    const uint32_t col_base = (ntt_route_block(rt) * kNttTileCols + 2u * warp + e) << kNttTileBits; // 128 contiguous elements
-    Fr             v[8];
+    const uint32_t units = n_tiles * count;
+    // first element of this warp's column pair in work unit u
+    auto pair_base = [&](uint32_t u) { return (ntt_route_block(rt, u / count, n_tiles) * kNttTileCols + 2u * warp) << kNttTileBits; };
+    auto prefetch  = [&](uint32_t u) {
+        if (lane == 0)
+        {
+            ntt_mbar_expect_tx(bar, (uint32_t)kNttWarpSmem);
+            ntt_bulk_load(wsm, batch.x[u % count] + pair_base(u), (uint32_t)kNttWarpSmem, bar);
+        }
+    };
+    uint32_t u = blockIdx.x, parity = 0;
+    if (u < units)
+        prefetch(u);
+    for (; u < units; u += gridDim.x)
+    {
+        Fr* __restrict__ x        = batch.x[u % count];
+        const uint32_t   col_base = pair_base(u) + (e << kNttTileBits); // 128 contiguous elements
+        ntt_mbar_wait(bar, parity);
+        parity ^= 1u;
+        Fr v[8];
+        {
+            // landed layout: element (column e, row t) at 16-byte slot e * 256 + 2 t (+1). Quarter-warps read rows
+            // t, t + 1, .. t + 7: lanes 4..7 take the upper half first, so that the eight 16-byte accesses of one
+            // instruction fall into eight different bank groups.
+            const uint32_t h = (g >> 2) & 1u;
 #pragma unroll
-    for (int q = 0; q < 8; q++)
-        v[q] = x[col_base + ntt_row1(g, q)];
-    ntt_dif_rounds(v, wsm, twI, g, e);
-    const Fr* pp = post + col_base + ntt_row3(g, 0);
+            for (int q = 0; q < 8; q++)
+            {
+                const uint4* src = wsm + e * 256u + 2u * ntt_row1(g, q);
+                uint4        a = src[h], b = src[h ^ 1u];
+                uint4        lo = h ? b : a, hi = h ? a : b;
+                v[q].v[0] = lo.x; v[q].v[1] = lo.y; v[q].v[2] = lo.z; v[q].v[3] = lo.w;
+                v[q].v[4] = hi.x; v[q].v[5] = hi.y; v[q].v[6] = hi.z; v[q].v[7] = hi.w;
+            }
+        }
+        __syncwarp(); // every lane has its rows before the rounds start to exchange through the same buffer
+        ntt_dif_rounds(v, wsm, twI, g, e);
+        const Fr* pp = post + col_base + ntt_row3(g, 0);
 #pragma unroll
-    for (int q = 0; q < 8; q++)
-        Fr::mul(v[q], v[q], pp[q]);
-    __syncwarp();
-    ntt_dit_rounds(v, wsm, twF, g, e);
+        for (int q = 0; q < 8; q++)
+            Fr::mul(v[q], v[q], pp[q]);
+        __syncwarp();
+        const uint32_t next = u + gridDim.x;
+        ntt_dit_rounds(v, wsm, twF, g, e, [&] {
+            if (next < units)
+            {
+                ntt_fence_async_proxy(); // this lane's generic-proxy accesses to the buffer, before the copy engine's
+                __syncwarp();
+                prefetch(next);
+            }
+        });
 #pragma unroll
-    for (int q = 0; q < 8; q++)
-        *ntt_route_dst<ROUTED>(rt, x, col_base + ntt_row1(g, q)) = v[q];
+        for (int q = 0; q < 8; q++)
+            *ntt_route_dst<ROUTED>(rt, x, col_base + ntt_row1(g, q), u % count) = v[q];
+    }
 }
 
 } // namespace kzp

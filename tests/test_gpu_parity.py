@@ -568,7 +568,7 @@ int main(int argc, char** argv) {
     link = [kzp.LIB_PATH, "-Wl,-rpath," + os.path.dirname(kzp.LIB_PATH)]
     rel, hooked = os.path.join(workdir, "abi_run"), os.path.join(workdir, "abi_run_hooked")
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", inc, src, "-o", rel] + link)
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-DKZP_TEST_HOOKS", "-I", inc, src, "-x", "c++", shim, "-o", hooked] + link)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-DKZP_TEST_HOOKS", "-I", inc, src, "-x", "c++", shim, "-x", "none", "-o", hooked] + link)
     env = dict(os.environ, KZP_FIXED_RS=exp["r"] + exp["s"])
     args = [os.path.join(toy, "toy_1.zkey"), os.path.join(toy, "toy.wtns")]
     state, rtype, err, js = subprocess.check_output([hooked] + args, text=True, env=env).strip().split(" ", 3)
