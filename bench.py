@@ -37,7 +37,13 @@ WORKLOADS = {
     # name: (n_constraints, n_vars, seed)  — SURVEY.md §8(d) configs 2 and 1
     "keyless": (1376867, 1343588, 2),
     "small": (60000, 58000, 1),
+    # the keyless shape with a pessimistic witness: ~30 % full-width field elements instead of ~4 % (bounds the
+    # distribution assumption of the headline workload; the witness-side MSMs and the packed upload both grow)
+    "keyless-wide": (1376867, 1343588, 2),
 }
+# gate mix per workload (tools/setupgen.c kzp_setupgen_set_mix) and what the resulting witness looks like
+MIXES = {"keyless-wide": ((35, 55, 70), "~56% bits / ~14% bytes / ~30% full-width")}
+DEFAULT_MIX = ((50, 80, 95), "~84% bits / ~12% bytes / ~4% full-width")
 # XYZZ madd-2008-s in G1 (curve.cpp:203-249) is 8M + 2S. As issued by csrc/ec.cuh + csrc/ff.cuh: 6 products of 128 wide
 # (32x32+64) multiply-adds, 2 dedicated squarings of 100 (28 off-diagonal + 8 diagonal + 64 reduction) and one dual
 # product (Q - x3) R + (-y1) PPP with a single reduction, 192. The 8 low IMADs per reduction (m) are not counted.
@@ -104,7 +110,9 @@ def ensure_inputs(workload):
     t0 = time.time()
     lib = ensure_setupgen()
     arr = (ctypes.c_uint64 * 8)()
+    assert lib.kzp_setupgen_set_mix(*MIXES.get(workload, DEFAULT_MIX)[0]) == 0
     rc = lib.kzp_setupgen(nc, nv, seed, (zkey + ".tmp").encode(), (wtns + ".tmp").encode(), arr, None)
+    lib.kzp_setupgen_set_mix(*DEFAULT_MIX[0])
     if rc != 0:
         raise RuntimeError("setup generation failed")
     os.replace(zkey + ".tmp", zkey)
@@ -248,9 +256,9 @@ def measured_traffic():
 
 def workload_config(args, info):
     return {"workload": "%s-shaped synthetic circuit (trapdoor setup, tools/setupgen.c seed %d): nVars %d, nPublic %d, "
-                        "%d constraints, domain 2^%d, nCoefs %d; witness ~84%% bits / ~12%% bytes / ~4%% full-width"
+                        "%d constraints, domain 2^%d, nCoefs %d; witness %s"
                         % (args.workload, info["seed"], info["n_vars"], info["n_public"], info["n_constraints"],
-                           int(info["domain"]).bit_length() - 1, info["n_coefs"]),
+                           int(info["domain"]).bit_length() - 1, info["n_coefs"], MIXES.get(args.workload, DEFAULT_MIX)[1]),
             "proofs_per_step_per_gpu": 1, "parallelism": "replicas x%d (one proof per GPU)" % args.gpus,
             "l2": "working set (multi-GB resident key tables, 4 x %d MiB vectors) exceeds the 126 MB L2; no flush needed"
                   % (info["domain"] * 32 >> 20)}

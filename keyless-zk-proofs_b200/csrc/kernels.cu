@@ -7,6 +7,7 @@
 //   h_pointwise     groth16.cpp:266-275      msm_run      multiexp.cpp:183-245 (+ curve.cpp group law)
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -185,9 +186,19 @@ void fr_scale(Fr* x, uint64_t n, const Fr& k, cudaStream_t st)
     KZP_CUDA_CHECK(cudaGetLastError());
 }
 
-// persistent grid of the bulk-async kernels: what is resident at once (kNttMinCtas CTAs per SM)
+// Grid of the copy-engine-staged NTT kernels. Default: one work unit (16 columns of one vector) per CTA. With
+// KZP_NTT_PERSIST=1 the grid is what is resident at once (kNttMinCtas CTAs per SM) and every warp loops over its tiles,
+// prefetching the next one under the last round of the current one. Measured on B200 (2^21, a, b, c batched, ncu
+// durations of the five launches of a chain): persistent 3.02 ms, persistent + one CTA barrier per tile 2.79 ms, one
+// unit per CTA 2.49 ms (plain LDG loads before the copy engine was used: 2.53 ms). The unrolled rounds are 160-370 KB of
+// code; warps of a persistent CTA drift apart over its tiles and evict one another's instructions (no-instruction
+// stalls 1.0-3.7 cycles per issue against 0.15-0.8, profiles/r02_ncu_ntt_persistent.txt), which costs more than the
+// prefetch hides — these kernels are bound by the integer pipe and issue slots, not by load latency.
 static unsigned int ntt_persistent_grid(uint32_t units)
 {
+    static const int persist = getenv("KZP_NTT_PERSIST") ? atoi(getenv("KZP_NTT_PERSIST")) : 0;
+    if (!persist)
+        return units;
     int dev = 0, sms = 0;
     KZP_CUDA_CHECK(cudaGetDevice(&dev));
     KZP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

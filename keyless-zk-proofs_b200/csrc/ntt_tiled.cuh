@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
                 prefetch(next);
             }
         };
+        __syncthreads(); // keeps the CTA's warps on the same stretch of the (large, unrolled) code: see k_ntt_mid
         ntt_mbar_wait(bar, parity);
         parity ^= 1u;
         Fr v[8];
@@ -561,6 +562,10 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
     {
         Fr* __restrict__ x        = batch.x[u % count];
         const uint32_t   col_base = pair_base(u) + (e << kNttTileBits); // 128 contiguous elements
+        // The unrolled rounds are ~370 KB of code: warps that drift apart over the tiles of a persistent CTA evict one
+        // another's instructions (ncu: 3.7 no-instruction stall cycles per issue without this barrier). One CTA barrier
+        // per tile keeps the eight warps on the same stretch of code.
+        __syncthreads();
         ntt_mbar_wait(bar, parity);
         parity ^= 1u;
         Fr v[8];

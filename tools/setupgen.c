@@ -413,6 +413,19 @@ static void circuit_free(circuit_t* c)
     free(c->a_ptr); free(c->b_ptr); free(c->c_ptr); free(c->a); free(c->b); free(c->c); free(c->w); free(c);
 }
 
+/* Gate mix of the synthetic circuit, as cumulative percentages: XOR below g_mix[0], AND below g_mix[1], byte
+ * recomposition below g_mix[2], field product above. The default (50 / 80 / 95) gives the keyless-like witness of the
+ * bench (~84 % bits, ~12 % bytes, ~4 % full-width values); kzp_setupgen_set_mix(35, 55, 70) makes ~30 % of the wires
+ * full-width field elements — the pessimistic end for the witness-side MSMs. */
+static int g_mix[3] = {50, 80, 95};
+int kzp_setupgen_set_mix(int xor_below, int and_below, int byte_below)
+{
+    if (xor_below < 1 || xor_below > and_below || and_below > byte_below || byte_below > 100)
+        return -1;
+    g_mix[0] = xor_below; g_mix[1] = and_below; g_mix[2] = byte_below;
+    return 0;
+}
+
 static circuit_t* circuit_synth(uint32_t n_constraints, uint32_t n_vars, uint64_t seed)
 {
     circuit_t* C = (circuit_t*)calloc(1, sizeof(circuit_t));
@@ -436,7 +449,7 @@ static circuit_t* circuit_synth(uint32_t n_constraints, uint32_t n_vars, uint64_
     for (uint32_t out = 10; out < n_vars; out++)
     {
         uint64_t t = rng_below(&rng, 100);
-        if (t < 50 || n_bits < 8)
+        if (t < (uint64_t)g_mix[0] || n_bits < 8)
         {
             /* XOR: 2ij = i + j - out */
             uint32_t i = bits[rng_below(&rng, n_bits)], j = bits[rng_below(&rng, n_bits)];
@@ -449,8 +462,8 @@ static circuit_t* circuit_synth(uint32_t n_constraints, uint32_t n_vars, uint64_
             END_ROW();
             bits[n_bits++] = out;
         }
-        else if (t < 80) { AND_GATE(out); bits[n_bits++] = out; }
-        else if (t < 95)
+        else if (t < (uint64_t)g_mix[1]) { AND_GATE(out); bits[n_bits++] = out; }
+        else if (t < (uint64_t)g_mix[2])
         {
             /* byte = sum 2^k bit_k ; duplicates merged like a Python dict keeps insertion order of first use */
             uint32_t ws[8]; uint64_t cs[8]; int cnt = 0; uint64_t val = 0;
