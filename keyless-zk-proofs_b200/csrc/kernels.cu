@@ -291,79 +291,156 @@ uint32_t ntt_launches(uint32_t log_n)
 {
     if (log_n == 0)
         return 0;
-    return ntt_use_levels(log_n) ? log_n / kNttTileBits + log_n % kNttTileBits : log_n;
+    return ntt_use_levels(log_n) ? log_n / kNttTileBits + (log_n % kNttTileBits ? 1 : 0) : log_n;
 }
 
-void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st)
+// The r <= 6 stages on the lowest r index bits that are left over when log_n is not a multiple of 7, in ONE pass
+// through shared memory: contiguous groups of 512 elements, 256 butterflies per stage and block. DIF: half-distances
+// 2^(r-1) .. 1 (the end of an inverse transform, `post` applied on the way out); DIT: 1 .. 2^(r-1) (the start of a
+// forward transform). The same radix-2 stages as k_ntt_dif_stage / k_ntt_dit_stage, which remain for sizes below 2^11.
+constexpr int kNttLowElems = 512;
+template <bool DIT>
+__global__ void __launch_bounds__(kNttLowElems / 2)
+    k_ntt_low_stages(NttBatch batch, const Fr* __restrict__ tw, uint32_t log_n, uint32_t r, const Fr* __restrict__ post)
 {
-    uint32_t log_n = d.log_n;
+    __shared__ uint4 sm_raw[kNttLowElems * 2];
+    Fr*              sm   = reinterpret_cast<Fr*>(sm_raw);
+    Fr* __restrict__ x    = batch.x[blockIdx.y];
+    const size_t     base = (size_t)blockIdx.x * kNttLowElems;
+    const uint32_t   t    = threadIdx.x;
+    sm[t]                    = x[base + t];
+    sm[t + kNttLowElems / 2] = x[base + t + kNttLowElems / 2];
+    __syncthreads();
+    for (uint32_t s = 0; s < r; s++)
+    {
+        const uint32_t lh = DIT ? s : r - 1 - s, half = 1u << lh;
+        const uint32_t j = t & (half - 1u), i0 = ((t >> lh) << (lh + 1)) + j, i1 = i0 + half;
+        Fr             u = sm[i0], v = sm[i1], w = tw[(size_t)j << (log_n - 1 - lh)], a, d;
+        if (DIT)
+        {
+            Fr::mul(v, v, w);
+            Fr::add(a, u, v);
+            Fr::sub(d, u, v);
+        }
+        else
+        {
+            Fr::add(a, u, v);
+            Fr::sub(d, u, v);
+            Fr::mul(d, d, w);
+        }
+        sm[i0] = a;
+        sm[i1] = d;
+        __syncthreads();
+    }
+    Fr o0 = sm[t], o1 = sm[t + kNttLowElems / 2];
+    if (post)
+    {
+        Fr::mul(o0, o0, post[base + t]);
+        Fr::mul(o1, o1, post[base + t + kNttLowElems / 2]);
+    }
+    x[base + t]                    = o0;
+    x[base + t + kNttLowElems / 2] = o1;
+}
+
+// `count` vectors through every launch together (blockIdx.y / work units); sizes below 2^11 one vector at a time
+static uint32_t ntt_inverse_dif_batch(const NttDomain& d, const NttBatch& b, int count, const Fr* post, cudaStream_t st)
+{
+    uint32_t log_n = d.log_n, launches = 0;
     if (log_n == 0)
     {
         if (post)
+            for (int i = 0; i < count; i++)
+            {
+                k_fr_scale<<<1, 256, 0, st>>>(b.x[i], 1, Fr::zero(), post);
+                KZP_CUDA_CHECK(cudaGetLastError());
+                launches++;
+            }
+        return launches;
+    }
+    if (!ntt_use_levels(log_n))
+    {
+        unsigned int grid = div_up(1ull << (log_n - 1), 256);
+        for (int i = 0; i < count; i++)
+            for (int lh = (int)log_n - 1; lh >= 0; lh--)
+            {
+                k_ntt_dif_stage<<<grid, 256, 0, st>>>(b.x[i], d.tw_inv, log_n, (uint32_t)lh, lh == 0 ? post : nullptr);
+                KZP_CUDA_CHECK(cudaGetLastError());
+                launches++;
+            }
+        return launches;
+    }
+    ntt_level_attrs();
+    uint32_t     hi    = log_n;
+    unsigned int tiles = 1u << (log_n - kNttTileBits - kNttColBits);
+    while (hi >= (uint32_t)kNttTileBits)
+    {
+        uint32_t lo = hi - kNttTileBits;
+        if (lo == 0) // one-element columns: two adjacent columns are not adjacent in memory, plain loads
         {
-            k_fr_scale<<<1, 256, 0, st>>>(x, 1, Fr::zero(), post);
+            k_ntt_level<false><<<dim3(tiles, (unsigned int)count), kNttThreads, kNttLevelSmem, st>>>(b, d.tw_inv, log_n, lo, 0, post, NttRoute());
             KZP_CUDA_CHECK(cudaGetLastError());
         }
-        return;
+        else
+            ntt_launch_level<false, false>(b, count, d.tw_inv, log_n, lo, 0, NttRoute(), tiles, st);
+        launches++;
+        hi = lo;
     }
-    uint32_t hi = log_n;
-    if (ntt_use_levels(log_n))
+    if (hi > 0)
     {
-        ntt_level_attrs();
-        unsigned int grid = 1u << (log_n - kNttTileBits - kNttColBits);
-        while (hi >= (uint32_t)kNttTileBits)
-        {
-            uint32_t lo = hi - kNttTileBits;
-            if (lo == 0) // one-element columns: two adjacent columns are not adjacent in memory, plain loads
-            {
-                k_ntt_level<false><<<grid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_inv, log_n, lo, 0, post, NttRoute());
-                KZP_CUDA_CHECK(cudaGetLastError());
-            }
-            else
-                ntt_launch_level<false, false>(ntt_batch1(x), 1, d.tw_inv, log_n, lo, 0, NttRoute(), grid, st);
-            hi = lo;
-        }
-        if (hi == 0)
-            return;
-    }
-    unsigned int grid = div_up(1ull << (log_n - 1), 256);
-    for (int lh = (int)hi - 1; lh >= 0; lh--)
-    {
-        k_ntt_dif_stage<<<grid, 256, 0, st>>>(x, d.tw_inv, log_n, (uint32_t)lh, lh == 0 ? post : nullptr);
+        k_ntt_low_stages<false><<<dim3((unsigned int)((1ull << log_n) / kNttLowElems), (unsigned int)count), kNttLowElems / 2, 0, st>>>(
+            b, d.tw_inv, log_n, hi, post);
         KZP_CUDA_CHECK(cudaGetLastError());
+        launches++;
     }
+    return launches;
 }
 
-void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st)
+static uint32_t ntt_forward_dit_batch(const NttDomain& d, const NttBatch& b, int count, cudaStream_t st)
 {
-    uint32_t log_n = d.log_n;
+    uint32_t log_n = d.log_n, launches = 0;
     if (log_n == 0)
-        return;
-    bool         levels = ntt_use_levels(log_n);
-    uint32_t     r      = levels ? log_n % kNttTileBits : log_n;
-    unsigned int grid   = div_up(1ull << (log_n - 1), 256);
-    for (uint32_t lh = 0; lh < r; lh++)
+        return 0;
+    if (!ntt_use_levels(log_n))
     {
-        k_ntt_dit_stage<<<grid, 256, 0, st>>>(x, d.tw_fwd, log_n, lh);
-        KZP_CUDA_CHECK(cudaGetLastError());
+        unsigned int grid = div_up(1ull << (log_n - 1), 256);
+        for (int i = 0; i < count; i++)
+            for (uint32_t lh = 0; lh < log_n; lh++)
+            {
+                k_ntt_dit_stage<<<grid, 256, 0, st>>>(b.x[i], d.tw_fwd, log_n, lh);
+                KZP_CUDA_CHECK(cudaGetLastError());
+                launches++;
+            }
+        return launches;
     }
-    if (!levels)
-        return;
     ntt_level_attrs();
-    unsigned int lgrid = 1u << (log_n - kNttTileBits - kNttColBits);
+    const uint32_t r = log_n % kNttTileBits;
+    if (r > 0)
+    {
+        k_ntt_low_stages<true><<<dim3((unsigned int)((1ull << log_n) / kNttLowElems), (unsigned int)count), kNttLowElems / 2, 0, st>>>(
+            b, d.tw_fwd, log_n, r, nullptr);
+        KZP_CUDA_CHECK(cudaGetLastError());
+        launches++;
+    }
+    unsigned int tiles = 1u << (log_n - kNttTileBits - kNttColBits);
     uint32_t     plo   = 0;
     for (uint32_t lo = r; lo + kNttTileBits <= log_n; lo += kNttTileBits)
     {
         if (lo == 0)
         {
-            k_ntt_level<true><<<lgrid, kNttThreads, kNttLevelSmem, st>>>(ntt_batch1(x), d.tw_fwd, log_n, lo, plo, nullptr, NttRoute());
+            k_ntt_level<true><<<dim3(tiles, (unsigned int)count), kNttThreads, kNttLevelSmem, st>>>(b, d.tw_fwd, log_n, lo, plo, nullptr, NttRoute());
             KZP_CUDA_CHECK(cudaGetLastError());
         }
         else
-            ntt_launch_level<true, false>(ntt_batch1(x), 1, d.tw_fwd, log_n, lo, plo, NttRoute(), lgrid, st);
+            ntt_launch_level<true, false>(b, count, d.tw_fwd, log_n, lo, plo, NttRoute(), tiles, st);
+        launches++;
         plo = lo;
     }
+    return launches;
 }
+
+void ntt_inverse_dif(const NttDomain& d, Fr* x, const Fr* post, cudaStream_t st) { ntt_inverse_dif_batch(d, ntt_batch1(x), 1, post, st); }
+
+void ntt_forward_dit(const NttDomain& d, Fr* x, cudaStream_t st) { ntt_forward_dit_batch(d, ntt_batch1(x), 1, st); }
 
 // The prover's H chain on `count` <= 3 vectors at once: ifft, multiply by w_2n^i, fft (groth16.cpp:172-262), all
 // vectors through each launch together. When log_n is a multiple of 7 the middle two levels run fused (k_ntt_mid).
@@ -374,21 +451,19 @@ uint32_t ntt_coset_chain(const NttDomain& d, Fr* const* xs, int count, cudaStrea
     uint32_t log_n = d.log_n;
     if (count < 1 || count > kNttMaxBatch)
         throw CudaError("NTT batch size out of range");
-    if (!ntt_chain_is_batched(log_n))
-    {
-        if (last_store)
-            throw CudaError("a routed NTT chain needs a batched domain size");
-        for (int i = 0; i < count; i++)
-        {
-            ntt_inverse_dif(d, xs[i], d.coset_br, st);
-            ntt_forward_dit(d, xs[i], st);
-        }
-        return 2 * ntt_launches(log_n) * (uint32_t)count;
-    }
-    ntt_level_attrs();
     NttBatch b;
     for (int i = 0; i < kNttMaxBatch; i++)
         b.x[i] = xs[i < count ? i : 0];
+    if (!ntt_chain_is_batched(log_n))
+    {
+        // no fused middle level for this size: inverse transform (with the coset / scale multiplier on the way out),
+        // then forward transform, every launch over all the vectors
+        if (last_store)
+            throw CudaError("a routed NTT chain needs a batched domain size");
+        uint32_t launches = ntt_inverse_dif_batch(d, b, count, d.coset_br, st);
+        return launches + ntt_forward_dit_batch(d, b, count, st);
+    }
+    ntt_level_attrs();
     dim3     grid(1u << (log_n - kNttTileBits - kNttColBits), (unsigned int)count, 1);
     uint32_t launches = 0;
     for (uint32_t lo = log_n - kNttTileBits; lo > 0; lo -= kNttTileBits)
