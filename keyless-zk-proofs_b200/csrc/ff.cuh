@@ -310,6 +310,191 @@ struct alignas(16) Fp
     }
 #endif
 
+#if defined(__CUDACC__)
+    // (bodies exist in the device pass only: nvcc's host pass just needs the declarations)
+    // s = a * b * R^-1 + (a multiple of p), NOT reduced: s < a b / R + p. For canonical a, b that is below 2p; more
+    // generally below 2p whenever a b < 4.2 p^2 (p / R = 0.19 for both BN254 fields), e.g. a < 4p and b < p.
+    static KZP_D void mul_core(uint32_t (&s)[8], const Fp& a, const Fp& b)
+    {
+#if defined(__CUDA_ARCH__)
+        // T = X + (Y << 32) + pend, X at limb offsets 0..7, Y at 1..8; T < 2^288 throughout.
+        uint32_t x[8], y[8], pend = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            x[i] = 0;
+            y[i] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            uint32_t bi = b.v[i];
+            chain_odd_pend(x[0], pend, y, a.v[1], a.v[3], a.v[5], a.v[7], bi);
+            chain_even(x, y[7], a.v[0], a.v[2], a.v[4], a.v[6], bi);
+            uint32_t m = x[0] * P::NP0;
+            chain_even(x, y[7], P::P0, P::P2, P::P4, P::P6, m);
+            chain_odd(y, P::P1, P::P3, P::P5, P::P7, m);
+            pend = x[1];
+            uint32_t t0 = y[0], t1 = y[1], t2 = y[2], t3 = y[3], t4 = y[4], t5 = y[5], t6 = y[6],
+                     t7 = y[7];
+            y[0] = x[2]; y[1] = x[3]; y[2] = x[4]; y[3] = x[5]; y[4] = x[6]; y[5] = x[7];
+            y[6] = 0; y[7] = 0;
+            x[0] = t0; x[1] = t1; x[2] = t2; x[3] = t3; x[4] = t4; x[5] = t5; x[6] = t6; x[7] = t7;
+        }
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
+            : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]),
+              "r"(x[7]), "r"(pend), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]),
+              "r"(y[5]), "r"(y[6]));
+#endif
+    }
+
+    // ---- lazy-reduction variants for chains of butterflies (values kept in [0, 2p): BN254's moduli leave two spare
+    //      bits in 256, so sums of two such values and a - b + 2p still fit). Used by the NTT levels only; everything
+    //      that leaves a kernel is canonical again (reduce_2p).
+    static constexpr uint32_t twice_p(int i)
+    {
+        const uint32_t m[8] = {P::P0, P::P1, P::P2, P::P3, P::P4, P::P5, P::P6, P::P7};
+        return (m[i] << 1) | (i ? (m[i - 1] >> 31) : 0u);
+    }
+    // r = a b R^-1 mod p as a value below 2p; a b < 4.2 p^2 (see mul_core)
+    static KZP_D void mul_lazy(Fp& r, const Fp& a, const Fp& b)
+    {
+#if defined(__CUDA_ARCH__)
+        uint32_t s[8];
+        mul_core(s, a, b);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            r.v[i] = s[i];
+#endif
+    }
+    // r = a - k (256-bit) if that does not borrow, else a: one conditional subtraction of the constant k
+    template <bool TWICE>
+    static KZP_D void cond_sub_const(Fp& r, const uint32_t (&s)[8])
+    {
+#if defined(__CUDA_ARCH__)
+        constexpr uint32_t k0 = TWICE ? twice_p(0) : P::P0, k1 = TWICE ? twice_p(1) : P::P1, k2 = TWICE ? twice_p(2) : P::P2,
+                           k3 = TWICE ? twice_p(3) : P::P3, k4 = TWICE ? twice_p(4) : P::P4, k5 = TWICE ? twice_p(5) : P::P5,
+                           k6 = TWICE ? twice_p(6) : P::P6, k7 = TWICE ? twice_p(7) : P::P7;
+        uint32_t t0, t1, t2, t3, t4, t5, t6, t7, bw;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7), "=r"(bw)
+            : "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]), "r"(k0), "r"(k1), "r"(k2),
+              "r"(k3), "r"(k4), "r"(k5), "r"(k6), "r"(k7));
+        bool keep = (bw != 0);
+        r.v[0] = keep ? s[0] : t0; r.v[1] = keep ? s[1] : t1; r.v[2] = keep ? s[2] : t2; r.v[3] = keep ? s[3] : t3;
+        r.v[4] = keep ? s[4] : t4; r.v[5] = keep ? s[5] : t5; r.v[6] = keep ? s[6] : t6; r.v[7] = keep ? s[7] : t7;
+#endif
+    }
+    // [0, 2p) -> canonical
+    static KZP_D void reduce_2p(Fp& r, const Fp& a)
+    {
+#if defined(__CUDA_ARCH__)
+        uint32_t s[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            s[i] = a.v[i];
+        cond_sub_const<false>(r, s);
+#endif
+    }
+    // a, b in [0, 2p) -> a + b mod 2p-window: a value in [0, 2p) congruent to a + b
+    static KZP_D void add_lazy(Fp& r, const Fp& a, const Fp& b)
+    {
+#if defined(__CUDA_ARCH__)
+        uint32_t s[8];
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+              "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+        cond_sub_const<true>(r, s);
+#endif
+    }
+    // a, b in [0, 2p) -> a value in [0, 2p) congruent to a - b (2p added back on borrow)
+    static KZP_D void sub_lazy(Fp& r, const Fp& a, const Fp& b)
+    {
+#if defined(__CUDA_ARCH__)
+        uint32_t s0, s1, s2, s3, s4, s5, s6, s7, bw;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7), "=r"(bw)
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+              "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;"
+            : "+r"(s0), "+r"(s1), "+r"(s2), "+r"(s3), "+r"(s4), "+r"(s5), "+r"(s6), "+r"(s7)
+            : "r"(twice_p(0) & bw), "r"(twice_p(1) & bw), "r"(twice_p(2) & bw), "r"(twice_p(3) & bw), "r"(twice_p(4) & bw),
+              "r"(twice_p(5) & bw), "r"(twice_p(6) & bw), "r"(twice_p(7) & bw));
+        r.v[0] = s0; r.v[1] = s1; r.v[2] = s2; r.v[3] = s3; r.v[4] = s4; r.v[5] = s5; r.v[6] = s6; r.v[7] = s7;
+#endif
+    }
+    // a, b in [0, 2p) -> a + 2p - b, a value in (0, 4p): no comparison at all; feed it to mul_lazy with a canonical
+    // second factor (4p * p < 4.2 p^2)
+    static KZP_D void sub_plus_2p(Fp& r, const Fp& a, const Fp& b)
+    {
+#if defined(__CUDA_ARCH__)
+        uint32_t s0, s1, s2, s3, s4, s5, s6, s7;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3), "=r"(s4), "=r"(s5), "=r"(s6), "=r"(s7)
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+              "r"(twice_p(0)), "r"(twice_p(1)), "r"(twice_p(2)), "r"(twice_p(3)), "r"(twice_p(4)), "r"(twice_p(5)),
+              "r"(twice_p(6)), "r"(twice_p(7)));
+        asm("sub.cc.u32 %0, %0, %8;\n\t"
+            "subc.cc.u32 %1, %1, %9;\n\t"
+            "subc.cc.u32 %2, %2, %10;\n\t"
+            "subc.cc.u32 %3, %3, %11;\n\t"
+            "subc.cc.u32 %4, %4, %12;\n\t"
+            "subc.cc.u32 %5, %5, %13;\n\t"
+            "subc.cc.u32 %6, %6, %14;\n\t"
+            "subc.u32 %7, %7, %15;"
+            : "+r"(s0), "+r"(s1), "+r"(s2), "+r"(s3), "+r"(s4), "+r"(s5), "+r"(s6), "+r"(s7)
+            : "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+        r.v[0] = s0; r.v[1] = s1; r.v[2] = s2; r.v[3] = s3; r.v[4] = s4; r.v[5] = s5; r.v[6] = s6; r.v[7] = s7;
+#endif
+    }
+#endif
+
     // r = a * b * R^-1 mod p, canonical (Fr_rawMMul: fr_raw_generic.cpp:107-148)
     static KZP_HD void mul(Fp& r, const Fp& a, const Fp& b)
     {

@@ -229,17 +229,32 @@ static TensorMapEncodeTiledFn tensor_map_encoder()
     return fn;
 }
 
-// x as {2^lo * 4 words, 128 rows, 2^(k - lo - 7) uppers} of 8-byte words; box = one warp's two columns. DIT levels
-// traverse the rows with a stride of 8 (16 rows per copy, see k_ntt_level_tma).
+// x as {2^lo * 4 words, 128 rows, 2^(k - lo - 7) uppers} of 8-byte words; box = one warp's two columns. The forward
+// levels split the rows into {8, 16} so that one copy brings every eighth row (see k_ntt_level_tma).
 static void ntt_encode_map(CUtensorMap& m, Fr* x, uint32_t k, uint32_t lo, bool dit)
 {
-    const uint32_t hi         = lo + kNttTileBits;
-    cuuint64_t     gdim[3]    = {(cuuint64_t)4 << lo, 128, (cuuint64_t)1 << (k - hi)};
-    cuuint64_t     gstride[2] = {(cuuint64_t)32 << lo, (cuuint64_t)32 << hi};
-    cuuint32_t     box[3]     = {8, 128, 1};
-    cuuint32_t     estr[3]    = {1, dit ? 8u : 1u, 1};
-    CUresult       r = tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, x, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const uint32_t hi = lo + kNttTileBits;
+    CUresult       r;
+    if (!dit)
+    {
+        cuuint64_t gdim[3]    = {(cuuint64_t)4 << lo, 128, (cuuint64_t)1 << (k - hi)};
+        cuuint64_t gstride[2] = {(cuuint64_t)32 << lo, (cuuint64_t)32 << hi};
+        cuuint32_t box[3]     = {8, 128, 1};
+        cuuint32_t estr[3]    = {1, 1, 1};
+        r = tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, x, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    else
+    {
+        // rows t = 8 g + q as two dimensions (q: 8 rows apart by one row, g: 16 groups apart by eight rows); the box
+        // {8 words, 1, 16, 1} at coordinate q is rows q, q + 8, ..., q + 120
+        cuuint64_t gdim[4]    = {(cuuint64_t)4 << lo, 8, 16, (cuuint64_t)1 << (k - hi)};
+        cuuint64_t gstride[3] = {(cuuint64_t)32 << lo, (cuuint64_t)256 << lo, (cuuint64_t)32 << hi};
+        cuuint32_t box[4]     = {8, 1, 16, 1};
+        cuuint32_t estr[4]    = {1, 1, 1, 1};
+        r = tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, x, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS)
         throw CudaError("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r) + " (k " + std::to_string(k) + ", lo " +
                         std::to_string(lo) + ")");

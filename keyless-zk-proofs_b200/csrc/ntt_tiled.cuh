@@ -145,10 +145,23 @@ __device__ __forceinline__ void ntt_tma_load_3d(void* dst_smem, const CUtensorMa
                  : "memory");
 }
 
+__device__ __forceinline__ void ntt_tma_load_4d(void* dst_smem, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                     ntt_smem_u32(dst_smem)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(ntt_smem_u32(bar))
+                 : "memory");
+}
+
 // One butterfly stage on v[0..7]: pairs (q, q | 1 << B) for the q with bit B clear. The twiddle of pair q is
 // w_128^idx with idx = (j0 + ((q & mask) << qsh)) << ish where mask = (1 << B) - 1, i.e. j = row mod half-distance.
 // DIF: (a, b) -> (a + b, (a - b) w);  DIT: (a, b) -> (a + w b, a - w b).  KNOWN0: j0 == 0 at compile time, so
 // pairs with (q & mask) == 0 have twiddle 1 and skip the product.
+// Lazy reduction: inside a level every value lives in [0, 2p) (ff.cuh: BN254's r leaves two spare bits). Products skip
+// their final conditional subtraction, and the DIF difference feeds its product as a + 2p - b without any comparison
+// (below 4p, times a canonical twiddle: the product is below 2p again). A level's inputs are canonical and its outputs
+// are made canonical before they are stored (reduce_2p), so nothing outside the level sees the wider range.
 template <bool DIT, int B, bool KNOWN0>
 __device__ __forceinline__ void ntt_stage(Fr (&v)[8], const uint4* twp, uint32_t j0, uint32_t qsh, uint32_t ish)
 {
@@ -162,8 +175,8 @@ __device__ __forceinline__ void ntt_stage(Fr (&v)[8], const uint4* twp, uint32_t
         if (KNOWN0 && qm == 0)
         {
             Fr a = v[q], b = v[q2];
-            Fr::add(v[q], a, b);
-            Fr::sub(v[q2], a, b);
+            Fr::add_lazy(v[q], a, b);
+            Fr::sub_lazy(v[q2], a, b);
             continue;
         }
         Fr w;
@@ -171,16 +184,16 @@ __device__ __forceinline__ void ntt_stage(Fr (&v)[8], const uint4* twp, uint32_t
         Fr a = v[q], b = v[q2];
         if (DIT)
         {
-            Fr::mul(b, b, w);
-            Fr::add(v[q], a, b);
-            Fr::sub(v[q2], a, b);
+            Fr::mul_lazy(b, b, w);
+            Fr::add_lazy(v[q], a, b);
+            Fr::sub_lazy(v[q2], a, b);
         }
         else
         {
             Fr d;
-            Fr::add(v[q], a, b);
-            Fr::sub(d, a, b);
-            Fr::mul(v[q2], d, w);
+            Fr::add_lazy(v[q], a, b);
+            Fr::sub_plus_2p(d, a, b);
+            Fr::mul_lazy(v[q2], d, w);
         }
     }
 }
@@ -336,11 +349,12 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
                 {
                     Fr w;
                     ntt_root(w, tw, ex, k);
-                    Fr::mul(v[q], v[q], w);
+                    Fr::mul_lazy(v[q], v[q], w);
                 }
             }
             if (post)
-                Fr::mul(v[q], v[q], post[pos]);
+                Fr::mul_lazy(v[q], v[q], post[pos]);
+            Fr::reduce_2p(v[q], v[q]);
             *ntt_route_dst<ROUTED>(rt, x, pos, blockIdx.y) = v[q];
         }
     }
@@ -361,14 +375,17 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
                 {
                     Fr w;
                     ntt_root(w, tw, ex, k);
-                    Fr::mul(v[q], v[q], w);
+                    Fr::mul_lazy(v[q], v[q], w);
                 }
             }
         }
         ntt_dit_rounds(v, wsm, twp, g, e);
 #pragma unroll
         for (int q = 0; q < 8; q++)
+        {
+            Fr::reduce_2p(v[q], v[q]);
             *ntt_route_dst<ROUTED>(rt, x, col_base | (ntt_row1(g, q) << lo), blockIdx.y) = v[q];
+        }
     }
 }
 
@@ -379,8 +396,9 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
 // A warp's two columns are the box {8 words, 128 rows, 1}: 128 rows of 64 bytes, 8 KiB, one tensor copy (DIF). The
 // first round wants lane g to hold rows g + 16 q (DIF) or 8 g + q (DIT); so that the lanes of a quarter-warp always
 // read CONSECUTIVE 64-byte rows of the landed image (with the 64-byte swizzle: eight different bank groups), the DIT
-// kernel fetches the tile as eight copies of 16 rows each with a traversal stride of 8 rows (elementStrides), copy q
-// landing at q * 1 KiB: in both cases virtual row g + 16 q of the image is the element the lane needs as v[q].
+// kernel sees the rows as two dimensions {q: 8, g: 16} (a 4-D tensor) and fetches the tile as eight copies of the box
+// {8 words, 1, 16, 1}, copy q (rows q, q + 8, ..., q + 120) landing at q * 1 KiB: in both cases virtual row g + 16 q of
+// the image is the element the lane needs as v[q].
 struct alignas(64) NttMaps
 {
     CUtensorMap m[kNttMaxBatch];
@@ -444,7 +462,7 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
         {
             __syncwarp();
             if (lane < 8)
-                ntt_tma_load_3d(wsm + lane * 64u, map, c0, lane, c2, bar); // rows lane, lane + 8, ..., lane + 120
+                ntt_tma_load_4d(wsm + lane * 64u, map, c0, lane, 0, c2, bar); // rows lane, lane + 8, ..., lane + 120
         }
     };
     uint32_t u = blockIdx.x, parity = 0;
@@ -484,8 +502,9 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
                 {
                     Fr w;
                     ntt_root(w, tw, ex, k);
-                    Fr::mul(v[q], v[q], w);
+                    Fr::mul_lazy(v[q], v[q], w);
                 }
+                Fr::reduce_2p(v[q], v[q]);
                 *ntt_route_dst<ROUTED>(rt, x, pos, u % count) = v[q];
             }
         }
@@ -503,13 +522,16 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
                 {
                     Fr w;
                     ntt_root(w, tw, ex, k);
-                    Fr::mul(v[q], v[q], w);
+                    Fr::mul_lazy(v[q], v[q], w);
                 }
             }
             ntt_dit_rounds(v, wsm, twp, g, e, smem_free);
 #pragma unroll
             for (int q = 0; q < 8; q++)
+            {
+                Fr::reduce_2p(v[q], v[q]);
                 *ntt_route_dst<ROUTED>(rt, x, col_base | (ntt_row1(g, q) << lo), u % count) = v[q];
+            }
         }
     }
 }
@@ -589,7 +611,7 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
         const Fr* pp = post + col_base + ntt_row3(g, 0);
 #pragma unroll
         for (int q = 0; q < 8; q++)
-            Fr::mul(v[q], v[q], pp[q]);
+            Fr::mul_lazy(v[q], v[q], pp[q]);
         __syncwarp();
         const uint32_t next = u + gridDim.x;
         ntt_dit_rounds(v, wsm, twF, g, e, [&] {
@@ -602,7 +624,10 @@ __global__ void __launch_bounds__(kNttThreads, kNttMinCtas)
         });
 #pragma unroll
         for (int q = 0; q < 8; q++)
+        {
+            Fr::reduce_2p(v[q], v[q]);
             *ntt_route_dst<ROUTED>(rt, x, col_base + ntt_row1(g, q), u % count) = v[q];
+        }
     }
 }
 
