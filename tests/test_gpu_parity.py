@@ -5,6 +5,7 @@ import json
 import os
 import random
 import subprocess
+import sys
 
 import pytest
 
@@ -204,6 +205,31 @@ def test_coset_chain_matches_reference(gpu, kzp, oracle, port, log_n):
         acc = o.mont_mul(acc, w2n, o.R_MOD)
     want = port.ntt(_fr_bytes(o, shift), False)
     assert kzp.fr_coset_chain(X) == want
+
+
+def test_ntt_persistent_variant_matches(gpu, kzp, workdir):
+    """KZP_NTT_PERSIST=1 (persistent CTAs, every warp prefetching its next tile through the copy engine) is the measured-
+    slower variant that stays selectable: a fresh process with the switch set produces the same chain and the same
+    transforms as this process (sizes with 2, 3 and no fused middle level, and a leftover low-stage pass)."""
+    import numpy as np
+    rnd = random.Random(99)
+    script = os.path.join(workdir, "ntt_persist.py")
+    open(script, "w").write(
+        "import sys, hashlib\nsys.path.insert(0, %r)\nimport keyless_zk_proofs_b200 as kzp\n"
+        "for path in sys.argv[1:]:\n    X = open(path, 'rb').read()\n"
+        "    print(hashlib.sha256(kzp.fr_coset_chain(X)).hexdigest(), hashlib.sha256(kzp.fr_ntt(X, True)).hexdigest())\n" % ROOT)
+    import hashlib
+    paths, want = [], []
+    for log_n in (14, 16, 21):
+        raw = np.frombuffer(rnd.randbytes((1 << log_n) * 32), dtype=np.uint8).reshape(1 << log_n, 32).copy()
+        raw[:, 31] &= 0x1F  # < 2^253 < r: canonical
+        X = raw.tobytes()
+        path = os.path.join(workdir, "ntt_in_%d.bin" % log_n)
+        open(path, "wb").write(X)
+        paths.append(path)
+        want.append("%s %s" % (hashlib.sha256(kzp.fr_coset_chain(X)).hexdigest(), hashlib.sha256(kzp.fr_ntt(X, True)).hexdigest()))
+    out = subprocess.check_output([sys.executable, script] + paths, env=dict(os.environ, KZP_NTT_PERSIST="1"), text=True, timeout=300)
+    assert out.split("\n")[:3] == want
 
 
 @pytest.mark.slow
