@@ -185,7 +185,8 @@ int kzp_msm_bench(kzp_msm* m, const uint8_t* scalars, int iters, float* ms_per_m
  * 6 square 7 inverse 8 a*b + b*b (dual product with one reduction, Fr / Fq only). Host buffers, `count` elements; b may be NULL for unary ops. */
 int kzp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t count,
                  int device);
-/* group: 0 G1, 1 G2; op: 0 xyzz += affine, 1 xyzz += xyzz, 2 double. p/out XYZZ (128/256 B per point). */
+/* group: 0 G1, 1 G2; op: 0 xyzz += affine, 1 xyzz += xyzz, 2 double, 3 / 4 the same addition / doubling as the
+ * bucket-reduction kernels run it (four lanes per point). p/out XYZZ (128/256 B per point). */
 int kzp_point_op(int group, int op, const uint8_t* p, const uint8_t* q, uint8_t* out, uint64_t count,
                  int device);
 /* integer-pipe roofline probe: carry-chained 32x32+64 multiply-adds (IMAD.WIDE.U32[.X]) on every SM */

@@ -843,14 +843,14 @@ int kzp_point_op(int group, int op, const uint8_t* p, const uint8_t* q, uint8_t*
                  int device)
 {
     return guarded([&] {
-        if (group < 0 || group > 1 || op < 0 || op > 2)
+        if (group < 0 || group > 1 || op < 0 || op > 4)
             throw FormatError("bad group/op");
         use_device(device);
         size_t psz = group == 0 ? 128 : 256;
         size_t qsz = op == 0 ? psz / 2 : psz;
         DevBuf dp(count * psz), dq(count * qsz), dout(count * psz);
         KZP_CUDA_CHECK(cudaMemcpy(dp.p, p, count * psz, cudaMemcpyHostToDevice));
-        if (q && op != 2)
+        if (q && op != 2 && op != 4)
             KZP_CUDA_CHECK(cudaMemcpy(dq.p, q, count * qsz, cudaMemcpyHostToDevice));
         point_op(group, op, dp.p, dq.p, dout.p, count, 0);
         KZP_CUDA_CHECK(cudaDeviceSynchronize());

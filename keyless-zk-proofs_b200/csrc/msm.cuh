@@ -131,19 +131,140 @@ __device__ __noinline__ void cold_dbl(XY& p)
     XY::dbl(p, t);
 }
 
-template <class XY>
-__device__ __forceinline__ void block_tree_sum(XY* sm, uint32_t active, uint32_t tid)
+// ---- cooperative group operations for the latency-bound kernels ---------------------------------------------------
+// A lone point addition is a chain of 14 dependent field products (~5 us for a warp that has an SM to itself), and the
+// bucket reduction is nothing but sequential additions. kCoop = 4 consecutive lanes therefore act as ONE logical
+// thread: all four hold the same operands (loaded from the same addresses), each computes one of the up to four
+// independent products of a dependency level, and the results travel by warp shuffle inside the group. The chain
+// shrinks from 14 products to 4 (9 to 3 for a doubling). Exceptional cases are decided on replicated data, so the
+// four lanes always branch together; the shuffles name only the group's lanes in their mask.
+constexpr uint32_t kCoop = 4;
+
+__device__ __forceinline__ uint32_t coop_mask() { return 0xfu << (threadIdx.x & 28u); }
+
+// value of lane `src` of the group, on every lane of the group
+template <class F>
+__device__ __forceinline__ F coop_bcast(const F& v, uint32_t src, uint32_t mask)
 {
-    // sm[0..active) hold points; result in sm[0]
+    F               r;
+    const uint32_t* in  = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t*       out = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(F) / 4); i++)
+        out[i] = __shfl_sync(mask, in[i], (int)src, (int)kCoop);
+    return r;
+}
+
+template <class F>
+__device__ __forceinline__ F coop_pick(uint32_t sub, const F& a0, const F& a1, const F& a2, const F& a3)
+{
+    return sub == 0 ? a0 : (sub == 1 ? a1 : (sub == 2 ? a2 : a3));
+}
+
+// acc += q (add-2008-s, the same formulas as XyzzT::add) by the 4 lanes of a group; sub = lane index in the group
+template <class XY>
+__device__ __noinline__ void coop_add(XY& acc, const XY& q, uint32_t sub)
+{
+    typedef typename XY::Field F;
+    if (XY::is_inf(q))
+        return;
+    if (XY::is_inf(acc))
+    {
+        acc = q;
+        return;
+    }
+    const uint32_t mask = coop_mask();
+    F              t, u;
+    // level 1: U1 = x1 zz2 | U2 = x2 zz1 | S1 = y1 zzz2 | S2 = y2 zzz1
+    F::mul(t, coop_pick(sub, acc.x, q.x, acc.y, q.y), coop_pick(sub, q.zz, acc.zz, q.zzz, acc.zzz));
+    F U1 = coop_bcast(t, 0, mask), S1 = coop_bcast(t, 2, mask), P, R;
+    u = coop_bcast(t, 1, mask);
+    F::sub(P, u, U1);
+    u = coop_bcast(t, 3, mask);
+    F::sub(R, u, S1);
+    if (F::is_zero(P))
+    {
+        if (F::is_zero(R))
+        {
+            XY c = acc;
+            XY::dbl(acc, c); // same point twice: rare, every lane doubles for itself
+            return;
+        }
+        XY::set_inf(acc);
+        return;
+    }
+    // level 2: PP = P^2 | RR = R^2 | ZZ = zz1 zz2 | ZZZ = zzz1 zzz2
+    F::mul(t, coop_pick(sub, P, R, acc.zz, acc.zzz), coop_pick(sub, P, R, q.zz, q.zzz));
+    F PP = coop_bcast(t, 0, mask), RR = coop_bcast(t, 1, mask);
+    // level 3: PPP = P PP | Q = U1 PP | zz3 = ZZ PP | (lane 3 keeps ZZZ, computes PPP as well)
+    F keep = t;
+    F::mul(t, coop_pick(sub, P, U1, keep, P), PP);
+    F PPP = coop_bcast(t, 0, mask), Q = coop_bcast(t, 1, mask);
+    F zz3 = coop_bcast(t, 2, mask);
+    F x3;
+    F::sub(x3, RR, PPP);
+    F::sub(x3, x3, Q);
+    F::sub(x3, x3, Q);
+    // level 4: B = S1 PPP | A = R (Q - x3) | - | zzz3 = ZZZ PPP
+    F::sub(u, Q, x3);
+    F::mul(t, coop_pick(sub, S1, R, S1, keep), coop_pick(sub, PPP, u, PPP, PPP));
+    F A = coop_bcast(t, 1, mask);
+    u   = coop_bcast(t, 0, mask);
+    acc.x = x3;
+    F::sub(acc.y, A, u);
+    acc.zz  = zz3;
+    acc.zzz = coop_bcast(t, 3, mask);
+}
+
+// p = 2 p (dbl-2008-s with a = 0, the same formulas as XyzzT::dbl) by the 4 lanes of a group
+template <class XY>
+__device__ __noinline__ void coop_dbl(XY& p, uint32_t sub)
+{
+    typedef typename XY::Field F;
+    if (XY::is_inf(p))
+        return;
+    const uint32_t mask = coop_mask();
+    F              U, t, u;
+    F::add(U, p.y, p.y);
+    // level 1: V = U^2 | XX = x^2
+    F::mul(t, coop_pick(sub, U, p.x, U, p.x), coop_pick(sub, U, p.x, U, p.x));
+    F V = coop_bcast(t, 0, mask), M = coop_bcast(t, 1, mask);
+    F::add(u, M, M);
+    F::add(M, M, u); // M = 3 x^2
+    // level 2: W = U V | S = x V | MM = M^2 | zz3 = V zz
+    F::mul(t, coop_pick(sub, U, p.x, M, V), coop_pick(sub, V, V, M, p.zz));
+    F W = coop_bcast(t, 0, mask), S = coop_bcast(t, 1, mask), x3 = coop_bcast(t, 2, mask), zz3 = coop_bcast(t, 3, mask);
+    F::sub(x3, x3, S);
+    F::sub(x3, x3, S);
+    // level 3: A = M (S - x3) | B = W y | zzz3 = W zzz
+    F::sub(u, S, x3);
+    F::mul(t, coop_pick(sub, M, W, W, W), coop_pick(sub, u, p.y, p.zzz, p.zzz));
+    F A = coop_bcast(t, 0, mask);
+    u   = coop_bcast(t, 1, mask);
+    p.x = x3;
+    F::sub(p.y, A, u);
+    p.zz  = zz3;
+    p.zzz = coop_bcast(t, 2, mask);
+}
+
+// sm[0..active) hold points (one per LOGICAL thread lt = threadIdx.x / kCoop, written by all four of its lanes);
+// result in sm[0]. Every thread of the block must call this.
+template <class XY>
+__device__ __forceinline__ void block_tree_sum(XY* sm, uint32_t active, uint32_t lt, uint32_t sub)
+{
     for (uint32_t stride = active >> 1; stride > 0; stride >>= 1)
     {
         __syncthreads();
-        if (tid < stride)
+        XY a;
+        if (lt < stride)
         {
-            XY a = sm[tid], b = sm[tid + stride];
-            cold_add(a, b);
-            sm[tid] = a;
+            a    = sm[lt];
+            XY b = sm[lt + stride];
+            coop_add(a, b, sub);
         }
+        __syncthreads(); // all lanes of a group have read before any of them writes the slot back
+        if (lt < stride && sub == 0)
+            sm[lt] = a;
     }
     __syncthreads();
 }
@@ -208,6 +329,7 @@ __global__ void __launch_bounds__(256)
     XY*                     sums    = args.heavy_sum[blockIdx.y];
     uint32_t*               done    = args.heavy_done[blockIdx.y];
     uint32_t                tid     = threadIdx.x;
+    const uint32_t          lt = tid / kCoop, sub = tid % kCoop, lthreads = blockDim.x / kCoop; // logical threads (coop_add)
     uint32_t                n       = min(*args.heavy_count, kMsmMaxHeavy);
     if (n == 0)
         return;
@@ -253,13 +375,14 @@ __global__ void __launch_bounds__(256)
         uint32_t  e   = min(s + per, cnt);
         XY        acc;
         XY::set_inf(acc);
-        for (uint32_t k = s + tid; k < e; k += blockDim.x)
+        for (uint32_t k = s + lt; k < e; k += lthreads)
         {
             XY q = rec[k];
-            cold_add(acc, q);
+            coop_add(acc, q, sub);
         }
-        sm[tid] = acc;
-        block_tree_sum(sm, blockDim.x, tid);
+        if (sub == 0)
+            sm[lt] = acc;
+        block_tree_sum(sm, lthreads, lt, sub);
         if (nsl == 1)
         {
             if (tid == 0)
@@ -278,14 +401,16 @@ __global__ void __launch_bounds__(256)
         if (s_last)
         {
             __threadfence();
-            if (tid < kMsmHeavyBlocks)
-            {
-                if (tid < nsl)
-                    sm[tid] = load_cg(partial + (size_t)h * kMsmHeavyBlocks + tid);
-                else
-                    XY::set_inf(sm[tid]);
-            }
-            block_tree_sum(sm, kMsmHeavyBlocks, tid);
+            // (a block has at least 16 logical threads; kMsmHeavyBlocks slots are filled in strides of that)
+            for (uint32_t k = lt; k < kMsmHeavyBlocks; k += lthreads)
+                if (sub == 0)
+                {
+                    if (k < nsl)
+                        sm[k] = load_cg(partial + (size_t)h * kMsmHeavyBlocks + k);
+                    else
+                        XY::set_inf(sm[k]);
+                }
+            block_tree_sum(sm, kMsmHeavyBlocks, lt, sub);
             if (tid == 0)
             {
                 sums[h] = sm[0];
@@ -305,7 +430,8 @@ __global__ void __launch_bounds__(kMsmFoldBlock)
 {
     const uint32_t* __restrict__ heavy_slot = args.heavy_slot;
     const XY* __restrict__       records    = args.records[blockIdx.y];
-    uint32_t                     b          = blockIdx.x * kMsmFoldBlock + threadIdx.x + 1;
+    const uint32_t               sub        = threadIdx.x % kCoop; // four lanes per bucket (coop_add)
+    uint32_t                     b          = blockIdx.x * (kMsmFoldBlock / kCoop) + threadIdx.x / kCoop + 1;
     uint32_t                     lo = offsets[b], hi = offsets[b + 1];
     XY                           acc;
     XY::set_inf(acc);
@@ -323,11 +449,12 @@ __global__ void __launch_bounds__(kMsmFoldBlock)
             for (uint32_t k = 1; k < cnt; k++)
             {
                 XY r = rec[k];
-                cold_add(acc, r);
+                coop_add(acc, r, sub);
             }
         }
     }
-    args.bsum[blockIdx.y][b - 1] = acc;
+    if (sub == 0)
+        args.bsum[blockIdx.y][b - 1] = acc;
 }
 
 // lane exchange of a whole point (for the shuffle trees below)
@@ -351,8 +478,11 @@ __device__ __forceinline__ XY shfl_xor_point(const XY& p, int mask)
 template <class XY>
 __global__ void __launch_bounds__(256) k_msm_plane_fold(MsmBatchArgs<XY> args)
 {
-    const XY* __restrict__ bs   = args.bsum[blockIdx.y] + (size_t)blockIdx.x * 1024;
-    const uint32_t         tid  = threadIdx.x;
+    // four lanes per logical thread (coop_add): a block is 64 of the plane's 256 logical threads, grid.x = 4 x planes
+    const uint32_t         plane = blockIdx.x >> 2;
+    const XY* __restrict__ bs    = args.bsum[blockIdx.y] + (size_t)plane * 1024;
+    const uint32_t         sub   = threadIdx.x % kCoop;
+    const uint32_t         tid   = (blockIdx.x & 3u) * 64u + threadIdx.x / kCoop; // logical thread of the plane
     if (tid < 128)
     {
         const uint32_t row = tid >> 2, part = tid & 3u;
@@ -362,16 +492,16 @@ __global__ void __launch_bounds__(256) k_msm_plane_fold(MsmBatchArgs<XY> args)
         for (uint32_t k = 1; k < 8; k++)
         {
             XY r = src[k];
-            cold_add(acc, r);
+            coop_add(acc, r, sub);
         }
 #pragma unroll 1
         for (int m = 1; m <= 2; m <<= 1)
         {
-            XY o = shfl_xor_point(acc, m);
-            cold_add(acc, o);
+            XY o = shfl_xor_point(acc, m * (int)kCoop); // the logical neighbour is kCoop lanes away
+            coop_add(acc, o, sub);
         }
-        if (part == 0)
-            args.s1part[blockIdx.y][(size_t)blockIdx.x * 32 + row] = acc;
+        if (part == 0 && sub == 0)
+            args.s1part[blockIdx.y][(size_t)plane * 32 + row] = acc;
     }
     else
     {
@@ -382,9 +512,10 @@ __global__ void __launch_bounds__(256) k_msm_plane_fold(MsmBatchArgs<XY> args)
         for (uint32_t k = 1; k < 8; k++)
         {
             XY r = src[k * 32];
-            cold_add(acc, r);
+            coop_add(acc, r, sub);
         }
-        args.s0part[blockIdx.y][((size_t)blockIdx.x * 4 + q4) * 32 + d0] = acc;
+        if (sub == 0)
+            args.s0part[blockIdx.y][((size_t)plane * 4 + q4) * 32 + d0] = acc;
     }
 }
 
@@ -402,25 +533,25 @@ __global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args, uint32
     const uint32_t          planes = nbuckets >> 10;
     const XY* __restrict__  s0     = args.s0part[blockIdx.y];
     const XY* __restrict__  s1     = args.s1part[blockIdx.y];
-    uint32_t                tid    = threadIdx.x;
+    const uint32_t          tid = threadIdx.x / kCoop, sub = threadIdx.x % kCoop, nthr = blockDim.x / kCoop; // logical threads
     uint32_t                l      = blockIdx.x >> 5;
     uint32_t                v      = blockIdx.x & 31;
     XY                      acc;
     XY::set_inf(acc);
     if (l == 0)
     {
-        for (uint32_t t = tid; t < planes * 4; t += blockDim.x)
+        for (uint32_t t = tid; t < planes * 4; t += nthr)
         {
             XY r = s0[(size_t)t * 32 + v];
-            cold_add(acc, r);
+            coop_add(acc, r, sub);
         }
     }
     else if (l == 1)
     {
-        for (uint32_t t = tid; t < planes; t += blockDim.x)
+        for (uint32_t t = tid; t < planes; t += nthr)
         {
             XY r = s1[(size_t)t * 32 + v];
-            cold_add(acc, r);
+            coop_add(acc, r, sub);
         }
     }
     else
@@ -430,25 +561,27 @@ __global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args, uint32
         uint32_t span  = 1u << shift; // consecutive planes sharing the digit
         uint32_t reps  = (planes + (span << 5) - 1) / (span << 5);
         uint32_t nterm = reps * span * 32;
-        for (uint32_t t = tid; t < nterm; t += blockDim.x)
+        for (uint32_t t = tid; t < nterm; t += nthr)
         {
             uint32_t row = t & 31u, q = t >> 5;
             uint32_t pl  = ((q >> shift) << (shift + 5)) | (v << shift) | (q & (span - 1));
             if (pl < planes)
             {
                 XY r = s1[(size_t)pl * 32 + row];
-                cold_add(acc, r);
+                coop_add(acc, r, sub);
             }
         }
     }
-    sm[tid] = acc;
-    block_tree_sum(sm, blockDim.x, tid);
+    if (sub == 0)
+        sm[tid] = acc;
+    block_tree_sum(sm, nthr, tid, sub);
     if (tid == 0)
     {
         XY r = sm[0];
         for (uint32_t k = 0; k < 5 * l; k++)
-            cold_dbl(r);
-        args.classes[blockIdx.y][blockIdx.x] = r;
+            coop_dbl(r, sub);
+        if (sub == 0)
+            args.classes[blockIdx.y][blockIdx.x] = r;
     }
 }
 
@@ -492,18 +625,19 @@ __global__ void __launch_bounds__(192) k_msm_final(MsmBatchArgs<XY> args, int le
         __syncwarp();
     }
     __syncthreads();
-    if (tid == 0)
+    if (tid < kCoop) // the Horner chain is sequential: the first four lanes run it as one logical thread
     {
         XY r = sm[4 * 32];
         for (int k = 3; k >= 0; k--)
         {
-            cold_dbl(r);
+            coop_dbl(r, tid);
             XY z = sm[k * 32];
-            cold_add(r, z);
+            coop_add(r, z, tid);
         }
         XY t = sm[5 * 32];
-        cold_add(r, t);
-        args.result[blockIdx.y][0] = r;
+        coop_add(r, t, tid);
+        if (tid == 0)
+            args.result[blockIdx.y][0] = r;
     }
 }
 
@@ -824,15 +958,17 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     // whole proof from 12.72 ms to 12.33 ms (B2 finishes later, in the shadow of the H MSM).
     constexpr bool is_g2   = sizeof(XY) == 256;
     static const bool wide = getenv("KZP_COLD_WIDE") && atoi(getenv("KZP_COLD_WIDE")) != 0; // A/B switch: old shapes
-    const uint32_t heavy_t = (is_g2 && !wide) ? 64 : 256, heavy_g = (is_g2 && !wide) ? 2 * kMsmHeavyGrid : kMsmHeavyGrid;
-    const uint32_t fold2_t = (is_g2 && !wide) ? 64 : 256;
+    // (four lanes per logical thread since the cooperative additions: KZP_COLD_G2_T threads per G2 CTA, default 128)
+    static const uint32_t g2_t = getenv("KZP_COLD_G2_T") ? (uint32_t)atoi(getenv("KZP_COLD_G2_T")) : 128u;
+    const uint32_t heavy_t = (is_g2 && !wide) ? g2_t : 256, heavy_g = (is_g2 && !wide) ? 2 * kMsmHeavyGrid : kMsmHeavyGrid;
+    const uint32_t fold2_t = (is_g2 && !wide) ? g2_t : 256;
     by.x = heavy_g;
     k_msm_heavy<XY><<<by, heavy_t, heavy_t * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
-    by.x = nbuckets / kMsmFoldBlock;
+    by.x = nbuckets / (kMsmFoldBlock / kCoop);
     k_msm_bucket_sums<XY><<<by, kMsmFoldBlock, 0, st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
-    by.x = nbuckets >> 10;
+    by.x = (nbuckets >> 10) * 4;
     k_msm_plane_fold<XY><<<by, 256, 0, st>>>(a);
     KZP_CUDA_CHECK(cudaGetLastError());
     by.x = 32 * sort.shape.levels;
@@ -860,6 +996,27 @@ void msm_last_accumulate(const MsmSort& sort, const MsmScratch<XY>& s, float* ms
         *entries = total;
 }
 
+// ops 3 / 4: the cooperative addition / doubling of the cold kernels, 4 lanes per point
+template <class XY>
+__global__ void __launch_bounds__(128)
+    k_point_op_coop(int op, const XY* __restrict__ p, const XY* __restrict__ q, XY* __restrict__ out, uint64_t n)
+{
+    uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, i = gid / kCoop;
+    uint32_t sub = (uint32_t)(gid % kCoop);
+    if (i >= n)
+        return;
+    XY acc = p[i];
+    if (op == 3)
+    {
+        XY b = q[i];
+        coop_add(acc, b, sub);
+    }
+    else
+        coop_dbl(acc, sub);
+    if (sub == 0)
+        out[i] = acc;
+}
+
 template <class XY>
 __global__ void __launch_bounds__(128)
     k_point_op(int op, const XY* __restrict__ p, const void* __restrict__ q, XY* __restrict__ out, uint64_t n)
@@ -885,6 +1042,12 @@ void point_op_t(int op, const void* p, const void* q, void* out, uint64_t count,
 {
     if (count == 0)
         return;
+    if (op == 3 || op == 4)
+    {
+        k_point_op_coop<XY><<<msm_div_up(count * kCoop, 128), 128, 0, st>>>(op, (const XY*)p, (const XY*)q, (XY*)out, count);
+        KZP_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     k_point_op<XY><<<msm_div_up(count, 128), 128, 0, st>>>(op, (const XY*)p, q, (XY*)out, count);
     KZP_CUDA_CHECK(cudaGetLastError());
 }

@@ -130,6 +130,17 @@ def test_g1_point_ops_with_exceptional_cases(gpu, kzp, oracle):
     out = kzp.point_op(0, 2, pb, None)
     got = [_g1_from_xyzz(o, out[i * 128:(i + 1) * 128]) for i in range(32)]
     assert got == [o.g1_add(p, p) for (p, _) in P]
+    # the four-lane cooperative addition / doubling of the bucket-reduction kernels: same group elements, same
+    # exceptional cases (37 points: the last group of lanes is ragged)
+    out = kzp.point_op(0, 3, pb, qx)
+    got = [_g1_from_xyzz(o, out[i * 128:(i + 1) * 128]) for i in range(32)]
+    assert got == [o.g1_add(p, q) for (p, _), q in zip(P, Q)]
+    out = kzp.point_op(0, 4, pb, None)
+    got = [_g1_from_xyzz(o, out[i * 128:(i + 1) * 128]) for i in range(32)]
+    assert got == [o.g1_add(p, p) for (p, _) in P]
+    out = kzp.point_op(0, 3, pb + pb[:5 * 128], qx + qx[:5 * 128])
+    got = [_g1_from_xyzz(o, out[i * 128:(i + 1) * 128]) for i in range(37)]
+    assert got == ([o.g1_add(p, q) for (p, _), q in zip(P, Q)] * 2)[:37]
 
 
 def test_g2_point_ops(gpu, kzp, oracle):
@@ -158,6 +169,10 @@ def test_g2_point_ops(gpu, kzp, oracle):
     out = kzp.point_op(1, 1, pb, b"".join(xyzz(q) for q in Q))
     assert [dec(out[i * 256:(i + 1) * 256]) for i in range(6)] == [o.g2_add(p, q) for p, q in zip(P, Q)]
     out = kzp.point_op(1, 2, pb, None)
+    assert [dec(out[i * 256:(i + 1) * 256]) for i in range(6)] == [o.g2_add(p, p) for p in P]
+    out = kzp.point_op(1, 3, pb, b"".join(xyzz(q) for q in Q))  # cooperative (four lanes per point)
+    assert [dec(out[i * 256:(i + 1) * 256]) for i in range(6)] == [o.g2_add(p, q) for p, q in zip(P, Q)]
+    out = kzp.point_op(1, 4, pb, None)
     assert [dec(out[i * 256:(i + 1) * 256]) for i in range(6)] == [o.g2_add(p, p) for p in P]
 
 
