@@ -156,6 +156,17 @@ def test_everything_refuses_without_gpu(kzp, oracle):
         kzp.field_op(0, 0, bytes(32), bytes(32))
     with pytest.raises(kzp.KzpError):
         kzp.imad_peak(16)
+    # the sharded prover (one proof over several GPUs) refuses the same way, through the explicit entry point and
+    # through $KZP_SHARD_DEVICES behind the reference-shaped constructor
+    with pytest.raises(kzp.ZKeyFileLoadError) as e:
+        kzp.FullProver(os.path.join(GOLDEN, "toy", "toy_1.zkey"), devices=[0, 1])
+    assert "no CPU fallback" in str(e.value)
+    os.environ["KZP_SHARD_DEVICES"] = "0,1"
+    try:
+        with pytest.raises(kzp.ZKeyFileLoadError):
+            kzp.FullProver(os.path.join(GOLDEN, "toy", "toy_1.zkey"))
+    finally:
+        del os.environ["KZP_SHARD_DEVICES"]
 
 
 def _partials_from_oracle(oracle, zk, w, lo_hi):
