@@ -182,7 +182,7 @@ int kzp_msm_run(kzp_msm* m, const uint8_t* scalars, uint8_t* out);
 int kzp_msm_bench(kzp_msm* m, const uint8_t* scalars, int iters, float* ms_per_msm, uint64_t* entries);
 
 /* field: 0 Fr, 1 Fq, 2 Fq2 (64-byte elements); op: 0 mul 1 add 2 sub 3 neg 4 toMontgomery 5 fromMontgomery
- * 6 square 7 inverse 8 a*b + b*b (dual product with one reduction, Fr / Fq only). Host buffers, `count` elements; b may be NULL for unary ops. */
+ * 6 square 7 inverse 8 a*b + b*b (dual product with one reduction per component). Host buffers, `count` elements; b may be NULL for unary ops. */
 int kzp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t count,
                  int device);
 /* group: 0 G1, 1 G2; op: 0 xyzz += affine, 1 xyzz += xyzz, 2 double, 3 / 4 the same addition / doubling as the

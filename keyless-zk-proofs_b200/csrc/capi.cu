@@ -827,7 +827,7 @@ int kzp_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t*
                  int device)
 {
     return guarded([&] {
-        if (field < 0 || field > 2 || op < 0 || op > 8 || (op == 8 && field == 2))
+        if (field < 0 || field > 2 || op < 0 || op > 8)
             throw FormatError("bad field/op");
         use_device(device);
         size_t esz = field == 2 ? 64 : 32;

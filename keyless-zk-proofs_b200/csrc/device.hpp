@@ -192,11 +192,11 @@ struct MsmScratch
     XY*       records       = nullptr; // cap_entries / chunk + buckets + 2 partial sums, grouped by bucket
     XY*       heavy_partial = nullptr; // kMsmMaxHeavy x kMsmHeavyBlocks
     XY*       heavy_sum     = nullptr; // kMsmMaxHeavy
-    uint32_t* heavy_done    = nullptr; // kMsmMaxHeavy arrival counters (self-resetting)
+    uint32_t* heavy_done    = nullptr; // arrival counters (self-resetting): kMsmMaxHeavy heavy buckets, then the fold classes + 1 (msm.cuh)
     XY*       bsum          = nullptr; // buckets : the sum of every bucket
     XY*       s0part        = nullptr; // (buckets / 1024) x 4 x 32 : per plane and quarter of digit 1, per digit 0
     XY*       s1part        = nullptr; // (buckets / 1024) x 32     : per plane, per digit 1 (sum over digit 0)
-    XY*       classes       = nullptr; // levels x 32 weighted class sums
+    XY*       classes       = nullptr; // levels x 32 weighted class sums, then their slice sums (msm.cuh: kMsmFoldPartOffset)
     XY*       result        = nullptr; // 1 (device)
     cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr; // bracket the bucket-accumulation kernel of the last run
 };

@@ -28,6 +28,8 @@ template <class F>
 __device__ __noinline__ void fp2_mul_ool(Fp2T<F>& r, const Fp2T<F>& x, const Fp2T<F>& y);
 template <class F>
 __device__ __noinline__ void fp2_sqr_ool(Fp2T<F>& r, const Fp2T<F>& x);
+template <class F>
+__device__ __noinline__ void fp2_mul_add2_ool(Fp2T<F>& r, const Fp2T<F>& x, const Fp2T<F>& y, const Fp2T<F>& z, const Fp2T<F>& w);
 #endif
 
 template <class F>
@@ -36,7 +38,9 @@ struct alignas(16) Fp2T
     F a; // real part
     F b; // coefficient of u
 
-    static constexpr bool kFusedMulAdd2 = false; // the group law keeps the two-product form over Fq2
+    // y3 = (Q - x3) R - y1 PPP as one dual product (mul_add2) over the device's base field; the host's 4 x 64-bit
+    // base field (hostff.hpp) keeps the two-product form
+    static constexpr bool kFusedMulAdd2 = F::kFusedMulAdd2;
 
     static KZP_HD Fp2T zero()
     {
@@ -92,8 +96,30 @@ struct alignas(16) Fp2T
 #endif
     }
     // (r may be x or y: every operand is read before the first write)
+    // Device: lazy reduction — the three Karatsuba products stay unreduced 512-bit integers, the additions and
+    // subtractions happen there (p^2 keeps the real part non-negative), and only the two results are reduced:
+    // 3 x 64 + 2 x 72 wide multiply-adds instead of 3 x 136. Results are canonical, i.e. the same bits.
     static KZP_HD void mul_body(Fp2T& r, const Fp2T& x, const Fp2T& y)
     {
+#if defined(__CUDA_ARCH__)
+        if constexpr (F::kFusedMulAdd2) // (the device's own base field; host-field instantiations take the plain form)
+        {
+        uint32_t Ta[16], Tb[16], Tc[16];
+        F        s1, s2;
+        F::add_raw(s1, x.a, x.b);
+        F::add_raw(s2, y.a, y.b);
+        F::mul_wide(Tc, s1, s2);
+        F::mul_wide(Ta, x.a, y.a);
+        F::mul_wide(Tb, x.b, y.b);
+        F::wide_sub(Tc, Ta);
+        F::wide_sub(Tc, Tb); // x.a y.b + x.b y.a < 2 p^2
+        F::template wide_add_psq<1>(Ta);
+        F::wide_sub(Ta, Tb); // x.a y.a - x.b y.b + p^2 in (0, 2 p^2)
+        F::redc_wide(r.a, Ta);
+        F::redc_wide(r.b, Tc);
+        return;
+        }
+#endif
         F aa, bb, s1, s2, t;
         F::mul(aa, x.a, y.a);
         F::mul(bb, x.b, y.b);
@@ -104,9 +130,66 @@ struct alignas(16) Fp2T
         F::sub(r.b, t, bb);
         F::sub(r.a, aa, bb);
     }
+    // r = x y + z w with one reduction per component (device: six wide products, two reductions)
+    static KZP_HD void mul_add2(Fp2T& r, const Fp2T& x, const Fp2T& y, const Fp2T& z, const Fp2T& w)
+    {
+#if defined(__CUDA_ARCH__)
+        if constexpr (F::kFusedMulAdd2)
+        {
+            fp2_mul_add2_ool<F>(r, x, y, z, w);
+            return;
+        }
+#endif
+        Fp2T t, u;
+        mul_body(t, x, y);
+        mul_body(u, z, w);
+        add(r, t, u);
+    }
+#if defined(__CUDA_ARCH__)
+    static KZP_D void mul_add2_body(Fp2T& r, const Fp2T& x, const Fp2T& y, const Fp2T& z, const Fp2T& w)
+    {
+        uint32_t Ta[16], Tc[16], U[16];
+        F        s1, s2;
+        F::add_raw(s1, x.a, x.b);
+        F::add_raw(s2, y.a, y.b);
+        F::mul_wide(Tc, s1, s2);
+        F::mul_wide(Ta, x.a, y.a);
+        F::mul_wide(U, x.b, y.b);
+        F::wide_sub(Tc, Ta);
+        F::wide_sub(Tc, U);
+        F::template wide_add_psq<2>(Ta);
+        F::wide_sub(Ta, U); // x.a y.a - x.b y.b + 2 p^2
+        F::add_raw(s1, z.a, z.b);
+        F::add_raw(s2, w.a, w.b);
+        F::mul_wide(U, s1, s2);
+        F::wide_add(Tc, U);
+        F::mul_wide(U, z.a, w.a);
+        F::wide_add(Ta, U);
+        F::wide_sub(Tc, U);
+        F::mul_wide(U, z.b, w.b);
+        F::wide_sub(Ta, U); // real part + 2 p^2, in (0, 4 p^2)
+        F::wide_sub(Tc, U); // imaginary part, in [0, 4 p^2)
+        F::redc_wide(r.a, Ta);
+        F::redc_wide(r.b, Tc);
+    }
+#endif
     // (a+bu)^2 = (a+b)(a-b) + 2ab u                            [f2field.cpp:144-175]
     static KZP_HD void sqr_body(Fp2T& r, const Fp2T& x)
     {
+#if defined(__CUDA_ARCH__)
+        if constexpr (F::kFusedMulAdd2)
+        {
+            // a + b and 2a stay unreduced (below 2p: the products stay inside the multiplier's input bound)
+            F s, d, a2, ra;
+            F::add_raw(s, x.a, x.b);
+            F::sub(d, x.a, x.b);
+            F::add_raw(a2, x.a, x.a);
+            F::mul(ra, s, d);
+            F::mul(r.b, a2, x.b);
+            r.a = ra;
+            return;
+        }
+#endif
         F s, d, ab;
         F::add(s, x.a, x.b);
         F::sub(d, x.a, x.b);
@@ -140,6 +223,11 @@ template <class F>
 __device__ __noinline__ void fp2_sqr_ool(Fp2T<F>& r, const Fp2T<F>& x)
 {
     Fp2T<F>::sqr_body(r, x);
+}
+template <class F>
+__device__ __noinline__ void fp2_mul_add2_ool(Fp2T<F>& r, const Fp2T<F>& x, const Fp2T<F>& y, const Fp2T<F>& z, const Fp2T<F>& w)
+{
+    Fp2T<F>::mul_add2_body(r, x, y, z, w);
 }
 #endif
 

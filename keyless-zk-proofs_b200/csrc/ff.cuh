@@ -833,6 +833,153 @@ struct alignas(16) Fp
 #endif
     }
 
+#if defined(__CUDA_ARCH__)
+    // ---- unreduced 512-bit products for the quadratic extension (lazy reduction: an Fq2 product is three wide
+    //      products and TWO reductions, 3 x 64 + 2 x 72 multiply-adds instead of 3 x 136)
+    // limb k (0..15) of p^2
+    static constexpr uint32_t psq_limb(int k)
+    {
+        const uint32_t m[8]    = {P::P0, P::P1, P::P2, P::P3, P::P4, P::P5, P::P6, P::P7};
+        uint32_t       out[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 8; i++)
+        {
+            uint64_t carry = 0;
+            for (int j = 0; j < 8; j++)
+            {
+                uint64_t t = (uint64_t)m[i] * m[j] + out[i + j] + carry;
+                out[i + j] = (uint32_t)t;
+                carry      = t >> 32;
+            }
+            out[i + 8] = (uint32_t)carry;
+        }
+        return out[k];
+    }
+    // r = a + b as a plain 256-bit integer (operands below 2^255: no carry out)
+    static KZP_D void add_raw(Fp& r, const Fp& a, const Fp& b)
+    {
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+            : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+              "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    }
+    // T (16 limbs) = a * b, the plain integer product (a, b < 2^256). Same even/odd accumulator walk as mul(), without
+    // the m * p rows: limb 0 of the running sum is final after each row and leaves through T[i]. 64 multiply-adds.
+    static KZP_D void mul_wide(uint32_t (&T)[16], const Fp& a, const Fp& b)
+    {
+        uint32_t x[8], y[8], pend = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            x[i] = 0;
+            y[i] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            uint32_t bi = b.v[i];
+            chain_odd_pend(x[0], pend, y, a.v[1], a.v[3], a.v[5], a.v[7], bi);
+            chain_even(x, y[7], a.v[0], a.v[2], a.v[4], a.v[6], bi);
+            T[i] = x[0];
+            pend = x[1];
+            uint32_t t0 = y[0], t1 = y[1], t2 = y[2], t3 = y[3], t4 = y[4], t5 = y[5], t6 = y[6], t7 = y[7];
+            y[0] = x[2]; y[1] = x[3]; y[2] = x[4]; y[3] = x[5]; y[4] = x[6]; y[5] = x[7];
+            y[6] = 0; y[7] = 0;
+            x[0] = t0; x[1] = t1; x[2] = t2; x[3] = t3; x[4] = t4; x[5] = t5; x[6] = t6; x[7] = t7;
+        }
+        // upper half = pend + X + (Y << 32) (the product is below 2^512: nothing beyond limb 7 of this sum)
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(T[8]), "=r"(T[9]), "=r"(T[10]), "=r"(T[11]), "=r"(T[12]), "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
+            : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(pend), "r"(y[0]),
+              "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]));
+    }
+    // T += U, T -= U (512-bit, no carry / borrow out by the callers' bounds)
+    static KZP_D void wide_add(uint32_t (&T)[16], const uint32_t (&U)[16])
+    {
+        asm("add.cc.u32 %0, %0, %16;\n\t"
+            "addc.cc.u32 %1, %1, %17;\n\t"
+            "addc.cc.u32 %2, %2, %18;\n\t"
+            "addc.cc.u32 %3, %3, %19;\n\t"
+            "addc.cc.u32 %4, %4, %20;\n\t"
+            "addc.cc.u32 %5, %5, %21;\n\t"
+            "addc.cc.u32 %6, %6, %22;\n\t"
+            "addc.cc.u32 %7, %7, %23;\n\t"
+            "addc.cc.u32 %8, %8, %24;\n\t"
+            "addc.cc.u32 %9, %9, %25;\n\t"
+            "addc.cc.u32 %10, %10, %26;\n\t"
+            "addc.cc.u32 %11, %11, %27;\n\t"
+            "addc.cc.u32 %12, %12, %28;\n\t"
+            "addc.cc.u32 %13, %13, %29;\n\t"
+            "addc.cc.u32 %14, %14, %30;\n\t"
+            "addc.u32 %15, %15, %31;"
+            : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(T[8]),
+              "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+            : "r"(U[0]), "r"(U[1]), "r"(U[2]), "r"(U[3]), "r"(U[4]), "r"(U[5]), "r"(U[6]), "r"(U[7]), "r"(U[8]), "r"(U[9]),
+              "r"(U[10]), "r"(U[11]), "r"(U[12]), "r"(U[13]), "r"(U[14]), "r"(U[15]));
+    }
+    static KZP_D void wide_sub(uint32_t (&T)[16], const uint32_t (&U)[16])
+    {
+        asm("sub.cc.u32 %0, %0, %16;\n\t"
+            "subc.cc.u32 %1, %1, %17;\n\t"
+            "subc.cc.u32 %2, %2, %18;\n\t"
+            "subc.cc.u32 %3, %3, %19;\n\t"
+            "subc.cc.u32 %4, %4, %20;\n\t"
+            "subc.cc.u32 %5, %5, %21;\n\t"
+            "subc.cc.u32 %6, %6, %22;\n\t"
+            "subc.cc.u32 %7, %7, %23;\n\t"
+            "subc.cc.u32 %8, %8, %24;\n\t"
+            "subc.cc.u32 %9, %9, %25;\n\t"
+            "subc.cc.u32 %10, %10, %26;\n\t"
+            "subc.cc.u32 %11, %11, %27;\n\t"
+            "subc.cc.u32 %12, %12, %28;\n\t"
+            "subc.cc.u32 %13, %13, %29;\n\t"
+            "subc.cc.u32 %14, %14, %30;\n\t"
+            "subc.u32 %15, %15, %31;"
+            : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(T[8]),
+              "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+            : "r"(U[0]), "r"(U[1]), "r"(U[2]), "r"(U[3]), "r"(U[4]), "r"(U[5]), "r"(U[6]), "r"(U[7]), "r"(U[8]), "r"(U[9]),
+              "r"(U[10]), "r"(U[11]), "r"(U[12]), "r"(U[13]), "r"(U[14]), "r"(U[15]));
+    }
+    // T += K p^2 (K = 1 or 2): keeps a difference of products non-negative without changing its residue
+    template <int K>
+    static KZP_D void wide_add_psq(uint32_t (&T)[16])
+    {
+        uint32_t U[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            U[i] = K == 1 ? psq_limb(i) : ((psq_limb(i) << 1) | (i ? (psq_limb(i - 1) >> 31) : 0u));
+        wide_add(T, U);
+    }
+    // r = T R^-1 mod p, canonical, for T < 4 p^2 (< p R for both BN254 fields: the quotient is below 2p)
+    static KZP_D void redc_wide(Fp& r, const uint32_t (&T)[16])
+    {
+        uint32_t x[8], y[8], pend = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            x[i] = T[i];
+            y[i] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            redc_round(x, y, pend, T[8 + i]);
+        merge_reduce(r, x, y, pend);
+    }
+#endif
+
     // canonical integer -> Montgomery (Fr_rawToMontgomery: fr_raw_generic.cpp:192-196)
     static KZP_HD void to_mont(Fp& r, const Fp& a)
     {

@@ -247,6 +247,16 @@ __device__ __noinline__ void coop_dbl(XY& p, uint32_t sub)
     p.zzz = coop_bcast(t, 2, mask);
 }
 
+// one addition by a logical thread of LANES lanes: 4 = cooperative (latency), 1 = a lane on its own (throughput)
+template <class XY, int LANES>
+__device__ __forceinline__ void group_add(XY& acc, const XY& q, uint32_t sub)
+{
+    if constexpr (LANES == 1)
+        cold_add(acc, q);
+    else
+        coop_add(acc, q, sub);
+}
+
 // sm[0..active) hold points (one per LOGICAL thread lt = threadIdx.x / kCoop, written by all four of its lanes);
 // result in sm[0]. Every thread of the block must call this.
 template <class XY>
@@ -422,16 +432,19 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- bucket sums ----------------------------------------------------------------------------------------
-// Thread = bucket: sum its records (or take the heavy sum) and store the bucket's point. Every lane does the same
-// kind of work (a bucket of a uniform scalar vector spans one or two chunks). grid = (buckets / 128, batch).
-template <class XY>
+// Logical thread = bucket: sum its records (or take the heavy sum) and store the bucket's point. Every lane does the
+// same kind of work (a bucket of a uniform scalar vector spans one or two chunks). LANES lanes per bucket: four
+// (cooperative additions) when the MSM is small and the kernel is a latency chain, one when there are enough buckets
+// to fill the chip (the replicated additions, subtractions and shuffles of the cooperative form then cost throughput:
+// 2^19 buckets take 0.26 ms with four lanes, 0.16 ms with one). grid = (buckets * LANES / 128, batch).
+template <class XY, int LANES>
 __global__ void __launch_bounds__(kMsmFoldBlock)
     k_msm_bucket_sums(const uint32_t* __restrict__ offsets, MsmBatchArgs<XY> args, uint32_t chunk)
 {
     const uint32_t* __restrict__ heavy_slot = args.heavy_slot;
     const XY* __restrict__       records    = args.records[blockIdx.y];
-    const uint32_t               sub        = threadIdx.x % kCoop; // four lanes per bucket (coop_add)
-    uint32_t                     b          = blockIdx.x * (kMsmFoldBlock / kCoop) + threadIdx.x / kCoop + 1;
+    const uint32_t               sub        = threadIdx.x % LANES;
+    uint32_t                     b          = blockIdx.x * (kMsmFoldBlock / LANES) + threadIdx.x / LANES + 1;
     uint32_t                     lo = offsets[b], hi = offsets[b + 1];
     XY                           acc;
     XY::set_inf(acc);
@@ -449,7 +462,7 @@ __global__ void __launch_bounds__(kMsmFoldBlock)
             for (uint32_t k = 1; k < cnt; k++)
             {
                 XY r = rec[k];
-                coop_add(acc, r, sub);
+                group_add<XY, LANES>(acc, r, sub);
             }
         }
     }
@@ -475,14 +488,15 @@ __device__ __forceinline__ XY shfl_xor_point(const XY& p, int mask)
 // row sum s1part[plane][d1] (sum over d0; feeds digit classes 1 and up). Threads 128..255 = (quarter of d1, d0):
 // 8 buckets 32 apart -> s0q[plane][quarter][d0] (partial sums over d1; feed the digit-0 classes). All lanes run the
 // same 7 sequential additions: no idle lanes as in a per-warp tree over 32 buckets. grid = (buckets / 1024, batch).
-template <class XY>
+template <class XY, int LANES>
 __global__ void __launch_bounds__(256) k_msm_plane_fold(MsmBatchArgs<XY> args)
 {
-    // four lanes per logical thread (coop_add): a block is 64 of the plane's 256 logical threads, grid.x = 4 x planes
-    const uint32_t         plane = blockIdx.x >> 2;
+    // LANES lanes per logical thread (see k_msm_bucket_sums): a block is 256 / LANES of the plane's 256 logical
+    // threads, grid.x = LANES x planes
+    const uint32_t         plane = blockIdx.x / LANES;
     const XY* __restrict__ bs    = args.bsum[blockIdx.y] + (size_t)plane * 1024;
-    const uint32_t         sub   = threadIdx.x % kCoop;
-    const uint32_t         tid   = (blockIdx.x & 3u) * 64u + threadIdx.x / kCoop; // logical thread of the plane
+    const uint32_t         sub   = threadIdx.x % LANES;
+    const uint32_t         tid   = (blockIdx.x % LANES) * (256u / LANES) + threadIdx.x / LANES; // logical thread of the plane
     if (tid < 128)
     {
         const uint32_t row = tid >> 2, part = tid & 3u;
@@ -492,13 +506,13 @@ __global__ void __launch_bounds__(256) k_msm_plane_fold(MsmBatchArgs<XY> args)
         for (uint32_t k = 1; k < 8; k++)
         {
             XY r = src[k];
-            coop_add(acc, r, sub);
+            group_add<XY, LANES>(acc, r, sub);
         }
 #pragma unroll 1
         for (int m = 1; m <= 2; m <<= 1)
         {
-            XY o = shfl_xor_point(acc, m * (int)kCoop); // the logical neighbour is kCoop lanes away
-            coop_add(acc, o, sub);
+            XY o = shfl_xor_point(acc, m * LANES); // the logical neighbour is LANES lanes away
+            group_add<XY, LANES>(acc, o, sub);
         }
         if (part == 0 && sub == 0)
             args.s1part[blockIdx.y][(size_t)plane * 32 + row] = acc;
@@ -512,7 +526,7 @@ __global__ void __launch_bounds__(256) k_msm_plane_fold(MsmBatchArgs<XY> args)
         for (uint32_t k = 1; k < 8; k++)
         {
             XY r = src[k * 32];
-            coop_add(acc, r, sub);
+            group_add<XY, LANES>(acc, r, sub);
         }
         if (sub == 0)
             args.s0part[blockIdx.y][((size_t)plane * 4 + q4) * 32 + d0] = acc;
@@ -520,27 +534,39 @@ __global__ void __launch_bounds__(256) k_msm_plane_fold(MsmBatchArgs<XY> args)
 }
 
 // ---- second fold: the levels x 32 class sums ---------------------------------------------------------------
-// Block (l, v) sums every partial of the buckets whose base-32 digit l equals v and scales it by 32^l.
+// Class (l, v) is the sum of every partial of the buckets whose base-32 digit l equals v, scaled by 32^l:
 //   l = 0: s0part[plane][quarter][v] over all planes and quarters
 //   l = 1: s1part[plane][v] over all planes
 //   l >= 2: digit l of the index is digit l - 2 of the plane number: all 32 rows of the matching planes
-// grid = (32 * levels, batch).
+// The kernel is a latency chain (sequential point additions on a handful of SMs), so with many buckets every class is
+// cut into `slices` <= kMsmFoldSlices slices, one block each: a block adds up its share of the terms, and the last slice
+// of a class to arrive (arrival counter) adds the slice sums and applies the 5 l doublings. The grid must stay one wave
+// (measured: 512 blocks of 256 threads are two waves and gain nothing over 128 unsliced blocks; 512 x 128 threads fit).
+// grid = (32 * levels * slices, batch).
+constexpr uint32_t kMsmFoldSlices = 4;
+// layout of the `classes` scratch: [0, 32 L) class sums, then 32 L x slices slice sums (reused by k_msm_final for its
+// six partial results); of `heavy_done` beyond the heavy buckets: 32 L class counters + 1 for k_msm_final
+constexpr uint32_t kMsmFoldPartOffset = 32 * kMsmMaxLevels;
+constexpr uint32_t kMsmFoldDoneOffset = kMsmMaxHeavy;
+
 template <class XY>
-__global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args, uint32_t nbuckets)
+__global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args, uint32_t nbuckets, uint32_t slices)
 {
     extern __shared__ uint4 smem_raw[];
+    __shared__ uint32_t     s_last;
     XY*                     sm     = reinterpret_cast<XY*>(smem_raw);
     const uint32_t          planes = nbuckets >> 10;
     const XY* __restrict__  s0     = args.s0part[blockIdx.y];
     const XY* __restrict__  s1     = args.s1part[blockIdx.y];
     const uint32_t          tid = threadIdx.x / kCoop, sub = threadIdx.x % kCoop, nthr = blockDim.x / kCoop; // logical threads
-    uint32_t                l      = blockIdx.x >> 5;
-    uint32_t                v      = blockIdx.x & 31;
+    const uint32_t          cls = blockIdx.x / slices, slice = blockIdx.x % slices;
+    const uint32_t          l = cls >> 5, v = cls & 31;
+    const uint32_t          first = slice * nthr + tid, step = nthr * slices;
     XY                      acc;
     XY::set_inf(acc);
     if (l == 0)
     {
-        for (uint32_t t = tid; t < planes * 4; t += nthr)
+        for (uint32_t t = first; t < planes * 4; t += step)
         {
             XY r = s0[(size_t)t * 32 + v];
             coop_add(acc, r, sub);
@@ -548,7 +574,7 @@ __global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args, uint32
     }
     else if (l == 1)
     {
-        for (uint32_t t = tid; t < planes; t += nthr)
+        for (uint32_t t = first; t < planes; t += step)
         {
             XY r = s1[(size_t)t * 32 + v];
             coop_add(acc, r, sub);
@@ -561,7 +587,7 @@ __global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args, uint32
         uint32_t span  = 1u << shift; // consecutive planes sharing the digit
         uint32_t reps  = (planes + (span << 5) - 1) / (span << 5);
         uint32_t nterm = reps * span * 32;
-        for (uint32_t t = tid; t < nterm; t += nthr)
+        for (uint32_t t = first; t < nterm; t += step)
         {
             uint32_t row = t & 31u, q = t >> 5;
             uint32_t pl  = ((q >> shift) << (shift + 5)) | (v << shift) | (q & (span - 1));
@@ -575,69 +601,97 @@ __global__ void __launch_bounds__(256) k_msm_fold2(MsmBatchArgs<XY> args, uint32
     if (sub == 0)
         sm[tid] = acc;
     block_tree_sum(sm, nthr, tid, sub);
-    if (tid == 0)
+    XY*       part = args.classes[blockIdx.y] + kMsmFoldPartOffset + (size_t)cls * kMsmFoldSlices;
+    uint32_t* done = args.heavy_done[blockIdx.y] + kMsmFoldDoneOffset + cls;
+    if (threadIdx.x == 0)
     {
-        XY r = sm[0];
+        part[slice] = sm[0];
+        __threadfence();
+        uint32_t ticket = atomicAdd(done, 1u);
+        s_last          = (ticket == slices - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    if (tid == 0) // the first four lanes, as one logical thread
+    {
+        XY r = load_cg(part);
+        for (uint32_t k = 1; k < slices; k++)
+        {
+            XY q = load_cg(part + k);
+            coop_add(r, q, sub);
+        }
         for (uint32_t k = 0; k < 5 * l; k++)
             coop_dbl(r, sub);
         if (sub == 0)
-            args.classes[blockIdx.y][blockIdx.x] = r;
+        {
+            args.classes[blockIdx.y][cls] = r;
+            *done                         = 0;
+        }
     }
 }
 
 // ---- final combination -----------------------------------------------------------------------------------
 // result = T + sum_v v * E[v], E[v] = sum_l classes[l][v] (already scaled), T = sum_v classes[0][v].
-// Warps 0..4 build Z_k = sum of E[v] over v with bit k set, warp 5 builds T, thread 0 runs Horner over k.
-// grid = (1, batch), 192 threads.
+// Block k < 5 builds Z_k = sum of E[v] over v with bit k set, block 5 builds T: 32 logical threads of four lanes
+// (cooperative additions), a tree over the 32 values; the last block to arrive runs Horner over k on its first four
+// lanes. 3 + 5 + 9 sequential cooperative operations. grid = (6, batch), 128 threads.
 template <class XY>
-__global__ void __launch_bounds__(192) k_msm_final(MsmBatchArgs<XY> args, int levels)
+__global__ void __launch_bounds__(128) k_msm_final(MsmBatchArgs<XY> args, int levels)
 {
     extern __shared__ uint4 smem_raw[];
+    __shared__ uint32_t     s_last;
     XY*                     sm  = reinterpret_cast<XY*>(smem_raw);
     const XY* __restrict__  cls = args.classes[blockIdx.y];
-    uint32_t                tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    XY                      e   = cls[lane];
+    const uint32_t          v = threadIdx.x / kCoop, sub = threadIdx.x % kCoop, w = blockIdx.x;
+    XY                      e   = cls[v];
     if (w < 5)
     {
-        if ((lane >> w) & 1u)
+        if ((v >> w) & 1u)
         {
 #pragma unroll 1
             for (int l = 1; l < levels; l++)
             {
-                XY u = cls[32 * l + lane];
-                cold_add(e, u);
+                XY u = cls[32 * l + v];
+                coop_add(e, u, sub);
             }
         }
         else
             XY::set_inf(e);
     }
-    sm[tid] = e;
-    __syncwarp();
-#pragma unroll 1
-    for (uint32_t stride = 16; stride > 0; stride >>= 1)
+    if (sub == 0)
+        sm[v] = e;
+    block_tree_sum(sm, 32, v, sub);
+    XY*       part = args.classes[blockIdx.y] + kMsmFoldPartOffset; // (the slice sums of k_msm_fold2 are spent)
+    uint32_t* done = args.heavy_done[blockIdx.y] + kMsmFoldDoneOffset + 32 * kMsmMaxLevels;
+    if (threadIdx.x == 0)
     {
-        if (lane < stride)
-        {
-            XY a = sm[tid], c = sm[tid + stride];
-            cold_add(a, c);
-            sm[tid] = a;
-        }
-        __syncwarp();
+        part[w] = sm[0];
+        __threadfence();
+        uint32_t ticket = atomicAdd(done, 1u);
+        s_last          = (ticket == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (tid < kCoop) // the Horner chain is sequential: the first four lanes run it as one logical thread
+    if (!s_last)
+        return;
+    __threadfence();
+    if (v == 0)
     {
-        XY r = sm[4 * 32];
+        XY r = load_cg(part + 4);
         for (int k = 3; k >= 0; k--)
         {
-            coop_dbl(r, tid);
-            XY z = sm[k * 32];
-            coop_add(r, z, tid);
+            coop_dbl(r, sub);
+            XY z = load_cg(part + k);
+            coop_add(r, z, sub);
         }
-        XY t = sm[5 * 32];
-        coop_add(r, t, tid);
-        if (tid == 0)
+        XY t = load_cg(part + 5);
+        coop_add(r, t, sub);
+        if (sub == 0)
+        {
             args.result[blockIdx.y][0] = r;
+            *done                      = 0;
+        }
     }
 }
 
@@ -820,7 +874,7 @@ static void msm_set_smem_attrs()
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_fold2<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(256 * sizeof(XY))));
     KZP_CUDA_CHECK(cudaFuncSetAttribute(k_msm_final<XY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(192 * sizeof(XY))));
+                                        (int)(32 * sizeof(XY))));
 }
 
 template <class XY>
@@ -836,13 +890,15 @@ void msm_scratch_create(MsmScratch<XY>& s, const MsmSort& sort, uint32_t chunk)
     KZP_CUDA_CHECK(cudaMalloc(&s.records, ((size_t)sort.cap_entries / s.chunk + nb + 1) * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_partial, (size_t)kMsmMaxHeavy * kMsmHeavyBlocks * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.heavy_sum, (size_t)kMsmMaxHeavy * sizeof(XY)));
-    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_done, (size_t)kMsmMaxHeavy * 4));
-    KZP_CUDA_CHECK(cudaMemset(s.heavy_done, 0, (size_t)kMsmMaxHeavy * 4));
+    // (arrival counters, all self-resetting: heavy buckets, then the classes of k_msm_fold2, then k_msm_final's)
+    const size_t n_done = (size_t)kMsmFoldDoneOffset + 32 * kMsmMaxLevels + 1;
+    KZP_CUDA_CHECK(cudaMalloc(&s.heavy_done, n_done * 4));
+    KZP_CUDA_CHECK(cudaMemset(s.heavy_done, 0, n_done * 4));
     size_t planes = s.shape.buckets >> 10;
     KZP_CUDA_CHECK(cudaMalloc(&s.bsum, (size_t)s.shape.buckets * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.s0part, planes * 4 * 32 * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.s1part, planes * 32 * sizeof(XY)));
-    KZP_CUDA_CHECK(cudaMalloc(&s.classes, (size_t)kMsmMaxLevels * 32 * sizeof(XY)));
+    KZP_CUDA_CHECK(cudaMalloc(&s.classes, (size_t)kMsmMaxLevels * 32 * (1 + kMsmFoldSlices) * sizeof(XY)));
     KZP_CUDA_CHECK(cudaMalloc(&s.result, sizeof(XY)));
     KZP_CUDA_CHECK(cudaEventCreate(&s.ev_acc0));
     KZP_CUDA_CHECK(cudaEventCreate(&s.ev_acc1));
@@ -943,6 +999,13 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
             by.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 6>());
             k_msm_accumulate<XY, 6><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
         }
+        else if constexpr (sizeof(XY) == 256)
+        {
+            // G2: capped at 168 registers so that three CTAs stay resident per SM (uncapped, the lazy-reduction Fq2
+            // products raise the kernel to 197 registers: two CTAs)
+            by.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 3>());
+            k_msm_accumulate<XY, 3><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
+        }
         else
         {
             by.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 1>());
@@ -965,17 +1028,35 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     by.x = heavy_g;
     k_msm_heavy<XY><<<by, heavy_t, heavy_t * sizeof(XY), st>>>(sort.offsets, a, chunk);
     KZP_CUDA_CHECK(cudaGetLastError());
-    by.x = nbuckets / (kMsmFoldBlock / kCoop);
-    k_msm_bucket_sums<XY><<<by, kMsmFoldBlock, 0, st>>>(sort.offsets, a, chunk);
+    // bucket sums and the plane fold: cooperative additions (four lanes per logical thread) while the MSM is too
+    // small to fill the chip with one lane per bucket, plain ones from KZP_FOLD_COOP_MAX buckets per batch on
+    static const uint32_t coop_max = getenv("KZP_FOLD_COOP_MAX") ? (uint32_t)atoi(getenv("KZP_FOLD_COOP_MAX")) : (1u << 17);
+    if ((uint64_t)nbuckets * (unsigned int)nb < coop_max)
+    {
+        by.x = nbuckets / (kMsmFoldBlock / kCoop);
+        k_msm_bucket_sums<XY, (int)kCoop><<<by, kMsmFoldBlock, 0, st>>>(sort.offsets, a, chunk);
+        KZP_CUDA_CHECK(cudaGetLastError());
+        by.x = (nbuckets >> 10) * kCoop;
+        k_msm_plane_fold<XY, (int)kCoop><<<by, 256, 0, st>>>(a);
+    }
+    else
+    {
+        by.x = nbuckets / kMsmFoldBlock;
+        k_msm_bucket_sums<XY, 1><<<by, kMsmFoldBlock, 0, st>>>(sort.offsets, a, chunk);
+        KZP_CUDA_CHECK(cudaGetLastError());
+        by.x = nbuckets >> 10;
+        k_msm_plane_fold<XY, 1><<<by, 256, 0, st>>>(a);
+    }
     KZP_CUDA_CHECK(cudaGetLastError());
-    by.x = (nbuckets >> 10) * 4;
-    k_msm_plane_fold<XY><<<by, 256, 0, st>>>(a);
+    // (sliced classes from 2^18 buckets on: the H MSM; 128-thread blocks then, so that the grid stays one wave)
+    static const uint32_t slices_env = getenv("KZP_FOLD_SLICES") ? (uint32_t)atoi(getenv("KZP_FOLD_SLICES")) : 0u;
+    const uint32_t slices  = slices_env ? std::min(slices_env, kMsmFoldSlices) : (nbuckets >= (1u << 18) ? kMsmFoldSlices : 1u);
+    const uint32_t fold2_b = slices > 1 ? std::min(fold2_t, 128u) : fold2_t;
+    by.x = 32 * sort.shape.levels * slices;
+    k_msm_fold2<XY><<<by, fold2_b, fold2_b * sizeof(XY), st>>>(a, nbuckets, slices);
     KZP_CUDA_CHECK(cudaGetLastError());
-    by.x = 32 * sort.shape.levels;
-    k_msm_fold2<XY><<<by, fold2_t, fold2_t * sizeof(XY), st>>>(a, nbuckets);
-    KZP_CUDA_CHECK(cudaGetLastError());
-    by.x = 1;
-    k_msm_final<XY><<<by, 192, 192 * sizeof(XY), st>>>(a, (int)sort.shape.levels);
+    by.x = 6;
+    k_msm_final<XY><<<by, 128, 32 * sizeof(XY), st>>>(a, (int)sort.shape.levels);
     KZP_CUDA_CHECK(cudaGetLastError());
 }
 

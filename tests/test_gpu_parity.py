@@ -75,6 +75,13 @@ def test_fq2_ops(gpu, kzp, oracle):
     a[0], b[0] = (2, 2), (3, 3)  # f2_simpleMul, RS/alt_bn128_test.cpp:12-29
     a[1] = (0, 0)
     b[2] = (0, 5)
+    # extremes of the device's lazy reduction (unreduced 512-bit Karatsuba terms, p^2 added to the real part)
+    m = o.Q_MOD - 1
+    a[3], b[3] = (m, m), (m, m)
+    a[4], b[4] = (0, m), (0, m)      # real part = -(p-1)^2: the most negative difference
+    a[5], b[5] = (m, 0), (m, 0)
+    a[6], b[6] = (m, m), (0, 0)
+    a[7], b[7] = (1, m), (m, 1)
     enc = lambda xs: b"".join(o.le32(o.to_mont(x[0], o.Q_MOD)) + o.le32(o.to_mont(x[1], o.Q_MOD)) for x in xs)
     dec = lambda blob: [(o.from_mont(o.from_le(blob[i:i + 32]), o.Q_MOD), o.from_mont(o.from_le(blob[i + 32:i + 64]), o.Q_MOD))
                         for i in range(0, len(blob), 64)]
@@ -85,6 +92,8 @@ def test_fq2_ops(gpu, kzp, oracle):
     assert dec(kzp.field_op(2, 2, A, B)) == [o.f2_sub(x, y) for x, y in zip(a, b)]
     assert dec(kzp.field_op(2, 3, A, None)) == [o.f2_neg(x) for x in a]
     assert dec(kzp.field_op(2, 6, A, None)) == [o.f2_sqr(x) for x in a]
+    # x y + y y as one dual product (six wide products, two reductions on the device)
+    assert dec(kzp.field_op(2, 8, A, B)) == [o.f2_add(o.f2_mul(x, y), o.f2_mul(y, y)) for x, y in zip(a, b)]
     got = dec(kzp.field_op(2, 7, A[:64 * 32], None))
     assert got == [o.f2_inv(x) if x != (0, 0) else (0, 0) for x in a[:32]]
 
