@@ -48,30 +48,38 @@ struct MsmBatchArgs
 // t + bucket: the map (t, bucket) -> t + bucket is injective and monotone over the pairs that occur, and
 // the records of bucket b are exactly slots [lo/L + b, (hi-1)/L + b] for its range [lo, hi). Work per
 // thread is therefore independent of the digit distribution (a bit-heavy witness puts ~half of all
-// entries in bucket 1). blockIdx.y selects the MSM of the batch (same sort, different base table).
+// entries in bucket 1). The MSMs of a batch (same sort, different base tables) share ONE ticket counter: ticket k is
+// the (k / nb)-th run of 32 chunks of MSM k % nb. (With one counter and one grid slice per MSM, the warps of the
+// first slice raced for a third of the tickets, the losers exited, and every CTA stayed resident with one or two
+// live warps until those finished — three under-filled phases, 1.2 ms for the A/B1/C batch instead of 0.75.)
 template <class XY, int MINB>
 __global__ void __launch_bounds__(128, MINB)
     k_msm_accumulate(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ sorted,
-                     MsmBatchArgs<XY> args, uint32_t chunk, uint32_t n, uint32_t nbuckets)
+                     MsmBatchArgs<XY> args, uint32_t chunk, uint32_t n, uint32_t nbuckets, uint32_t nb)
 {
     typedef typename XY::Affine Affine;
     typedef typename XY::Field  F;
-    const Affine* __restrict__  table   = args.table[blockIdx.y];
-    const uint8_t* __restrict__ skip    = args.skip[blockIdx.y];
-    XY* __restrict__            records = args.records[blockIdx.y];
-    uint32_t*                   ticket  = args.work_counter + blockIdx.y;
+    uint32_t*                   ticket  = args.work_counter;
     const uint32_t              total   = offsets[nbuckets + 1];
     const uint32_t              lane    = threadIdx.x & 31;
+    const uint32_t              runs    = ((total + chunk - 1) / chunk + 31) / 32; // runs of 32 chunks per MSM
     // The grid is sized to what is resident at once; warps take 32 consecutive chunks at a time from a ticket
-    // counter until the sorted list is used up, so no SM idles through the tail of a last partial wave.
+    // counter until the sorted lists are used up, so no SM idles through the tail of a last partial wave.
     for (;;)
     {
-        uint32_t first = 0;
+        uint32_t k = 0;
         if (lane == 0)
-            first = atomicAdd(ticket, 32u);
-        first = __shfl_sync(0xffffffffu, first, 0);
-        if ((uint64_t)first * chunk >= total)
+            k = atomicAdd(ticket, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= runs * nb)
             return;
+        const uint32_t y     = k % nb;
+        const uint32_t first = (k / nb) * 32;
+        // (selects, not an indexed read of the parameter arrays: those would be copied to local memory)
+        static_assert(kMsmMaxBatch == 3, "the selects below name the batch members");
+        const Affine* __restrict__  table   = y == 0 ? args.table[0] : (y == 1 ? args.table[1] : args.table[2]);
+        const uint8_t* __restrict__ skip    = y == 0 ? args.skip[0] : (y == 1 ? args.skip[1] : args.skip[2]);
+        XY* __restrict__            records = y == 0 ? args.records[0] : (y == 1 ? args.records[1] : args.records[2]);
         uint32_t t       = first + lane;
         uint64_t start64 = (uint64_t)t * chunk;
         if (start64 >= total)
@@ -986,30 +994,32 @@ void msm_reduce_batch(const MsmSort& sort, const MsmBases<XY>* const* bases, Msm
     KZP_CUDA_CHECK(cudaEventRecord(scr[0]->ev_acc0, st));
     if (sort.n > 0)
     {
-        uint64_t threads = ((uint64_t)sort.cap_entries + chunk - 1) / chunk;
+        // one grid for the whole batch (the MSMs share the ticket counter), sized to what is resident at once
+        uint64_t threads = (((uint64_t)sort.cap_entries + chunk - 1) / chunk) * (uint64_t)nb;
+        dim3     ga(1, 1, 1);
         // resident CTAs per SM the kernel is compiled for (register cap): KZP_ACC_OCC = 4 | 5 | 6 (G1 only)
         static const int occ = getenv("KZP_ACC_OCC") ? atoi(getenv("KZP_ACC_OCC")) : 4;
         if (sizeof(XY) == 128 && occ == 5)
         {
-            by.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 5>());
-            k_msm_accumulate<XY, 5><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
+            ga.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 5>());
+            k_msm_accumulate<XY, 5><<<ga, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets, (uint32_t)nb);
         }
         else if (sizeof(XY) == 128 && occ == 6)
         {
-            by.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 6>());
-            k_msm_accumulate<XY, 6><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
+            ga.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 6>());
+            k_msm_accumulate<XY, 6><<<ga, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets, (uint32_t)nb);
         }
         else if constexpr (sizeof(XY) == 256)
         {
             // G2: capped at 168 registers so that three CTAs stay resident per SM (uncapped, the lazy-reduction Fq2
             // products raise the kernel to 197 registers: two CTAs)
-            by.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 3>());
-            k_msm_accumulate<XY, 3><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
+            ga.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 3>());
+            k_msm_accumulate<XY, 3><<<ga, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets, (uint32_t)nb);
         }
         else
         {
-            by.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 1>());
-            k_msm_accumulate<XY, 1><<<by, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets);
+            ga.x = std::min(msm_div_up(threads, 128), msm_resident_blocks<XY, 1>());
+            k_msm_accumulate<XY, 1><<<ga, 128, 0, st>>>(sort.offsets, sort.sorted, a, chunk, sort.n, nbuckets, (uint32_t)nb);
         }
         KZP_CUDA_CHECK(cudaGetLastError());
     }
