@@ -309,8 +309,10 @@ def _scalars(o, rnd, n, mix):
 
 
 # (window bits, two-level sort): the default one-level sort with 16-bit windows (witness MSMs), the same windows
-# through the two-level sort, and the wide windows of the H MSM (c = 20: 13 table windows, 2^19 buckets)
-MSM_SHAPES = [(0, False), (16, True), (17, False), (20, False), (22, False)]
+# through the two-level sort, and the wide windows of the H MSM (c = 20: 13 table windows, 2^19 buckets). Between them the
+# shapes cover every variant of the bucket reduction: cooperative / one-lane bucket sums (from 2^17 buckets), whole / sliced
+# class sums (from 2^18 buckets)
+MSM_SHAPES = [(0, False), (16, True), (17, False), (18, False), (20, False), (22, False)]
 
 
 @pytest.mark.parametrize("shape", MSM_SHAPES, ids=lambda s: "c%d%s" % (s[0], "t" if s[1] else ""))
