@@ -409,3 +409,97 @@ def test_witness_packing_round_trip(kzp, oracle):
         assert all(((flags[i >> 3] >> (i & 7)) & 1) == 0 for i in range(count, pad_end))
     with pytest.raises(kzp.KzpError):
         kzp.host_pack_witness_slice(bytes(32 * 32769))
+
+
+def _mutated_zkeys(base: bytes, rnd, count):
+    """Seeded corruptions of a zkey image: bit flips, extreme header fields, truncations, extensions."""
+    head = min(len(base), 1200)  # container header, section 1 and 2, start of the IC section
+    for it in range(count):
+        blob = bytearray(base)
+        kind = it % 6
+        if kind == 0:    # a few bit flips in the headers
+            for _ in range(rnd.randrange(1, 4)):
+                blob[rnd.randrange(head)] ^= 1 << rnd.randrange(8)
+        elif kind == 1:  # an extreme 32-bit value at a 4-byte aligned header position
+            pos = 4 * rnd.randrange(head // 4 - 1)
+            blob[pos:pos + 4] = rnd.choice([0, 1, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF, 0xFFFFFFFE]).to_bytes(4, "little")
+        elif kind == 2:  # an extreme 64-bit section size somewhere in the section table walk
+            pos = rnd.randrange(8, head - 8)
+            blob[pos:pos + 8] = rnd.choice([0, 0xFFFFFFFFFFFFFFFF, 0x8000000000000000, len(base), len(base) + 1]).to_bytes(8, "little")
+        elif kind == 3:  # truncation
+            blob = blob[:rnd.randrange(0, len(base))]
+        elif kind == 4:  # random bytes anywhere
+            for _ in range(rnd.randrange(1, 16)):
+                blob[rnd.randrange(len(blob))] = rnd.randrange(256)
+        else:            # trailing garbage
+            blob += bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 64)))
+        yield bytes(blob)
+
+
+def test_file_parsers_survive_mutated_inputs(kzp, workdir):
+    """Seeded fuzz of the bounds-checked loaders (csrc/binfile.hpp; the reference asserts instead,
+    binfile_utils.cpp:21,143): corrupted copies of the reference's toy zkey and of the generated 256-wire zkey go
+    through kzp_host_parse_zkey and kzp_host_verify (which also walks the IC section). Every outcome must be an error
+    code or a verdict — never a crash — and an accepted header must describe sections that really fit in the file."""
+    L = kzp.lib()
+    nv, npub, dom, nc, st = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64(), ctypes.c_int()
+    args = (ctypes.byref(nv), ctypes.byref(npub), ctypes.byref(dom), ctypes.byref(nc), ctypes.byref(st))
+    rnd = random.Random(20261018)
+    path = os.path.join(workdir, "fuzz.zkey")
+    n_ok = n_err = 0
+    for name, zkey in (("toy", "toy_1.zkey"), ("syn256", "syn256.zkey")):
+        d = os.path.join(GOLDEN, name)
+        base = open(os.path.join(d, zkey), "rb").read()
+        exp = json.load(open(os.path.join(d, "expected.json")))
+        pub = b"".join(int(v).to_bytes(32, "little") for v in exp["public"])
+        for it, blob in enumerate(_mutated_zkeys(base, rnd, 300)):
+            open(path, "wb").write(blob)
+            rc = L.kzp_host_parse_zkey(path.encode(), *args)
+            assert rc in (0, 2, 3), (name, it, rc)
+            if rc == 0:
+                n_ok += 1
+                assert st.value == 0 and dom.value & (dom.value - 1) == 0 and npub.value + 1 <= nv.value
+                # the sections an accepted header promises fit in the file
+                assert 64 * 2 * nv.value + 128 * nv.value + 64 * dom.value + 44 * nc.value <= len(blob)
+            else:
+                n_err += 1
+                assert st.value in (1, 2)
+            res = ctypes.c_int(-1)
+            rc = L.kzp_host_verify(path.encode(), exp["proof"].encode(), pub, len(exp["public"]), ctypes.byref(res))
+            assert rc in (0, 2, 3) and (rc != 0 or res.value in (0, 1)), (name, it, rc, res.value)
+    assert n_ok > 50 and n_err > 50, (n_ok, n_err)  # both sides of the parser were exercised
+
+
+def test_loaders_and_verifier_clean_under_sanitizers(kzp, workdir):
+    """The same corrupted files through csrc/verify.cpp (binfile.hpp loaders + IC walk + pairing.hpp) rebuilt with
+    -fsanitize=address,undefined: no out-of-bounds read, no undefined shift or overflow in the 4x64-bit host field
+    code, and the instrumented build gives the same return codes and verdicts as the shipped library."""
+    exe = os.path.join(workdir, "verify_fuzz")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined",
+                           "-fno-sanitize-recover=undefined",
+                           os.path.join(ROOT, "keyless-zk-proofs_b200", "csrc", "verify.cpp"),
+                           os.path.join(ROOT, "tests", "harness", "verify_fuzz_main.cpp"), "-o", exe])
+    L = kzp.lib()
+    rnd = random.Random(7)
+    for name, zkey in (("toy", "toy_1.zkey"), ("syn256", "syn256.zkey")):
+        d = os.path.join(GOLDEN, name)
+        exp = json.load(open(os.path.join(d, "expected.json")))
+        pub = b"".join(int(v).to_bytes(32, "little") for v in exp["public"])
+        proof_path, pub_path = os.path.join(workdir, "san_proof.json"), os.path.join(workdir, "san_pub.bin")
+        open(proof_path, "w").write(exp["proof"])
+        open(pub_path, "wb").write(pub)
+        files = [os.path.join(d, zkey)]
+        for it, blob in enumerate(_mutated_zkeys(open(files[0], "rb").read(), rnd, 120)):
+            files.append(os.path.join(workdir, "san_%s_%d.zkey" % (name, it)))
+            open(files[-1], "wb").write(blob)
+        r = subprocess.run([exe, proof_path, pub_path] + files, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "Sanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
+        lines = r.stdout.split("\n")
+        assert lines[0] == "0 1"  # the intact key accepts the reference's recorded proof
+        for f, line in zip(files, lines):
+            res = ctypes.c_int(-1)
+            rc = L.kzp_host_verify(f.encode(), exp["proof"].encode(), pub, len(exp["public"]), ctypes.byref(res))
+            assert line == "%d %d" % (rc, res.value if rc == 0 else 0) or (rc != 0 and line.split()[0] == str(rc)), (f, line, rc)
+        assert "pairing 0 1" in lines and "pairing 2 -1" in lines
+        for f in files[1:]:
+            os.unlink(f)
