@@ -79,8 +79,25 @@ void log_line(const char* level, const char* msg)
 {
     if (!getenv("KZP_LOG"))
         return;
+    // the message may quote a path or a CUDA error string: keep the line valid JSON
+    char   esc[512];
+    size_t k = 0;
+    for (const char* p = msg ? msg : ""; *p && k + 7 < sizeof esc; p++)
+    {
+        unsigned char c = (unsigned char)*p;
+        if (c == '"' || c == '\\')
+        {
+            esc[k++] = '\\';
+            esc[k++] = (char)c;
+        }
+        else if (c < 0x20)
+            k += (size_t)snprintf(esc + k, 7, "\\u%04x", c);
+        else
+            esc[k++] = (char)c;
+    }
+    esc[k] = 0;
     printf("{\"level\":\"%s\",\"message\":\"%s\",\"native_code\":\"1\",\"target\":\"prover_service::rapidsnark\"}\n",
-           level, msg);
+           level, esc);
     fflush(stdout);
 }
 } // namespace

@@ -1600,7 +1600,12 @@ public:
     {
         const int                       n = world();
         std::vector<std::exception_ptr> err(n);
-        std::atomic<int>                failed{0};
+        // failed[s]: some shard threw while launching stage s. A thread looks only at the flags of stages that ended
+        // before the barrier it has just left — those are final, so every thread takes the same decision and nobody is
+        // left waiting at the next barrier for a thread that has already given up.
+        std::atomic<int> failed[4];
+        for (auto& f : failed)
+            f.store(0);
         crew->run([&](int r) {
             try
             {
@@ -1617,13 +1622,16 @@ public:
             catch (...)
             {
                 err[r] = std::current_exception();
-                failed.store(1);
+                failed[0].store(1);
             }
             // every barrier: the events the next stage waits on have been recorded by all shards for this proof
             for (int stage = 1; stage <= (links.dist_ntt ? 3 : 1); stage++)
             {
                 crew->barrier();
-                if (failed.load())
+                bool give_up = false;
+                for (int done = 0; done < stage; done++)
+                    give_up = give_up || failed[done].load() != 0;
+                if (give_up)
                     return;
                 try
                 {
@@ -1638,8 +1646,9 @@ public:
                 }
                 catch (...)
                 {
-                    err[r] = std::current_exception();
-                    failed.store(1);
+                    if (!err[r])
+                        err[r] = std::current_exception();
+                    failed[stage].store(1);
                 }
             }
         });
