@@ -493,7 +493,9 @@ inline auto witness_reader_fd(int fd, uint64_t file_offset)
         while (len > 0)
         {
             ssize_t got = ::pread(fd, dst, len, off);
-            if (got <= 0)
+            if (got < 0 && errno == EINTR)
+                continue;
+            if (got <= 0) // error, or the file is shorter than its section table says
                 return nullptr;
             dst += got;
             off += got;

@@ -57,7 +57,13 @@ def main():
             elif re.search(r"\bLDL(\.|\b)", line):
                 spills[cur][1] += 1
     names = demangle(sorted(rows))
+    import hashlib
+
+    body = "\n".join(l for l in sass.split("\n") if l and not l.startswith("Fatbin") and "identifier" not in l)
+    sass_md5 = hashlib.md5((body + "\n").encode()).hexdigest()
     print("# kernels of keyless-zk-proofs_b200/libkzp_b200.so (sm_100a), library stamp %s" % open(STAMP).read().strip())
+    print("# md5 of the SASS of all kernels (cuobjdump -sass without the Fatbin / identifier lines): %s" % sass_md5)
+    print("#   -- equal digests = identical device code; host-only changes move the stamp but not this")
     print("# regs = registers per thread; stack = bytes of per-thread stack (spills + local arrays); STL/LDL = local-memory")
     print("# store / load instructions in the kernel's SASS (static counts); smem = static shared memory per CTA (dynamic")
     print("# shared memory of the NTT / sort kernels is set at launch); instr = SASS instructions")
