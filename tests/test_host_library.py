@@ -518,3 +518,59 @@ def test_pool_under_thread_sanitizer(workdir):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (r.stdout, r.stderr[-3000:])
     assert "healthy 4 total 640" in r.stdout and "failures 0" in r.stdout
+
+
+def test_shipped_binary_is_sm100a_with_copy_engine_staged_ntt(kzp):
+    """Static properties of the shipped libkzp_b200.so, read with cuobjdump (no GPU): every cubin with code is sm_100a;
+    the NTT level kernels fetch their tiles with tensor copies (UTMALDG) and the fused middle level with a bulk copy
+    (UBLKCP), both completed through an mbarrier (SYNCS.ARRIVE / SYNCS.PHASECHK) — north_star's "TMA-staged" NTT;
+    the field arithmetic is on the wide integer multiply-add (IMAD.WIDE); the accumulate kernels keep their register
+    budgets (G1 <= 128: four CTAs of 128 threads per SM; G2 <= 168: three)."""
+    import shutil
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run(["cuobjdump", "--list-elf", kzp.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"\.(sm_\w+)\.cubin", elf))
+    res = subprocess.run(["cuobjdump", "--dump-resource-usage", kzp.LIB_PATH], capture_output=True, text=True).stdout
+    regs, arch_of, arch = {}, {}, None
+    fn = None
+    for line in res.split("\n"):
+        m = re.match(r"\s*arch = (sm_\w+)", line)
+        if m:
+            arch = m.group(1)
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            fn = m.group(1)
+            arch_of[fn] = arch
+        m = re.match(r"\s*REG:(\d+)", line)
+        if m and fn:
+            regs[fn] = int(m.group(1))
+            fn = None
+    assert regs and set(arch_of.values()) == {"sm_100a"}, (archs, set(arch_of.values()))
+    sass = subprocess.run(["cuobjdump", "-sass", kzp.LIB_PATH], capture_output=True, text=True).stdout
+    ops, cur = {}, None
+    for line in sass.split("\n"):
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            ops[cur] = {}
+            continue
+        if cur:
+            for k in ("UTMALDG", "UBLKCP", "SYNCS.ARRIVE", "SYNCS.PHASECHK", "IMAD.WIDE"):
+                if k in line:
+                    ops[cur][k] = ops[cur].get(k, 0) + 1
+    tma = [f for f in ops if "k_ntt_level_tma" in f]
+    mid = [f for f in ops if "k_ntt_mid" in f]
+    assert len(tma) == 4 and len(mid) == 2
+    for f in tma:
+        assert ops[f].get("UTMALDG", 0) >= 1 and ops[f].get("SYNCS.ARRIVE", 0) >= 1 and ops[f].get("SYNCS.PHASECHK", 0) >= 1, (f, ops[f])
+    for f in mid:
+        assert ops[f].get("UBLKCP", 0) >= 1 and ops[f].get("SYNCS.PHASECHK", 0) >= 1, (f, ops[f])
+    for f in tma + mid:
+        assert ops[f]["IMAD.WIDE"] > 3000  # the butterflies' Montgomery products
+    acc = {f: r for f, r in regs.items() if "k_msm_accumulate" in f}
+    assert acc
+    for f, r in acc.items():
+        g2 = "Fp2T" in f
+        assert r <= (168 if g2 else 128), (f, r)
