@@ -150,8 +150,8 @@ int main()
                not_ready.load(), kzp_pool_healthy(pool), (unsigned long long)total, (unsigned long long)maxw);
         // one proof per faulting prover was lost, both slots retired, every request was answered; a proof that fails
         // the check AFTER its prover has faulted under the next caller is NOT_READY as well (documented: the device
-        // is suspected before the witness), so not_ready may exceed 2 by a few
-        if (not_ready < 2 || not_ready > 6 || g_verify_calls != 638 || kzp_pool_healthy(pool) != 4 || total != 640 ||
+        // is suspected before the witness), so not_ready may exceed 2 — by at most the 4 proofs each faulting prover served before
+        if (not_ready < 2 || not_ready > 10 || g_verify_calls != 638 || kzp_pool_healthy(pool) != 4 || total != 640 ||
             ok + rejected + not_ready != 640 || ok < 318)
             failures++;
         kzp_pool_free(pool);
