@@ -411,6 +411,18 @@ def test_witness_packing_round_trip(kzp, oracle):
         kzp.host_pack_witness_slice(bytes(32 * 32769))
 
 
+def _require_sanitizer(flag, workdir):
+    """Skips when this machine cannot build or run a trivial program under the sanitizer (missing runtime, or a kernel
+    whose address-space layout the runtime refuses): the tests below are about OUR code, not about the toolchain."""
+    src = os.path.join(workdir, "san_probe.cpp")
+    exe = os.path.join(workdir, "san_probe")
+    open(src, "w").write("#include <thread>\nint x; int main() { std::thread t([] { x = 1; }); t.join(); return x - 1; }\n")
+    ok = subprocess.run(["g++", "-std=c++17", flag, src, "-o", exe, "-lpthread"], capture_output=True).returncode == 0
+    ok = ok and subprocess.run([exe], capture_output=True, timeout=60).returncode == 0
+    if not ok:
+        pytest.skip("g++ %s does not work on this machine" % flag)
+
+
 def _mutated_zkeys(base: bytes, rnd, count):
     """Seeded corruptions of a zkey image: bit flips, extreme header fields, truncations, extensions."""
     head = min(len(base), 1200)  # container header, section 1 and 2, start of the IC section
@@ -474,6 +486,7 @@ def test_loaders_and_verifier_clean_under_sanitizers(kzp, workdir):
     """The same corrupted files through csrc/verify.cpp (binfile.hpp loaders + IC walk + pairing.hpp) rebuilt with
     -fsanitize=address,undefined: no out-of-bounds read, no undefined shift or overflow in the 4x64-bit host field
     code, and the instrumented build gives the same return codes and verdicts as the shipped library."""
+    _require_sanitizer("-fsanitize=address,undefined", workdir)
     exe = os.path.join(workdir, "verify_fuzz")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined",
                            "-fno-sanitize-recover=undefined",
@@ -511,6 +524,7 @@ def test_pool_under_thread_sanitizer(workdir):
     threads x 40 requests over 6 provers of which two fault, then five rounds of freeing a pool with 10 callers queued
     behind 2 busy provers. No data race, no two callers inside one prover, no prover freed under a caller, every
     request answered with the documented code."""
+    _require_sanitizer("-fsanitize=thread", workdir)
     exe = os.path.join(workdir, "pool_tsan")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread",
                            os.path.join(ROOT, "keyless-zk-proofs_b200", "csrc", "pool.cpp"),
