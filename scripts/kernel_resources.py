@@ -42,16 +42,19 @@ def main():
             fn = None
     # spill traffic: STL / LDL instruction counts per kernel in the SASS
     sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
-    spills, total, cur = {}, {}, None
+    spills, total, wide, cur = {}, {}, {}, None
     for line in sass.split("\n"):
         m = re.match(r"\s*Function : (\S+)", line)
         if m:
             cur = m.group(1)
             spills[cur] = [0, 0]
             total[cur] = 0
+            wide[cur] = 0
             continue
         if cur and re.search(r"/\*[0-9a-f]{4,}\*/\s+\S", line):
             total[cur] += 1
+            if "IMAD.WIDE" in line:
+                wide[cur] += 1
             if re.search(r"\bSTL(\.|\b)", line):
                 spills[cur][0] += 1
             elif re.search(r"\bLDL(\.|\b)", line):
@@ -66,12 +69,16 @@ def main():
     print("#   -- equal digests = identical device code; host-only changes move the stamp but not this")
     print("# regs = registers per thread; stack = bytes of per-thread stack (spills + local arrays); STL/LDL = local-memory")
     print("# store / load instructions in the kernel's SASS (static counts); smem = static shared memory per CTA (dynamic")
-    print("# shared memory of the NTT / sort kernels is set at launch); instr = SASS instructions")
-    print("%-78s %5s %6s %6s %5s %5s %7s" % ("kernel", "regs", "stack", "smem", "STL", "LDL", "instr"))
+    print("# shared memory of the NTT / sort kernels is set at launch); instr = SASS instructions, wide = IMAD.WIDE among them")
+    print("# (static mix: a loop body counts once however often it runs, and the out-of-line Fq2 routines of the G2 kernels")
+    print("#  count once however often they are called)")
+    print("%-78s %5s %6s %6s %5s %5s %7s %6s %5s" % ("kernel", "regs", "stack", "smem", "STL", "LDL", "instr", "wide", "share"))
     for mangled in sorted(rows, key=lambda k: short(names[k])):
         reg, stack, shared, local = rows[mangled]
         stl, ldl = spills.get(mangled, [0, 0])
-        print("%-78s %5d %6d %6d %5d %5d %7d" % (short(names[mangled])[:78], reg, stack, shared, stl, ldl, total.get(mangled, 0)))
+        n_i, n_w = total.get(mangled, 0), wide.get(mangled, 0)
+        print("%-78s %5d %6d %6d %5d %5d %7d %6d %4.0f%%" % (short(names[mangled])[:78], reg, stack, shared, stl, ldl, n_i, n_w,
+                                                             100.0 * n_w / max(n_i, 1)))
 
 
 if __name__ == "__main__":
